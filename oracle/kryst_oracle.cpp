@@ -1,0 +1,804 @@
+// kryst_oracle.cpp — CPU ORACLE for the kryst Krylov hot path.
+//
+// TEST INFRASTRUCTURE ONLY.  This file is the *checker*, never the product:
+// only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
+// legs may load it.  Nothing under kryst_b200/ links, imports or calls it.
+//
+// It restates, in plain C++ (no FMA contraction: build with -ffp-contract=off),
+// the algorithms of tmathis720/kryst 0.5.3 that lie on the north-star path.
+// Each function cites the reference file:line it follows (paths relative to
+// /root/reference).  The reference is pure Rust and no Rust toolchain exists in
+// this image, so the reference itself cannot be compiled or run here (see
+// DESIGN.md "Oracle"); the restatement is pinned against every known-answer
+// test the reference holds for this path (tests/test_oracle_golden.py).
+//
+// Parity tiers:
+//   Tier L (literal)  : SpMV, dot/norm, Jacobi, PCG, GMRES (mode None/Left/Right,
+//                       MGS + 2nd pass), BiCGStab (unpreconditioned, absolute tol),
+//                       Convergence::check, dense literal Ilu0 (ilu.rs, as-is).
+//   Tier T (textbook) : ILU(0) on the CSR pattern, level sets, triangular solves,
+//                       CGS2 GMRES (None/Left/Right), Jacobi right-preconditioned
+//                       BiCGStab, partition / ghost maps, block-Jacobi ILU(0).
+//                       PARITY UNPINNED by the reference for Tier T: the reference
+//                       has no working code/tests for these (SURVEY §0 F4-F7,F11);
+//                       the oracle is the specification, cross-checked in tests
+//                       against independent dense/scipy computations.
+//
+// Reductions: the reference's Rayon reduce has a non-deterministic tree
+// (src/core/wrappers.rs:90-128), so *any* fixed tree is a faithful restatement.
+// The oracle fixes one canonical tree ("R", below) which the CUDA kernels follow
+// exactly, so GPU results are bit-identical to the oracle, not merely close.
+#include <cmath>
+#include <cstdint>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+#include <algorithm>
+#include <limits>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+typedef uint64_t u64;
+typedef int64_t i64;
+
+extern "C" {
+
+// ----------------------------------------------------------------------------
+// status codes == KError discriminants (src/error.rs:6-19) as used by the C ABI
+// ----------------------------------------------------------------------------
+enum { KO_OK = 0, KO_FACTOR_ERROR = 1, KO_SOLVE_ERROR = 2, KO_INDEFINITE_MATRIX = 3,
+       KO_INDEFINITE_PC = 4, KO_ZERO_PIVOT = 5, KO_UNSUPPORTED = 6 };
+
+typedef struct {
+    u64 iterations;        // SolveStats.iterations      (src/utils/convergence.rs:9-14)
+    double final_residual; // SolveStats.final_residual
+    int32_t converged;     // SolveStats.converged
+    int32_t breakdown;     // 0 none; >0: which breakdown `break` fired (BiCGStab), Tier-T status
+} ko_stats;
+
+typedef struct {
+    u64 n, ncols;
+    const u64* row_ptr;
+    const u64* col_idx;
+    const double* vals;
+} ko_csr;
+
+int ko_num_threads(void) {
+#ifdef _OPENMP
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+}
+void ko_set_num_threads(int t) {
+#ifdef _OPENMP
+    omp_set_num_threads(t);
+#else
+    (void)t;
+#endif
+}
+
+// ----------------------------------------------------------------------------
+// Canonical reduction tree R (shared, bit-for-bit, with the CUDA kernels)
+//   level 1: tiles of 512 elements; lane l in [0,256) holds e(2l) + e(2l+1)
+//            (missing elements are +0.0); 32-lane halving butterflies
+//            (offsets 16,8,4,2,1), then the 8 warp sums added sequentially.
+//   level 2: over the P = ceil(n/512) tile sums u: lane l = 0.0 + u[l] + u[l+256] + ...
+//            (ascending), same butterfly + sequential warp sum.
+//   shards : sum over ranks r = 0..p-1 of R(local_r), sequential in rank order.
+// ----------------------------------------------------------------------------
+static inline double lanes256_reduce(double* a) {
+    double ws[8];
+    for (int w = 0; w < 8; ++w) {
+        double* v = a + 32 * w;
+        for (int off = 16; off >= 1; off >>= 1)
+            for (int l = 0; l < off; ++l) v[l] = v[l] + v[l + off];
+        ws[w] = v[0];
+    }
+    double s = ws[0];
+    for (int w = 1; w < 8; ++w) s = s + ws[w];
+    return s;
+}
+
+static double level2_reduce(const double* u, u64 P) {
+    double a[256];
+    for (int l = 0; l < 256; ++l) {
+        double acc = 0.0;
+        for (u64 k = (u64)l; k < P; k += 256) acc = acc + u[k];
+        a[l] = acc;
+    }
+    return lanes256_reduce(a);
+}
+
+// tile sum of products x[i]*y[i] for tile t (y may alias x)
+static inline double tile_dot(const double* x, const double* y, u64 n, u64 t) {
+    double a[256];
+    u64 base = t * 512;
+    if (base + 512 <= n) {
+        for (int l = 0; l < 256; ++l) {
+            double e0 = x[base + 2 * l] * y[base + 2 * l];
+            double e1 = x[base + 2 * l + 1] * y[base + 2 * l + 1];
+            a[l] = e0 + e1;
+        }
+    } else {
+        for (int l = 0; l < 256; ++l) {
+            u64 i0 = base + 2 * l, i1 = i0 + 1;
+            double e0 = (i0 < n) ? x[i0] * y[i0] : 0.0;
+            double e1 = (i1 < n) ? x[i1] * y[i1] : 0.0;
+            a[l] = e0 + e1;
+        }
+    }
+    return lanes256_reduce(a);
+}
+
+static double dot_local(const double* x, const double* y, u64 n) {
+    u64 P = (n + 511) / 512;
+    if (P == 0) return level2_reduce(nullptr, 0);
+    std::vector<double> u(P);
+#pragma omp parallel for schedule(static) if (P > 64)
+    for (i64 t = 0; t < (i64)P; ++t) u[t] = tile_dot(x, y, n, (u64)t);
+    return level2_reduce(u.data(), P);
+}
+
+// reference partition formula: src/preconditioner/asm.rs:46-57
+void ko_partition_range(u64 n, u64 p, u64 r, u64* lo, u64* hi) {
+    u64 chunk = (n + p - 1) / p;
+    u64 s = r * chunk, e = (r + 1) * chunk;
+    if (s > n) s = n;
+    if (e > n) e = n;
+    *lo = s; *hi = e;
+}
+
+// dot: value parity with src/core/wrappers.rs:90-108 (sum x_i*y_i)
+double ko_dot_sharded(u64 n, const double* x, const double* y, u64 nshards) {
+    if (nshards <= 1) return dot_local(x, y, n);
+    double s = 0.0;
+    for (u64 r = 0; r < nshards; ++r) {
+        u64 lo, hi; ko_partition_range(n, nshards, r, &lo, &hi);
+        double loc = dot_local(x + lo, y + lo, hi - lo);
+        s = (r == 0) ? loc : s + loc;
+    }
+    return s;
+}
+double ko_dot(u64 n, const double* x, const double* y) { return dot_local(x, y, n); }
+// norm: src/core/wrappers.rs:110-128 (sqrt of sum x_i^2)
+double ko_norm(u64 n, const double* x) { return std::sqrt(dot_local(x, x, n)); }
+// canonical sum of an arbitrary vector (used by tests of the tree itself)
+double ko_sum(u64 n, const double* v) {
+    std::vector<double> one(n, 1.0);
+    return dot_local(v, one.data(), n);
+}
+
+// ----------------------------------------------------------------------------
+// SpMV — literal row sum, ascending stored order, separate mul and add
+// (src/core/wrappers.rs:31-36 restricted to the stored entries; equals the
+//  dense loop bit-for-bit for finite inputs because skipped terms are +0.0*x)
+// ----------------------------------------------------------------------------
+void ko_spmv(const ko_csr* A, const double* x, double* y) {
+    const u64 n = A->n;
+#pragma omp parallel for schedule(static)
+    for (i64 i = 0; i < (i64)n; ++i) {
+        double s = 0.0;
+        for (u64 p = A->row_ptr[i]; p < A->row_ptr[i + 1]; ++p)
+            s = s + A->vals[p] * x[A->col_idx[p]];
+        y[i] = s;
+    }
+}
+
+// CSR validation in the spirit of faer's SymbolicSparseRowMat::new_checked
+// (call site src/matrix/sparse.rs:36-44): monotone row_ptr, in-range, strictly
+// ascending columns per row.  Returns 0 if valid, else 1 + first bad row.
+u64 ko_csr_validate(const ko_csr* A) {
+    if (A->row_ptr[0] != 0) return 1;
+    for (u64 i = 0; i < A->n; ++i) {
+        if (A->row_ptr[i + 1] < A->row_ptr[i]) return 1 + i;
+        for (u64 p = A->row_ptr[i]; p < A->row_ptr[i + 1]; ++p) {
+            if (A->col_idx[p] >= A->ncols) return 1 + i;
+            if (p > A->row_ptr[i] && A->col_idx[p] <= A->col_idx[p - 1]) return 1 + i;
+        }
+    }
+    return 0;
+}
+
+// ----------------------------------------------------------------------------
+// Jacobi — src/preconditioner/jacobi.rs:69-71 (setup rule), :84-86 (apply)
+// (the reference extracts a_ii by n unit-vector mat-vecs, :58-67; the value is
+//  the stored diagonal entry, or 0 when none is stored)
+// ----------------------------------------------------------------------------
+void ko_jacobi_setup(const ko_csr* A, double* inv_diag) {
+#pragma omp parallel for schedule(static)
+    for (i64 i = 0; i < (i64)A->n; ++i) {
+        double d = 0.0;
+        for (u64 p = A->row_ptr[i]; p < A->row_ptr[i + 1]; ++p)
+            if (A->col_idx[p] == (u64)i) d = d + A->vals[p];
+        inv_diag[i] = (d != 0.0) ? 1.0 / d : 0.0;
+    }
+}
+void ko_jacobi_apply(u64 n, const double* inv_diag, const double* r, double* z) {
+#pragma omp parallel for schedule(static)
+    for (i64 i = 0; i < (i64)n; ++i) z[i] = inv_diag[i] * r[i];
+}
+
+// ----------------------------------------------------------------------------
+// ILU(0), Tier T — Saad Alg. 10.4 (IKJ) on the sorted CSR pattern
+//   lu      : copy of A's values, factored in place (unit-lower L strict part, U incl. diag)
+//   diag_ptr: position of the diagonal entry of each row
+// returns KO_OK, KO_FACTOR_ERROR (row without stored diagonal; *bad_row set) or
+//         KO_ZERO_PIVOT (*bad_row set)           (src/error.rs:15-16)
+// ----------------------------------------------------------------------------
+int ko_ilu0_factor(const ko_csr* A, double* lu, u64* diag_ptr, double* inv_udiag, u64* bad_row) {
+    const u64 n = A->n;
+    const u64* rp = A->row_ptr; const u64* ci = A->col_idx;
+    std::memcpy(lu, A->vals, sizeof(double) * rp[n]);
+    for (u64 i = 0; i < n; ++i) {
+        u64 d = rp[i + 1];
+        for (u64 p = rp[i]; p < rp[i + 1]; ++p) if (ci[p] == i) { d = p; break; }
+        if (d == rp[i + 1]) { *bad_row = i; return KO_FACTOR_ERROR; }
+        diag_ptr[i] = d;
+    }
+    for (u64 i = 0; i < n; ++i) {
+        for (u64 p = rp[i]; p < diag_ptr[i]; ++p) {
+            u64 k = ci[p];
+            double lik = lu[p] / lu[diag_ptr[k]];
+            lu[p] = lik;
+            // merge row k's strict upper part into row i (both ascending)
+            u64 pos = p + 1;
+            for (u64 q = diag_ptr[k] + 1; q < rp[k + 1]; ++q) {
+                u64 j = ci[q];
+                while (pos < rp[i + 1] && ci[pos] < j) ++pos;
+                if (pos < rp[i + 1] && ci[pos] == j) lu[pos] = lu[pos] - lik * lu[q];
+            }
+        }
+        double piv = lu[diag_ptr[i]];
+        if (piv == 0.0 || piv != piv) { *bad_row = i; return KO_ZERO_PIVOT; }
+        inv_udiag[i] = 1.0 / piv;
+    }
+    return KO_OK;
+}
+
+// z = U^{-1} L^{-1} r ; row sums in ascending column order, mul then sub
+void ko_ilu0_apply(const ko_csr* A, const double* lu, const u64* diag_ptr, const double* inv_udiag,
+                   const double* r, double* z) {
+    const u64 n = A->n;
+    const u64* rp = A->row_ptr; const u64* ci = A->col_idx;
+    for (u64 i = 0; i < n; ++i) {
+        double s = r[i];
+        for (u64 p = rp[i]; p < diag_ptr[i]; ++p) s = s - lu[p] * z[ci[p]];
+        z[i] = s;
+    }
+    for (u64 ii = n; ii-- > 0;) {
+        double s = z[ii];
+        for (u64 p = diag_ptr[ii] + 1; p < rp[ii + 1]; ++p) s = s - lu[p] * z[ci[p]];
+        z[ii] = s * inv_udiag[ii];
+    }
+}
+
+// Level sets: lev_L[i] = 1 + max(lev_L[k]: k in cols(i), k < i), 0 if none;
+// lev_U symmetric from the bottom.  order[] = rows listed per level, ascending row
+// inside a level; level_ptr has nlevels+1 entries.  Returns nlevels.
+u64 ko_levels(const ko_csr* A, int upper, u64* level, u64* order, u64* level_ptr) {
+    const u64 n = A->n;
+    const u64* rp = A->row_ptr; const u64* ci = A->col_idx;
+    u64 nlev = 0;
+    if (!upper) {
+        for (u64 i = 0; i < n; ++i) {
+            u64 lv = 0;
+            for (u64 p = rp[i]; p < rp[i + 1]; ++p) { u64 k = ci[p]; if (k < i && level[k] + 1 > lv) lv = level[k] + 1; }
+            level[i] = lv; if (lv + 1 > nlev) nlev = lv + 1;
+        }
+    } else {
+        for (u64 i = n; i-- > 0;) {
+            u64 lv = 0;
+            for (u64 p = rp[i]; p < rp[i + 1]; ++p) { u64 k = ci[p]; if (k > i && k < n && level[k] + 1 > lv) lv = level[k] + 1; }
+            level[i] = lv; if (lv + 1 > nlev) nlev = lv + 1;
+        }
+    }
+    if (n == 0) { level_ptr[0] = 0; return 0; }
+    std::vector<u64> cnt(nlev + 1, 0);
+    for (u64 i = 0; i < n; ++i) cnt[level[i] + 1]++;
+    for (u64 l = 0; l < nlev; ++l) cnt[l + 1] += cnt[l];
+    for (u64 l = 0; l <= nlev; ++l) level_ptr[l] = cnt[l];
+    for (u64 i = 0; i < n; ++i) order[cnt[level[i]]++] = i;
+    return nlev;
+}
+
+// ----------------------------------------------------------------------------
+// Literal dense Ilu0 — src/preconditioner/ilu.rs:59-100 (setup) and :105-122 (apply),
+// restated AS-IS (it is not an ILU; kept to document the deviation and
+// to reproduce tests/preconditioner_integration.rs:169-179).  Row-major n*n arrays.
+// ----------------------------------------------------------------------------
+void ko_ilu_literal_setup(u64 n, const double* a, double* l, double* u) {
+    std::fill(l, l + n * n, 0.0); std::fill(u, u + n * n, 0.0);
+    for (u64 i = 0; i < n; ++i) {
+        u[i * n + i] = a[i * n + i];
+        for (u64 j = i + 1; j < n; ++j) if (a[i * n + j] != 0.0) u[i * n + j] = a[i * n + j];
+        l[i * n + i] = 1.0;
+        for (u64 j = i + 1; j < n; ++j) if (a[j * n + i] != 0.0) l[j * n + i] = a[j * n + i] / u[i * n + i];
+        for (u64 j = i + 1; j < n; ++j)
+            for (u64 k = i + 1; k < n; ++k)
+                if (a[j * n + k] != 0.0) {
+                    double v = a[j * n + k] - l[j * n + i] * u[i * n + k];
+                    if (v != 0.0) { if (k >= j) u[j * n + k] = v; else l[j * n + k] = v; }
+                }
+    }
+}
+void ko_ilu_literal_apply(u64 n, const double* l, const double* u, const double* x, double* y) {
+    std::vector<double> y1(x, x + n);
+    for (u64 i = 0; i < n; ++i) for (u64 j = 0; j < i; ++j) y1[i] = y1[i] - l[i * n + j] * y1[j];
+    for (u64 i = n; i-- > 0;) for (u64 j = i + 1; j < n; ++j) y1[i] = y1[i] - u[i * n + j] * y1[j];
+    std::memcpy(y, y1.data(), sizeof(double) * n);
+}
+
+// ----------------------------------------------------------------------------
+// Preconditioner object used by the oracle solvers
+// ----------------------------------------------------------------------------
+enum { KO_PC_NONE = 0, KO_PC_JACOBI = 1, KO_PC_ILU0 = 2, KO_PC_BLOCK_ILU0 = 3, KO_PC_ILU_LITERAL = 4 };
+
+struct ko_pc {
+    int kind = KO_PC_NONE;
+    u64 n = 0;
+    std::vector<double> inv_diag;                 // jacobi
+    // ilu0 / block ilu0: one factor per block, on the block-local CSR
+    struct Block { u64 lo, hi; std::vector<u64> rp, ci, dp; std::vector<double> av, lu, inv_ud; };
+    std::vector<Block> blocks;
+    std::vector<double> dl, du;                   // literal dense
+    int status = KO_OK; u64 bad_row = 0;
+};
+
+static void pc_apply(const ko_pc* pc, const double* r, double* z, u64 n) {
+    if (!pc || pc->kind == KO_PC_NONE) { std::memcpy(z, r, sizeof(double) * n); return; }
+    switch (pc->kind) {
+    case KO_PC_JACOBI: ko_jacobi_apply(n, pc->inv_diag.data(), r, z); break;
+    case KO_PC_ILU0:
+    case KO_PC_BLOCK_ILU0: {
+#pragma omp parallel for schedule(dynamic, 1)
+        for (i64 b = 0; b < (i64)pc->blocks.size(); ++b) {
+            const ko_pc::Block& B = pc->blocks[b];
+            ko_csr L{B.hi - B.lo, B.hi - B.lo, B.rp.data(), B.ci.data(), B.av.data()};
+            ko_ilu0_apply(&L, B.lu.data(), B.dp.data(), B.inv_ud.data(), r + B.lo, z + B.lo);
+        }
+        break; }
+    case KO_PC_ILU_LITERAL: ko_ilu_literal_apply(n, pc->dl.data(), pc->du.data(), r, z); break;
+    }
+}
+
+ko_pc* ko_pc_create_jacobi(const ko_csr* A) {
+    ko_pc* pc = new ko_pc; pc->kind = KO_PC_JACOBI; pc->n = A->n; pc->inv_diag.resize(A->n);
+    ko_jacobi_setup(A, pc->inv_diag.data()); return pc;
+}
+// block-Jacobi ILU(0): block b = reference chunk partition (asm.rs:46-57), couplings to
+// columns outside the block dropped, textbook ILU(0) on the block.  nblocks==1 -> plain ILU(0).
+ko_pc* ko_pc_create_ilu0(const ko_csr* A, u64 nblocks) {
+    ko_pc* pc = new ko_pc; pc->kind = nblocks > 1 ? KO_PC_BLOCK_ILU0 : KO_PC_ILU0; pc->n = A->n;
+    pc->blocks.resize(nblocks);
+    for (u64 b = 0; b < nblocks; ++b) {
+        ko_pc::Block& B = pc->blocks[b];
+        ko_partition_range(A->n, nblocks, b, &B.lo, &B.hi);
+        u64 m = B.hi - B.lo;
+        B.rp.assign(m + 1, 0);
+        for (u64 i = 0; i < m; ++i) {
+            for (u64 p = A->row_ptr[B.lo + i]; p < A->row_ptr[B.lo + i + 1]; ++p) {
+                u64 c = A->col_idx[p];
+                if (c >= B.lo && c < B.hi) { B.ci.push_back(c - B.lo); B.av.push_back(A->vals[p]); }
+            }
+            B.rp[i + 1] = B.ci.size();
+        }
+        B.lu.resize(B.av.size()); B.dp.resize(m); B.inv_ud.resize(m);
+        ko_csr L{m, m, B.rp.data(), B.ci.data(), B.av.data()};
+        u64 bad = 0;
+        int st = ko_ilu0_factor(&L, B.lu.data(), B.dp.data(), B.inv_ud.data(), &bad);
+        if (st != KO_OK && pc->status == KO_OK) { pc->status = st; pc->bad_row = B.lo + bad; }
+    }
+    return pc;
+}
+ko_pc* ko_pc_create_ilu_literal(u64 n, const double* dense_row_major) {
+    ko_pc* pc = new ko_pc; pc->kind = KO_PC_ILU_LITERAL; pc->n = n; pc->dl.resize(n * n); pc->du.resize(n * n);
+    ko_ilu_literal_setup(n, dense_row_major, pc->dl.data(), pc->du.data()); return pc;
+}
+int ko_pc_status(const ko_pc* pc, u64* bad_row) { if (bad_row) *bad_row = pc->bad_row; return pc->status; }
+void ko_pc_apply(const ko_pc* pc, const double* r, double* z) { pc_apply(pc, r, z, pc->n); }
+void ko_pc_destroy(ko_pc* pc) { delete pc; }
+// read back factor data of block b (for factor-parity tests); arrays sized by the caller
+u64 ko_pc_block_nnz(const ko_pc* pc, u64 b) { return pc->blocks[b].lu.size(); }
+void ko_pc_block_get(const ko_pc* pc, u64 b, double* lu, u64* diag_ptr, double* inv_ud, u64* rp, u64* ci) {
+    const ko_pc::Block& B = pc->blocks[b];
+    if (lu) std::memcpy(lu, B.lu.data(), sizeof(double) * B.lu.size());
+    if (diag_ptr) std::memcpy(diag_ptr, B.dp.data(), sizeof(u64) * B.dp.size());
+    if (inv_ud) std::memcpy(inv_ud, B.inv_ud.data(), sizeof(double) * B.inv_ud.size());
+    if (rp) std::memcpy(rp, B.rp.data(), sizeof(u64) * B.rp.size());
+    if (ci) std::memcpy(ci, B.ci.data(), sizeof(u64) * B.ci.size());
+}
+
+// ----------------------------------------------------------------------------
+// Convergence::check — src/utils/convergence.rs:18-34 (F8: max_iters => converged)
+// ----------------------------------------------------------------------------
+static inline bool conv_check(double res, double res0, u64 i, double tol, u64 max_iters, ko_stats* s) {
+    double rel = res / res0;
+    bool converged = (rel <= tol) || (i >= max_iters);
+    s->iterations = i; s->final_residual = res; s->converged = converged ? 1 : 0;
+    return converged;
+}
+
+// ----------------------------------------------------------------------------
+// PCG literal — src/solver/pcg.rs:114-222.  norm_type: 0 Preconditioned, 1 Unpreconditioned
+// (default, :53), 2 Natural, 3 None (:25).  history receives residual_history pushes (:146,:199).
+// x is written iff the return value is KO_OK (pcg.rs:171,212 return Err without writing x).
+// ----------------------------------------------------------------------------
+int ko_pcg(const ko_csr* A, const ko_pc* pc, const double* b, double* x, double tol, u64 max_iters,
+           int norm_type, u64 nshards, double* history, u64 hist_cap, u64* hist_len, ko_stats* stats) {
+    const u64 n = A->n;
+    std::vector<double> xv(x, x + n), r(n), z(n), p(n), ap(n);
+    u64 hl = 0;
+    auto push = [&](double v) { if (history && hl < hist_cap) history[hl] = v; ++hl; };
+    auto DOT = [&](const std::vector<double>& a, const std::vector<double>& c) { return ko_dot_sharded(n, a.data(), c.data(), nshards); };
+    ko_spmv(A, xv.data(), ap.data());
+#pragma omp parallel for schedule(static)
+    for (i64 i = 0; i < (i64)n; ++i) r[i] = b[i] - ap[i];
+    pc_apply(pc, r.data(), z.data(), n);
+    p = z;
+    double rz = DOT(r, z);
+    double res0 = std::sqrt(std::fabs(rz));
+    stats->iterations = 0; stats->final_residual = res0; stats->converged = 0; stats->breakdown = 0;
+    auto NORM = [&]() -> double {
+        switch (norm_type) {
+        case 0: return std::sqrt(DOT(z, z));
+        case 1: return std::sqrt(DOT(r, r));
+        case 2: return std::sqrt(std::fabs(DOT(r, z)));
+        default: return 0.0;
+        }
+    };
+    push(NORM());
+    for (u64 i = 0; i < max_iters; ++i) {
+        ko_spmv(A, p.data(), ap.data());
+        double pAp = DOT(p, ap);
+        if (pAp <= 0.0) {
+            stats->iterations = i + 1; stats->final_residual = NORM(); stats->converged = 0;
+            if (hist_len) *hist_len = hl;
+            return KO_INDEFINITE_MATRIX;
+        }
+        double alpha = rz / pAp;
+#pragma omp parallel for schedule(static)
+        for (i64 k = 0; k < (i64)n; ++k) { xv[k] = xv[k] + alpha * p[k]; r[k] = r[k] - alpha * ap[k]; }
+        pc_apply(pc, r.data(), z.data(), n);
+        double rz_new = DOT(r, z);
+        double res = NORM();
+        push(res);
+        if (conv_check(res, res0, i + 1, tol, max_iters, stats)) {
+            std::memcpy(x, xv.data(), sizeof(double) * n);
+            if (hist_len) *hist_len = hl;
+            return KO_OK;
+        }
+        double beta = rz_new / rz;
+        if (beta < 0.0) {
+            stats->iterations = i + 1; stats->final_residual = res; stats->converged = 0;
+            if (hist_len) *hist_len = hl;
+            return KO_INDEFINITE_PC;
+        }
+#pragma omp parallel for schedule(static)
+        for (i64 k = 0; k < (i64)n; ++k) p[k] = z[k] + beta * p[k];
+        rz = rz_new;
+    }
+    std::memcpy(x, xv.data(), sizeof(double) * n);
+    if (hist_len) *hist_len = hl;
+    return KO_OK;
+}
+
+// ----------------------------------------------------------------------------
+// GMRES
+//   variant 0 (LITERAL): src/solver/gmres.rs:216-402 exactly, incl. the inconsistent
+//       Left/Right branches (F7), MGS + unconditional second pass (:83-96).
+//   variant 1 (CGS2, Tier T): textbook None/Left/Right with classical Gram-Schmidt
+//       + reorthogonalisation as a block GEMV — what the GPU runs.
+//   variant 2 (MGS2, Tier T): same textbook formulation with the literal's MGS+2nd pass.
+//   mode: 0 None, 1 Left, 2 Right (gmres.rs:28-32); pc==NULL forces None (gmres.rs:262).
+// Shared pieces: Givens (:154-176), back-substitution (:180-192), eps = 1e-14 (:233),
+// Convergence::check inner stop (:349), true-residual test per cycle, strict < (:394-395).
+// ----------------------------------------------------------------------------
+static void givens_update(std::vector<std::vector<double>>& h, std::vector<double>& g, std::vector<double>& cs,
+                          std::vector<double>& sn, u64 j, double eps) {
+    for (u64 i = 0; i < j; ++i) {
+        double temp = cs[i] * h[i][j] + sn[i] * h[i + 1][j];
+        h[i + 1][j] = -sn[i] * h[i][j] + cs[i] * h[i + 1][j];
+        h[i][j] = temp;
+    }
+    double hkk = h[j][j], hk1k = h[j + 1][j];
+    double r = std::sqrt(hkk * hkk + hk1k * hk1k);
+    if (std::fabs(r) < eps) { cs[j] = 1.0; sn[j] = 0.0; }
+    else { cs[j] = hkk / r; sn[j] = hk1k / r; }
+    h[j][j] = cs[j] * hkk + sn[j] * hk1k;
+    h[j + 1][j] = 0.0;
+    double temp = cs[j] * g[j] + sn[j] * g[j + 1];
+    g[j + 1] = -sn[j] * g[j] + cs[j] * g[j + 1];
+    g[j] = temp;
+}
+static void back_subst(const std::vector<std::vector<double>>& h, const std::vector<double>& g, std::vector<double>& y,
+                       u64 m, double eps) {
+    for (u64 i = m; i-- > 0;) {
+        y[i] = g[i];
+        for (u64 j = i + 1; j < m; ++j) y[i] = y[i] - h[i][j] * y[j];
+        if (std::fabs(h[i][i]) > eps) y[i] = y[i] / h[i][i]; else y[i] = 0.0;
+    }
+}
+
+int ko_gmres(const ko_csr* A, const ko_pc* pc, const double* b, double* x, u64 restart, double tol, u64 max_iters,
+             int mode, int variant, u64 nshards, ko_stats* stats) {
+    const u64 n = A->n;
+    if (!pc || pc->kind == KO_PC_NONE) mode = 0;
+    const double eps = 1e-14;
+    auto DOT = [&](const double* a, const double* c) { return ko_dot_sharded(n, a, c, nshards); };
+    auto NRM = [&](const double* a) { return std::sqrt(ko_dot_sharded(n, a, a, nshards)); };
+    std::vector<double> xk(x, x + n), r0(n), tmp(n), w(n), z(n);
+    ko_spmv(A, xk.data(), tmp.data());
+    for (u64 i = 0; i < n; ++i) r0[i] = b[i] - tmp[i];
+    double beta = NRM(r0.data());
+    const double res0_true = beta;
+    double res0 = beta;               // inner-check denominator
+    stats->iterations = 0; stats->final_residual = beta; stats->converged = 0; stats->breakdown = 0;
+    const u64 n_outer = (max_iters + restart - 1) / restart;
+    u64 iteration = 0;
+    bool first_cycle = true;
+    std::vector<std::vector<double>> V, Z;
+    for (u64 outer = 0; outer < n_outer; ++outer) {
+        V.clear(); Z.clear();
+        double r0_norm = beta;
+        if (variant == 0) {
+            if (mode == 1) {          // gmres.rs:241-248
+                std::vector<double> v0(n); for (u64 i = 0; i < n; ++i) v0[i] = r0[i] / r0_norm;
+                std::vector<double> z0(n); pc_apply(pc, v0.data(), z0.data(), n);
+                V.push_back(v0); Z.push_back(z0);
+            } else if (mode == 2) {   // gmres.rs:249-261
+                std::vector<double> z0(n); pc_apply(pc, r0.data(), z0.data(), n);
+                r0_norm = NRM(z0.data());
+                std::vector<double> v0(n); for (u64 i = 0; i < n; ++i) v0[i] = z0[i] / r0_norm;
+                std::vector<double> z0p(n); pc_apply(pc, v0.data(), z0p.data(), n);
+                V.push_back(v0); Z.push_back(z0p);
+                beta = r0_norm;
+            } else {
+                std::vector<double> v0(n); for (u64 i = 0; i < n; ++i) v0[i] = r0[i] / r0_norm;
+                V.push_back(v0);
+            }
+        } else {
+            // textbook: Left -> Arnoldi on M^-1 A from M^-1 r0 ; None/Right -> from r0
+            std::vector<double> v0(n);
+            if (mode == 1) { pc_apply(pc, r0.data(), z.data(), n); r0_norm = NRM(z.data()); for (u64 i = 0; i < n; ++i) v0[i] = z[i] / r0_norm; }
+            else { for (u64 i = 0; i < n; ++i) v0[i] = r0[i] / r0_norm; }
+            if (first_cycle) res0 = r0_norm;
+            V.push_back(v0);
+        }
+        first_cycle = false;
+        std::vector<std::vector<double>> h(restart + 1, std::vector<double>(restart, 0.0));
+        std::vector<double> g(restart + 1, 0.0), cs(restart, 0.0), sn(restart, 0.0);
+        g[0] = r0_norm;
+        u64 m = 0; bool happy = false;
+        for (u64 j = 0; j < restart; ++j) {
+            iteration += 1;
+            // --- build w (the vector to orthogonalise) and the basis it is orthogonalised against
+            std::vector<std::vector<double>>* basis = &V;
+            if (variant == 0 && mode == 1) {          // gmres.rs:279-307
+                ko_spmv(A, V[j].data(), tmp.data()); pc_apply(pc, tmp.data(), w.data(), n); basis = &Z;
+            } else if (variant == 0 && mode == 2) {   // gmres.rs:308-342
+                pc_apply(pc, V[j].data(), tmp.data(), n); ko_spmv(A, tmp.data(), w.data());
+            } else if (mode == 1) {
+                ko_spmv(A, V[j].data(), tmp.data()); pc_apply(pc, tmp.data(), w.data(), n);
+            } else if (mode == 2) {
+                pc_apply(pc, V[j].data(), tmp.data(), n); ko_spmv(A, tmp.data(), w.data());
+            } else {
+                ko_spmv(A, V[j].data(), w.data());     // gmres.rs:80-81
+            }
+            if (variant == 1) {                        // CGS2 block GEMV
+                std::vector<double> h1(j + 1), h2(j + 1);
+                for (u64 c = 0; c <= j; ++c) h1[c] = DOT((*basis)[c].data(), w.data());
+#pragma omp parallel for schedule(static)
+                for (i64 i = 0; i < (i64)n; ++i) { double t = w[i]; for (u64 c = 0; c <= j; ++c) t = t - (*basis)[c][i] * h1[c]; w[i] = t; }
+                for (u64 c = 0; c <= j; ++c) h2[c] = DOT((*basis)[c].data(), w.data());
+#pragma omp parallel for schedule(static)
+                for (i64 i = 0; i < (i64)n; ++i) { double t = w[i]; for (u64 c = 0; c <= j; ++c) t = t - (*basis)[c][i] * h2[c]; w[i] = t; }
+                for (u64 c = 0; c <= j; ++c) h[c][j] = h1[c] + h2[c];
+            } else {                                   // MGS + unconditional second pass (gmres.rs:83-96)
+                for (u64 c = 0; c <= j; ++c) {
+                    h[c][j] = DOT(w.data(), (*basis)[c].data());
+                    const double hc = h[c][j]; const double* vc = (*basis)[c].data();
+#pragma omp parallel for schedule(static)
+                    for (i64 i = 0; i < (i64)n; ++i) w[i] = w[i] - hc * vc[i];
+                }
+                for (u64 c = 0; c <= j; ++c) {
+                    double t = DOT(w.data(), (*basis)[c].data());
+                    h[c][j] = h[c][j] + t; const double* vc = (*basis)[c].data();
+#pragma omp parallel for schedule(static)
+                    for (i64 i = 0; i < (i64)n; ++i) w[i] = w[i] - t * vc[i];
+                }
+            }
+            h[j + 1][j] = NRM(w.data());
+            if (std::fabs(h[j + 1][j]) < eps) {
+                happy = true;
+                if (variant == 0 && mode != 0) break;  // gmres.rs:299-302,330-333: break BEFORE Givens/check
+            } else {
+                std::vector<double> vj1(n); const double hn = h[j + 1][j];
+                for (u64 i = 0; i < n; ++i) vj1[i] = w[i] / hn;
+                V.push_back(vj1);
+                if (variant == 0 && mode == 1) Z.push_back(vj1);
+                if (variant == 0 && mode == 2) { std::vector<double> zj1(n); pc_apply(pc, vj1.data(), zj1.data(), n); Z.push_back(zj1); }
+            }
+            givens_update(h, g, cs, sn, j, eps);
+            double res_norm = std::fabs(g[j + 1]);
+            bool stop = conv_check(res_norm, res0, iteration, tol, max_iters, stats);
+            m = j + 1;
+            if (stop || happy) break;
+        }
+        std::vector<double> y(m, 0.0);
+        back_subst(h, g, y, m, eps);
+        if (mode == 2) {
+            if (variant == 0) { for (u64 j = 0; j < m; ++j) for (u64 i = 0; i < n; ++i) xk[i] = xk[i] + y[j] * Z[j][i]; }
+            else {  // textbook right: x += M^-1 (V y)
+                std::fill(tmp.begin(), tmp.end(), 0.0);
+                for (u64 i = 0; i < n; ++i) { double t = 0.0; for (u64 j = 0; j < m; ++j) t = t + y[j] * V[j][i]; tmp[i] = t; }
+                pc_apply(pc, tmp.data(), z.data(), n);
+                for (u64 i = 0; i < n; ++i) xk[i] = xk[i] + z[i];
+            }
+        } else {
+#pragma omp parallel for schedule(static)
+            for (i64 i = 0; i < (i64)n; ++i) { double t = xk[i]; for (u64 j = 0; j < m; ++j) t = t + y[j] * V[j][i]; xk[i] = t; }
+        }
+        ko_spmv(A, xk.data(), tmp.data());
+        for (u64 i = 0; i < n; ++i) r0[i] = b[i] - tmp[i];
+        beta = NRM(r0.data());
+        stats->final_residual = beta;
+        stats->converged = (beta < tol * res0_true) ? 1 : 0;
+        if (stats->converged || iteration >= max_iters) break;
+    }
+    std::memcpy(x, xk.data(), sizeof(double) * n);
+    return KO_OK;
+}
+
+// ----------------------------------------------------------------------------
+// BiCGStab
+//   variant 0 (LITERAL): src/solver/bicgstab.rs:69-293 — pc ignored (:70), absolute
+//       tolerance (:98,:189,:281), |.| < f64::EPSILON breakdown `break`s (:117,:161,:235,:285)
+//       which return Ok with the previous stats.
+//   variant 1 (Tier T): Jacobi/any-pc right-preconditioned, relative tolerance
+//       (SURVEY App. A.2); breakdowns are reported in stats->breakdown.
+// breakdown codes: 1 rho, 2 r̂·v, 3 t·t, 4 omega
+// ----------------------------------------------------------------------------
+int ko_bicgstab(const ko_csr* A, const ko_pc* pc, const double* b, double* x, double tol, u64 max_iters,
+                int variant, u64 nshards, ko_stats* stats) {
+    const u64 n = A->n;
+    const double EPS = std::numeric_limits<double>::epsilon();
+    auto DOT = [&](const std::vector<double>& a, const std::vector<double>& c) { return ko_dot_sharded(n, a.data(), c.data(), nshards); };
+    std::vector<double> xk(x, x + n), r(n), tmp(n), v(n, 0.0), p(n), s(n), t(n), ph(n), sh(n);
+    ko_spmv(A, xk.data(), tmp.data());
+    for (u64 i = 0; i < n; ++i) r[i] = b[i] - tmp[i];
+    std::vector<double> rhat(r);
+    double rho_prev = 1.0, alpha = 1.0, omega_prev = 1.0;
+    p = r;
+    double res0 = std::sqrt(DOT(r, r));
+    stats->iterations = 0; stats->final_residual = res0; stats->converged = 0; stats->breakdown = 0;
+    const bool lit = (variant == 0);
+    const double thr = lit ? tol : tol * res0;    // literal: absolute; Tier T: relative to ||r0||
+    if (res0 <= thr) { stats->converged = 1; return KO_OK; }   // bicgstab.rs:98-102 (x unchanged == xk)
+    double rnorm = res0;
+    for (u64 i = 1; i <= max_iters; ++i) {
+        double rho = DOT(rhat, r);
+        if (lit ? (std::fabs(rho) < EPS) : (std::fabs(rho) < EPS * res0 * rnorm)) { stats->breakdown = 1; break; }
+        double beta = (i == 1) ? 0.0 : (rho / rho_prev) * (alpha / omega_prev);
+#pragma omp parallel for schedule(static)
+        for (i64 k = 0; k < (i64)n; ++k) p[k] = r[k] + beta * (p[k] - omega_prev * v[k]);
+        if (lit) ko_spmv(A, p.data(), v.data());
+        else { pc_apply(pc, p.data(), ph.data(), n); ko_spmv(A, ph.data(), v.data()); }
+        double alpha_den = DOT(rhat, v);
+        if (lit ? (std::fabs(alpha_den) < EPS) : (std::fabs(alpha_den) < EPS * res0 * std::sqrt(DOT(v, v)))) { stats->breakdown = 2; break; }
+        alpha = rho / alpha_den;
+#pragma omp parallel for schedule(static)
+        for (i64 k = 0; k < (i64)n; ++k) s[k] = r[k] - alpha * v[k];
+        double s_norm = std::sqrt(DOT(s, s));
+        if (s_norm <= thr) {
+            const std::vector<double>& pp = lit ? p : ph;
+            for (u64 k = 0; k < n; ++k) xk[k] = xk[k] + alpha * pp[k];
+            std::memcpy(x, xk.data(), sizeof(double) * n);
+            stats->iterations = i; stats->final_residual = s_norm; stats->converged = 1;
+            return KO_OK;
+        }
+        if (lit) ko_spmv(A, s.data(), t.data());
+        else { pc_apply(pc, s.data(), sh.data(), n); ko_spmv(A, sh.data(), t.data()); }
+        double omega_num = DOT(t, s);
+        double omega_den = DOT(t, t);
+        if (lit ? (std::fabs(omega_den) < EPS) : (omega_den == 0.0)) { stats->breakdown = 3; break; }
+        double omega = omega_num / omega_den;
+        {
+            const std::vector<double>& pp = lit ? p : ph;
+            const std::vector<double>& ss = lit ? s : sh;
+#pragma omp parallel for schedule(static)
+            for (i64 k = 0; k < (i64)n; ++k) xk[k] = xk[k] + alpha * pp[k] + omega * ss[k];
+        }
+#pragma omp parallel for schedule(static)
+        for (i64 k = 0; k < (i64)n; ++k) r[k] = s[k] - omega * t[k];
+        double r_norm = std::sqrt(DOT(r, r));
+        rnorm = r_norm;
+        stats->iterations = i; stats->final_residual = r_norm; stats->converged = (r_norm <= thr) ? 1 : 0;
+        if (r_norm <= thr) { std::memcpy(x, xk.data(), sizeof(double) * n); return KO_OK; }
+        if (lit ? (std::fabs(omega) < EPS) : (omega == 0.0)) { stats->breakdown = 4; break; }
+        rho_prev = rho; omega_prev = omega;
+    }
+    std::memcpy(x, xk.data(), sizeof(double) * n);
+    return KO_OK;
+}
+
+// ----------------------------------------------------------------------------
+// Partition / ghost maps.  Rank r owns [lo,hi) (asm.rs:46-57 chunks).
+//   ghosts  : sorted unique off-range column indices referenced by the owned rows
+//   returns number of ghosts; if ghosts==NULL only counts.
+// ----------------------------------------------------------------------------
+u64 ko_ghost_list(const ko_csr* A, u64 lo, u64 hi, u64* ghosts) {
+    std::vector<u64> g;
+    for (u64 p = A->row_ptr[lo]; p < A->row_ptr[hi]; ++p) { u64 c = A->col_idx[p]; if (c < lo || c >= hi) g.push_back(c); }
+    std::sort(g.begin(), g.end()); g.erase(std::unique(g.begin(), g.end()), g.end());
+    if (ghosts) std::memcpy(ghosts, g.data(), sizeof(u64) * g.size());
+    return g.size();
+}
+
+// ----------------------------------------------------------------------------
+// Synthetic stencil generators for rows [lo,hi), global columns.
+//   kind 0: C1 2-D 5-pt Poisson (4,-1)            kind 1: C2 2-D 5-pt upwind conv-diff (px,py)
+//   kind 2: C3 3-D 27-pt variable coefficient       kind 3: C4 3-D 7-pt Poisson (6,-1)
+//   kind 4: C5 3-D 7-pt upwind conv-diff (px,py,pz)
+// Ordering row = i + N j (+ N^2 k), Dirichlet truncation, ascending columns.
+// ----------------------------------------------------------------------------
+static inline u64 splitmix64(u64 z) {
+    z += 0x9E3779B97F4A7C15ULL; z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL; return z ^ (z >> 31);
+}
+static inline double kappa(u64 r) {
+    return 0.1 + 1.9 * ((double)(splitmix64(0x5EEDB200ULL + r) >> 11) * (1.0 / 9007199254740992.0));
+}
+u64 ko_stencil_dim(int kind, u64 N) { return (kind <= 1) ? N * N : N * N * N; }
+
+// pass 1 (col_idx==NULL): fills row_ptr only and returns nnz; pass 2 fills everything.
+u64 ko_stencil(int kind, u64 N, u64 lo, u64 hi, double px, double py, double pz, u64* row_ptr, u64* col_idx, double* vals) {
+    const bool fill = (col_idx != nullptr);
+    u64 nnz = 0;
+    if (!fill || true) row_ptr[0] = 0;
+    const i64 n1 = (i64)N, n2 = (i64)(N * N);
+    for (u64 row = lo; row < hi; ++row) {
+        i64 i = (i64)(row % N), j = (i64)((row / N) % N), k = (i64)(row / (N * N));
+        auto emit = [&](i64 off, double v) { if (fill) { col_idx[nnz] = (u64)((i64)row + off); vals[nnz] = v; } ++nnz; };
+        if (kind == 0 || kind == 1) {
+            double west = (kind == 0) ? -1.0 : -(1.0 + px), south = (kind == 0) ? -1.0 : -(1.0 + py);
+            double diag = (kind == 0) ? 4.0 : (4.0 + px) + py;
+            if (j > 0) emit(-n1, south);
+            if (i > 0) emit(-1, west);
+            emit(0, diag);
+            if (i < n1 - 1) emit(1, -1.0);
+            if (j < n1 - 1) emit(n1, -1.0);
+        } else if (kind == 3 || kind == 4) {
+            double west = (kind == 3) ? -1.0 : -(1.0 + px), south = (kind == 3) ? -1.0 : -(1.0 + py), down = (kind == 3) ? -1.0 : -(1.0 + pz);
+            double diag = (kind == 3) ? 6.0 : ((6.0 + px) + py) + pz;
+            if (k > 0) emit(-n2, down);
+            if (j > 0) emit(-n1, south);
+            if (i > 0) emit(-1, west);
+            emit(0, diag);
+            if (i < n1 - 1) emit(1, -1.0);
+            if (j < n1 - 1) emit(n1, -1.0);
+            if (k < n1 - 1) emit(n2, -1.0);
+        } else {
+            double kr = kappa(row);
+            double diag = 0.0;
+            for (i64 dz = -1; dz <= 1; ++dz) for (i64 dy = -1; dy <= 1; ++dy) for (i64 dx = -1; dx <= 1; ++dx) {
+                if (!dz && !dy && !dx) continue;
+                bool inside = (i + dx >= 0 && i + dx < n1 && j + dy >= 0 && j + dy < n1 && k + dz >= 0 && k + dz < n1);
+                if (inside) diag = diag + 0.5 * (kr + kappa((u64)((i64)row + dx + n1 * dy + n2 * dz)));
+                else diag = diag + kr;
+            }
+            for (i64 dz = -1; dz <= 1; ++dz) for (i64 dy = -1; dy <= 1; ++dy) for (i64 dx = -1; dx <= 1; ++dx) {
+                bool inside = (i + dx >= 0 && i + dx < n1 && j + dy >= 0 && j + dy < n1 && k + dz >= 0 && k + dz < n1);
+                if (!inside) continue;
+                i64 off = dx + n1 * dy + n2 * dz;
+                if (!dz && !dy && !dx) emit(0, diag);
+                else emit(off, -(0.5 * (kr + kappa((u64)((i64)row + off)))));
+            }
+        }
+        row_ptr[row - lo + 1] = nnz;
+    }
+    return nnz;
+}
+
+} // extern "C"
