@@ -1,0 +1,63 @@
+// kb_epilogue.cuh — glue between fused reductions and the scalar recurrences of the solvers.
+//
+// Single GPU: the last block of the reducing kernel runs the scalar epilogue (alpha, beta,
+// Convergence::check ...) inline, so no extra launch and no host round trip.
+// Row-block shards: the last block stores its local sums to `slots`; they are all-gathered over
+// NVLink, summed in rank order (deterministic) and the same epilogue runs in a 1-thread kernel.
+#pragma once
+#include "kb_objects.h"
+#include "kb_spmv.cuh"
+
+template <class Fin>
+struct KbFinish {
+    Fin fin;
+    double* slots;   // nullptr => run the epilogue inline
+    int nred;
+    __device__ void operator()(const double* s) const {
+        if (slots) { for (int r = 0; r < nred; ++r) slots[r] = s[r]; }
+        else fin(s);
+    }
+};
+
+template <class Fin, int ND>
+struct KbSpmvEpi {
+    static constexpr int NDOT = ND;
+    KbCtl* ctl;          // may be null (never skip)
+    KbFinish<Fin> fin;
+    __device__ bool skip() const { return ctl != nullptr && ctl->done != 0; }
+    __device__ void finish(const double* s) const { fin(s); }
+};
+
+template <class Fin>
+__global__ void kb_fin_kernel(Fin fin, KbCtl* ctl, const double* sums) {
+    if (ctl->done) return;
+    fin(sums);
+}
+
+template <class Fin>
+static int kb_finish_dist(kb_ctx_s* c, Fin fin, KbCtl* ctl, double* slots, int nred) {
+    KB_TRY(kb_allreduce_slots(c, slots, nred));
+    KbLaunch L(c, KB_K_SMALL);
+    kb_fin_kernel<Fin><<<1, 1, 0, c->stream>>>(fin, ctl, slots);
+    KB_CUDA(cudaGetLastError());
+    return KB_OK;
+}
+
+// y = A x | y = b - A x with fused dots; dispatches on the kernel kind chosen at upload.
+template <class Epi, bool RESID>
+static int kb_launch_spmv(kb_csr_s* A, const double* x, double* y, const double* b, const double* w, double* partials,
+                          size_t pstride, Epi epi) {
+    if (A->n == 0) return KB_OK;
+    kb_ctx_s* c = A->ctx;
+    KbSpmvArgs a{};
+    a.row_ptr = A->row_ptr; a.col = A->col; a.vals = A->vals; a.x = x; a.y = y; a.b = b; a.w = w;
+    a.n = (int)A->n; a.tile0 = 0; a.ntiles_total = A->ntiles; a.tile_list = nullptr; a.finalize = 1;
+    a.partials = partials; a.pstride = pstride; a.ticket = c->ticket;
+    KbLaunch L(c, KB_K_SPMV);
+    if (A->kind == 0) kb_spmv_stream<Epi, RESID><<<A->ntiles, KB_THREADS, 0, c->stream>>>(a, epi);
+    else if (A->vec == 8) kb_spmv_vector<Epi, RESID, 8><<<A->ntiles, KB_THREADS, 0, c->stream>>>(a, epi);
+    else if (A->vec == 16) kb_spmv_vector<Epi, RESID, 16><<<A->ntiles, KB_THREADS, 0, c->stream>>>(a, epi);
+    else kb_spmv_vector<Epi, RESID, 32><<<A->ntiles, KB_THREADS, 0, c->stream>>>(a, epi);
+    KB_CUDA(cudaGetLastError());
+    return KB_OK;
+}

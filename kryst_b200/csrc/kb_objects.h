@@ -1,0 +1,86 @@
+// kb_objects.h — host-side handle layouts (opaque to ABI users).
+#pragma once
+#include "kb_internal.cuh"
+
+struct KbPcgWs;
+struct KbBicgWs;
+struct KbGmresWs;
+struct KbHalo;
+
+struct kb_csr_s {
+    kb_ctx_s* ctx = nullptr;
+    uint64_t n = 0;              // owned rows (Indexing::nrows)
+    uint64_t ncols_global = 0;   // MatShape::ncols
+    uint64_t ncols_local = 0;    // owned + ghost columns: length of the x operand of the kernels
+    uint64_t nnz = 0;
+    int* row_ptr = nullptr;      // i32 after checked narrowing
+    int* col = nullptr;          // local column ids, stored order == ascending GLOBAL column
+    double* vals = nullptr;
+    int ntiles = 0;
+    int kind = 0;                // 0 CSR-stream, 1 vector-per-row
+    int vec = 8;                 // sub-warp width of the vector kernel
+    uint64_t max_row_len = 0;
+    uint64_t hist[6] = {0, 0, 0, 0, 0, 0};   // row-length histogram: <=8,<=16,<=32,<=64,<=128,>128
+    // row-block shard (src/parallel gains this)
+    bool dist = false;
+    uint64_t n_global = 0, row_lo = 0, row_hi = 0, nghost = 0;
+    uint64_t* ghosts = nullptr;  // device: sorted unique global ids of ghost columns
+    KbHalo* halo = nullptr;
+    // scratch for host-slice matvec
+    double* x_tmp = nullptr;
+    double* y_tmp = nullptr;
+    // cached solver workspaces (device vectors, control block, CUDA graphs)
+    KbPcgWs* pcg_ws = nullptr;
+    KbBicgWs* bicg_ws = nullptr;
+    KbGmresWs* gmres_ws = nullptr;
+};
+
+enum { KB_PC_JACOBI = 1, KB_PC_ILU0 = 2 };
+
+struct kb_pc_s {
+    kb_csr_s* a = nullptr;
+    int kind = 0;
+    double* inv_diag = nullptr;       // Jacobi: 1/a_ii (0 if a_ii == 0); ILU(0): 1/u_ii
+    // ILU(0) on the owned diagonal block (pattern = A restricted to owned columns)
+    int* l_rp = nullptr;              // block-local CSR (ghost couplings dropped)
+    int* l_col = nullptr;
+    double* lu = nullptr;
+    int* diag_ptr = nullptr;
+    uint64_t l_nnz = 0;
+    int nlev[2] = {0, 0};             // lower / upper level counts
+    int* level_ptr[2] = {nullptr, nullptr};
+    int* order[2] = {nullptr, nullptr};     // rows per level, ascending inside a level
+    int* sched[2] = {nullptr, nullptr};     // warp-padded execution order for the sync-free solves
+    int sched_len[2] = {0, 0};
+    double* tmp = nullptr;            // y of L y = r
+    uint64_t bad_row = 0;
+    double* r_tmp = nullptr;
+    double* z_tmp = nullptr;
+};
+
+// allocation helpers
+template <class T>
+static inline int kb_alloc(T** p, size_t count) {
+    *p = nullptr;
+    if (count == 0) count = 1;
+    KB_CUDA(cudaMalloc((void**)p, count * sizeof(T)));
+    return KB_OK;
+}
+#define KB_FREE(p)            \
+    do {                      \
+        if (p) cudaFree(p);   \
+        p = nullptr;          \
+    } while (0)
+
+// ---- internal launch API (implemented across the .cu files) ---------------------------------
+int kb_csr_spmv_plain(kb_csr_s* A, const double* d_x, double* d_y);
+int kb_halo_exchange(kb_csr_s* A, double* d_x);   // fills ghost entries of d_x (no-op when !dist)
+int kb_allreduce_slots(kb_ctx_s* c, double* d_vals, int count);   // rank-ordered sum, in place
+int kb_pc_apply_dev(kb_pc_s* pc, const double* d_r, double* d_z);
+void kb_pcg_ws_free(KbPcgWs* w);
+void kb_bicg_ws_free(KbBicgWs* w);
+void kb_gmres_ws_free(KbGmresWs* w);
+void kb_halo_free(KbHalo* h);
+int kb_ilu0_build(kb_pc_s* pc);
+void kb_ilu0_free(kb_pc_s* pc);
+int kb_upload_or_alias(kb_ctx_s* c, const double* src, double* dst, uint64_t n, bool device_ptrs);

@@ -1,0 +1,306 @@
+// kb_pcg.cu — Preconditioned CG, device-resident (replaces src/solver/pcg.rs:114-222).
+//
+// Per iteration the reference runs 1 SpMV, 3 dots, 3 vector updates and 1 pc
+// apply as ~18 separate vector passes.  Here one iteration is three kernels:
+//   K2  ap = A p          fused with  p.Ap  -> alpha = rz / pAp          (IndefiniteMatrix test)
+//   K3  x += a p ; r -= a ap ; z = D^-1 r   fused with  r.z  and  ||r||^2 (or ||z||^2)
+//       -> history push, Convergence::check, beta = rz_new/rz            (IndefinitePreconditioner test)
+//   K4  p = z + beta p
+// All scalars stay in the device control block; the host replays a CUDA graph of several
+// iterations and polls `done` once per replay.  Kernels of iterations issued after convergence
+// exit immediately, so the reported iteration count is exactly the reference's.
+#include <cstring>
+#include <cstddef>
+#include <algorithm>
+#include "kb_objects.h"
+#include "kb_spmv.cuh"
+#include "kb_epilogue.cuh"
+
+// ---- scalar epilogues (device, single thread) ------------------------------------------------
+struct PcgInitFin {   // pcg.rs:132-146
+    KbCtl* ctl;
+    __device__ void operator()(const double* s) const {
+        KbCtl* c = ctl;
+        c->rz = s[0];
+        c->res0 = sqrt(fabs(s[0]));
+        double nrm = (c->norm_type == KB_NORM_PRECONDITIONED || c->norm_type == KB_NORM_UNPRECONDITIONED) ? sqrt(s[1])
+                     : (c->norm_type == KB_NORM_NATURAL ? sqrt(fabs(s[0])) : 0.0);
+        c->res = nrm;
+        if (c->hist_len < c->hist_cap) c->hist[c->hist_len] = nrm;
+        c->hist_len += 1;
+        if (c->max_iters == 0) { c->res = c->res0; c->done = 1; }   // loop body never runs: stats = {0,res0,false}
+    }
+};
+struct PcgApFin {     // pcg.rs:151-173
+    KbCtl* ctl;
+    __device__ void operator()(const double* s) const {
+        KbCtl* c = ctl;
+        c->pAp = s[0];
+        if (s[0] <= 0.0) { c->status = KB_INDEFINITE_MATRIX; c->iter = c->iter + 1; c->converged = 0; c->done = 1; return; }
+        c->alpha = c->rz / s[0];
+    }
+};
+struct PcgUpdateFin { // pcg.rs:188-218
+    KbCtl* ctl;
+    __device__ void operator()(const double* s) const {
+        KbCtl* c = ctl;
+        const double rz_new = s[0];
+        double res = (c->norm_type == KB_NORM_PRECONDITIONED || c->norm_type == KB_NORM_UNPRECONDITIONED) ? sqrt(s[1])
+                     : (c->norm_type == KB_NORM_NATURAL ? sqrt(fabs(rz_new)) : 0.0);
+        const unsigned long long it = c->iter + 1;
+        c->iter = it;
+        c->res = res;
+        if (c->hist_len < c->hist_cap) c->hist[c->hist_len] = res;
+        c->hist_len += 1;
+        const double rel = res / c->res0;                       // Convergence::check (convergence.rs:18-34)
+        if (rel <= c->tol || it >= c->max_iters) { c->converged = 1; c->done = 1; return; }
+        const double beta = rz_new / c->rz;
+        if (beta < 0.0) { c->status = KB_INDEFINITE_PC; c->converged = 0; c->done = 1; return; }
+        c->beta = beta;
+        c->rz = rz_new;
+    }
+};
+
+// ---- fused vector passes ------------------------------------------------------------------------
+template <class Fin>
+struct PcgInitOp : KbRedBase {        // z = D^-1 r (or r) ; p = z ; r.z ; norm
+    static constexpr int NRED = 2;
+    const double* r; const double* inv; double* z; double* p; KbCtl* ctl; KbFinish<Fin> fin;
+    __device__ bool skip() const { return false; }
+    __device__ void pair(long long i, bool has1, double* red) const {
+        const int nt = ctl->norm_type;
+        if (has1) {
+            double2 rr = kb_ld2(r + i), zz;
+            if (inv) { double2 d = kb_ld2(inv + i); zz = make_double2(d.x * rr.x, d.y * rr.y); } else zz = rr;
+            kb_st2(z + i, zz); kb_st2(p + i, zz);
+            red[0] = rr.x * zz.x + rr.y * zz.y;
+            red[1] = nt == KB_NORM_PRECONDITIONED ? (zz.x * zz.x + zz.y * zz.y) : nt == KB_NORM_UNPRECONDITIONED ? (rr.x * rr.x + rr.y * rr.y) : 0.0;
+        } else {
+            double rr = r[i], zz = inv ? inv[i] * rr : rr;
+            z[i] = zz; p[i] = zz;
+            red[0] = rr * zz + 0.0;
+            red[1] = nt == KB_NORM_PRECONDITIONED ? (zz * zz + 0.0) : nt == KB_NORM_UNPRECONDITIONED ? (rr * rr + 0.0) : 0.0;
+        }
+    }
+    __device__ void finish(const double* s) const { fin(s); }
+};
+
+template <class Fin>
+struct PcgUpdateOp : KbRedBase {      // K3
+    static constexpr int NRED = 2;
+    double* x; const double* p; double* r; const double* ap; const double* inv; double* z; KbCtl* ctl; KbFinish<Fin> fin;
+    __device__ bool skip() const { return ctl->done != 0; }
+    __device__ void pair(long long i, bool has1, double* red) const {
+        const double alpha = ctl->alpha;
+        const int nt = ctl->norm_type;
+        if (has1) {
+            double2 xx = kb_ld2(x + i), pp = kb_ld2(p + i), rr = kb_ld2(r + i), aa = kb_ld2(ap + i), zz;
+            xx.x = xx.x + alpha * pp.x; xx.y = xx.y + alpha * pp.y;
+            rr.x = rr.x - alpha * aa.x; rr.y = rr.y - alpha * aa.y;
+            if (inv) { double2 d = kb_ld2(inv + i); zz = make_double2(d.x * rr.x, d.y * rr.y); } else zz = rr;
+            kb_st2(x + i, xx); kb_st2(r + i, rr); kb_st2(z + i, zz);
+            red[0] = rr.x * zz.x + rr.y * zz.y;
+            red[1] = nt == KB_NORM_PRECONDITIONED ? (zz.x * zz.x + zz.y * zz.y) : nt == KB_NORM_UNPRECONDITIONED ? (rr.x * rr.x + rr.y * rr.y) : 0.0;
+        } else {
+            double xx = x[i] + alpha * p[i];
+            double rr = r[i] - alpha * ap[i];
+            double zz = inv ? inv[i] * rr : rr;
+            x[i] = xx; r[i] = rr; z[i] = zz;
+            red[0] = rr * zz + 0.0;
+            red[1] = nt == KB_NORM_PRECONDITIONED ? (zz * zz + 0.0) : nt == KB_NORM_UNPRECONDITIONED ? (rr * rr + 0.0) : 0.0;
+        }
+    }
+    __device__ void finish(const double* s) const { fin(s); }
+};
+
+struct PcgXpayOp : KbRedBase {        // K4: p = z + beta p  (pcg.rs:215-217)
+    static constexpr int NRED = 0;
+    const double* z; double* p; KbCtl* ctl;
+    __device__ bool skip() const { return ctl->done != 0; }
+    __device__ void pair(long long i, bool has1, double*) const {
+        const double beta = ctl->beta;
+        if (has1) { double2 zz = kb_ld2(z + i), pp = kb_ld2(p + i); kb_st2(p + i, make_double2(zz.x + beta * pp.x, zz.y + beta * pp.y)); }
+        else p[i] = z[i] + beta * p[i];
+    }
+    __device__ void finish(const double*) const {}
+};
+
+// ---- workspace ----------------------------------------------------------------------------------
+struct KbPcgWs {
+    uint64_t n = 0, nx = 0;
+    double *x = nullptr, *r = nullptr, *z = nullptr, *p = nullptr, *ap = nullptr, *b = nullptr;
+    double* partials = nullptr; size_t pstride = 0;
+    double* slots = nullptr;          // dist: local sums / gathered sums
+    KbCtl* ctl = nullptr; KbCtl* h_ctl = nullptr;
+    double* hist = nullptr; uint64_t hist_cap = 0;
+    cudaGraphExec_t graph = nullptr; int graph_iters = 0; const kb_pc_s* graph_pc = nullptr; uint64_t graph_launches = 0;
+};
+void kb_pcg_ws_free(KbPcgWs* w) {
+    if (!w) return;
+    if (w->graph) cudaGraphExecDestroy(w->graph);
+    KB_FREE(w->x); KB_FREE(w->r); KB_FREE(w->z); KB_FREE(w->p); KB_FREE(w->ap); KB_FREE(w->b);
+    KB_FREE(w->partials); KB_FREE(w->slots); KB_FREE(w->ctl); KB_FREE(w->hist);
+    if (w->h_ctl) cudaFreeHost(w->h_ctl);
+    delete w;
+}
+static int pcg_ws_get(kb_csr_s* A, uint64_t hist_cap, KbPcgWs** out) {
+    KbPcgWs* w = A->pcg_ws;
+    if (!w) {
+        w = new KbPcgWs;
+        A->pcg_ws = w;
+        w->n = A->n; w->nx = A->ncols_local;
+        KB_TRY(kb_alloc(&w->x, w->nx + 2)); KB_TRY(kb_alloc(&w->p, w->nx + 2));
+        KB_TRY(kb_alloc(&w->r, w->n + 2)); KB_TRY(kb_alloc(&w->z, w->n + 2));
+        KB_TRY(kb_alloc(&w->ap, w->n + 2)); KB_TRY(kb_alloc(&w->b, w->n + 2));
+        w->pstride = (size_t)A->ntiles + 1;
+        KB_TRY(kb_alloc(&w->partials, 2 * w->pstride));
+        KB_TRY(kb_alloc(&w->slots, 64));
+        KB_TRY(kb_alloc(&w->ctl, 1));
+        KB_CUDA(cudaMallocHost((void**)&w->h_ctl, sizeof(KbCtl)));
+    }
+    if (hist_cap > w->hist_cap || !w->hist) {
+        KB_FREE(w->hist);
+        w->hist_cap = std::max<uint64_t>(hist_cap, 1);
+        KB_TRY(kb_alloc(&w->hist, w->hist_cap));
+    }
+    *out = w;
+    return KB_OK;
+}
+
+// ---- one iteration's launches ---------------------------------------------------------------------
+template <bool DIST>
+static int pcg_launch_iteration(kb_csr_s* A, const kb_pc_s* pc, KbPcgWs* w) {
+    kb_ctx_s* c = A->ctx;
+    const double* inv = pc ? pc->inv_diag : nullptr;
+    if (DIST) KB_TRY(kb_halo_exchange(A, w->p));
+    {   // K2
+        KbSpmvEpi<PcgApFin, 1> epi; epi.ctl = w->ctl; epi.fin.fin = PcgApFin{w->ctl}; epi.fin.slots = DIST ? w->slots : nullptr; epi.fin.nred = 1;
+        KB_TRY((kb_launch_spmv<KbSpmvEpi<PcgApFin, 1>, false>(A, w->p, w->ap, nullptr, w->p, w->partials, w->pstride, epi)));
+        if (DIST) KB_TRY((kb_finish_dist<PcgApFin>(c, PcgApFin{w->ctl}, w->ctl, w->slots, 1)));
+    }
+    {   // K3
+        PcgUpdateOp<PcgUpdateFin> op; op.n = (long long)w->n; op.partials = w->partials; op.pstride = w->pstride; op.ticket = c->ticket;
+        op.x = w->x; op.p = w->p; op.r = w->r; op.ap = w->ap; op.inv = inv; op.z = w->z; op.ctl = w->ctl;
+        op.fin.fin = PcgUpdateFin{w->ctl}; op.fin.slots = DIST ? w->slots : nullptr; op.fin.nred = 2;
+        { KbLaunch L(c, KB_K_PCG_UPDATE); kb_tile_kernel<<<A->ntiles, KB_THREADS, 0, c->stream>>>(op); }
+        KB_CUDA(cudaGetLastError());
+        if (DIST) KB_TRY((kb_finish_dist<PcgUpdateFin>(c, PcgUpdateFin{w->ctl}, w->ctl, w->slots, 2)));
+    }
+    {   // K4
+        PcgXpayOp op; op.n = (long long)w->n; op.partials = nullptr; op.pstride = 0; op.ticket = c->ticket;
+        op.z = w->z; op.p = w->p; op.ctl = w->ctl;
+        { KbLaunch L(c, KB_K_XPAY); kb_tile_kernel<<<A->ntiles, KB_THREADS, 0, c->stream>>>(op); }
+        KB_CUDA(cudaGetLastError());
+    }
+    return KB_OK;
+}
+
+static int pcg_iteration(kb_csr_s* A, const kb_pc_s* pc, KbPcgWs* w) {
+    return A->dist && A->ctx->size > 1 ? pcg_launch_iteration<true>(A, pc, w) : pcg_launch_iteration<false>(A, pc, w);
+}
+
+extern "C" int kb_pcg_solve(kb_csr A, kb_pc pc, const double* b, double* x, double tol, uint64_t max_iters, int norm_type,
+                            uint32_t flags, double* history, uint64_t hist_cap, uint64_t* hist_len, kb_stats* stats) {
+    if (!A || !b || !x || !stats) { kb_set_error("kb_pcg_solve: null argument"); return KB_SOLVE_ERROR; }
+    if (pc && pc->a != A) { kb_set_error("preconditioner was set up for a different operator"); return KB_SOLVE_ERROR; }
+    if (pc && pc->kind != KB_PC_JACOBI && pc->kind != KB_PC_ILU0) { kb_set_error("unsupported preconditioner"); return KB_UNSUPPORTED; }
+    if (norm_type < 0 || norm_type > 3) { kb_set_error("bad norm_type"); return KB_SOLVE_ERROR; }
+    kb_ctx_s* c = A->ctx;
+    KB_CUDA(cudaSetDevice(c->device));
+    const bool dev = (flags & KB_FLAG_DEVICE_PTRS) != 0;
+    const bool dist = A->dist && c->size > 1;
+    if (!history) hist_cap = 0;
+    KbPcgWs* w = nullptr;
+    KB_TRY(pcg_ws_get(A, hist_cap, &w));
+    memset(stats, 0, sizeof(*stats));
+    if (hist_len) *hist_len = 0;
+    if (A->n == 0 && !dist) { stats->converged = 0; return KB_OK; }
+    const bool jacobi_like = !pc || pc->kind == KB_PC_JACOBI;
+    if (!jacobi_like) { kb_set_error("kb_pcg_solve: only Jacobi (or no) preconditioning is fused on device"); return KB_UNSUPPORTED; }
+
+    KB_TRY(kb_upload_or_alias(c, b, w->b, w->n, dev));
+    KB_TRY(kb_upload_or_alias(c, x, w->x, w->n, dev));
+    // control block head
+    KbCtl* h = w->h_ctl;
+    memset(h, 0, offsetof(KbCtl, h));
+    h->max_iters = max_iters; h->tol = tol; h->norm_type = norm_type; h->hist = w->hist; h->hist_cap = hist_cap;
+    KB_CUDA(cudaMemcpyAsync(w->ctl, h, offsetof(KbCtl, h), cudaMemcpyHostToDevice, c->stream));
+
+    const bool profile = (flags & KB_FLAG_PROFILE) != 0;
+    const bool use_graph = !(flags & (KB_FLAG_NO_GRAPH | KB_FLAG_PROFILE));
+    const bool was_prof = c->profiling;
+    c->profiling = profile;
+    int st = KB_OK;
+    do {
+        // r = b - A x  (pcg.rs:119-124)
+        if (dist && (st = kb_halo_exchange(A, w->x)) != KB_OK) break;
+        {
+            KbSpmvEpi<PcgApFin, 0> epi; epi.ctl = nullptr; epi.fin.fin = PcgApFin{w->ctl}; epi.fin.slots = nullptr; epi.fin.nred = 0;
+            if ((st = kb_launch_spmv<KbSpmvEpi<PcgApFin, 0>, true>(A, w->x, w->r, w->b, nullptr, w->partials, w->pstride, epi)) != KB_OK) break;
+        }
+        {   // z, p, rz, res0, first history entry (pcg.rs:126-146)
+            PcgInitOp<PcgInitFin> op; op.n = (long long)w->n; op.partials = w->partials; op.pstride = w->pstride; op.ticket = c->ticket;
+            op.r = w->r; op.inv = pc ? pc->inv_diag : nullptr; op.z = w->z; op.p = w->p; op.ctl = w->ctl;
+            op.fin.fin = PcgInitFin{w->ctl}; op.fin.slots = dist ? w->slots : nullptr; op.fin.nred = 2;
+            { KbLaunch L(c, KB_K_INIT); kb_tile_kernel<<<A->ntiles, KB_THREADS, 0, c->stream>>>(op); }
+            if (cudaGetLastError() != cudaSuccess) { kb_set_error("pcg init launch failed"); st = KB_SOLVE_ERROR; break; }
+            if (dist && (st = kb_finish_dist<PcgInitFin>(c, PcgInitFin{w->ctl}, w->ctl, w->slots, 2)) != KB_OK) break;
+        }
+        // iterations per graph replay: ~2 ms of work, so the per-replay host poll is amortised
+        const double bytes_iter = 12.0 * (double)A->nnz + 108.0 * (double)A->n;
+        int B = (int)std::min<double>(64.0, std::max<double>(4.0, 2.0e-3 / (bytes_iter / 6.0e12 + 8.0e-6)));
+        if ((uint64_t)B > max_iters) B = (int)std::max<uint64_t>(max_iters, 1);
+        if (use_graph && (!w->graph || w->graph_pc != pc || w->graph_iters != B)) {
+            if (w->graph) { cudaGraphExecDestroy(w->graph); w->graph = nullptr; }
+            cudaGraph_t g = nullptr;
+            c->capturing = true; c->captured_launches = 0;
+            cudaError_t e = cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal);
+            if (e == cudaSuccess) {
+                for (int k = 0; k < B && st == KB_OK; ++k) st = pcg_iteration(A, pc, w);
+                e = cudaStreamEndCapture(c->stream, &g);
+            }
+            c->capturing = false;
+            if (st != KB_OK) { if (g) cudaGraphDestroy(g); break; }
+            if (e != cudaSuccess || !g) { kb_set_error("graph capture failed: %s", cudaGetErrorString(e)); st = KB_SOLVE_ERROR; break; }
+            e = cudaGraphInstantiate(&w->graph, g, 0);
+            cudaGraphDestroy(g);
+            if (e != cudaSuccess) { kb_set_error("graph instantiate failed: %s", cudaGetErrorString(e)); st = KB_SOLVE_ERROR; break; }
+            w->graph_pc = pc; w->graph_iters = B; w->graph_launches = c->captured_launches;
+        }
+        uint64_t issued = 0;
+        while (true) {
+            if (max_iters == 0) break;
+            if (use_graph) {
+                if (cudaGraphLaunch(w->graph, c->stream) != cudaSuccess) { kb_set_error("graph launch failed"); st = KB_SOLVE_ERROR; break; }
+                c->launches += w->graph_launches;
+            } else {
+                for (int k = 0; k < B && st == KB_OK; ++k) st = pcg_iteration(A, pc, w);
+                if (st != KB_OK) break;
+            }
+            issued += (uint64_t)B;
+            if (cudaMemcpyAsync(h, w->ctl, offsetof(KbCtl, rz), cudaMemcpyDeviceToHost, c->stream) != cudaSuccess ||
+                cudaStreamSynchronize(c->stream) != cudaSuccess) {
+                kb_set_error("pcg: device error during iterations: %s", cudaGetErrorString(cudaGetLastError())); st = KB_SOLVE_ERROR; break;
+            }
+            if (h->done || issued >= max_iters + (uint64_t)B) break;
+        }
+        if (st != KB_OK) break;
+        if (cudaMemcpyAsync(h, w->ctl, offsetof(KbCtl, h), cudaMemcpyDeviceToHost, c->stream) != cudaSuccess ||
+            cudaStreamSynchronize(c->stream) != cudaSuccess) { kb_set_error("pcg: readback failed"); st = KB_SOLVE_ERROR; break; }
+        stats->iterations = h->iter; stats->final_residual = h->res; stats->converged = h->converged; stats->breakdown = 0;
+        st = h->status;
+        uint64_t hl = std::min<uint64_t>(h->hist_len, hist_cap);
+        if (hist_len) *hist_len = h->hist_len;
+        if (hl && cudaMemcpyAsync(history, w->hist, hl * sizeof(double), cudaMemcpyDeviceToHost, c->stream) != cudaSuccess) { st = KB_SOLVE_ERROR; break; }
+        if (st == KB_OK) {   // x is written only on Ok (pcg.rs:203,220 vs :171,:212)
+            if (cudaMemcpyAsync(x, w->x, w->n * sizeof(double), dev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, c->stream) != cudaSuccess) {
+                kb_set_error("pcg: copy-out of x failed"); st = KB_SOLVE_ERROR; break;
+            }
+        } else if (st == KB_INDEFINITE_MATRIX) kb_set_error("indefinite matrix detected (p^T A p <= 0)");
+        else if (st == KB_INDEFINITE_PC) kb_set_error("indefinite preconditioner detected (beta < 0)");
+        if (cudaStreamSynchronize(c->stream) != cudaSuccess) { kb_set_error("pcg: final sync failed"); st = KB_SOLVE_ERROR; }
+    } while (0);
+    c->profiling = was_prof;
+    if (profile) kb_prof_collect(c);
+    return st;
+}
