@@ -2,9 +2,10 @@
 // C ABI (include/kryst_b200.h) that is not a Krylov driver.
 #include <cstdarg>
 #include <cstring>
+#include <cstdlib>
 #include <algorithm>
 #include "kb_objects.h"
-#include "kb_spmv.cuh"
+#include "kb_epilogue.cuh"
 
 // ---------------------------------------------------------------------------------------------
 // errors
@@ -175,6 +176,38 @@ static int upload_narrow(kb_ctx_s* c, const uint64_t* h_src, int* d_dst, size_t 
 
 int kb_csr_build_dist(kb_csr_s* A);   // kb_dist.cu: ghost list, column remap, halo plan
 
+// chunk table of the bulk-async SpMV (rows grouped so each group's nnz fit one shared-memory stage)
+static int build_chunk_table(kb_csr_s* A) {
+    kb_ctx_s* c = A->ctx;
+    if (getenv("KB_SPMV_KIND") && atoi(getenv("KB_SPMV_KIND")) == 0) return KB_OK;   // benchmarking knob: plain-load kernel
+    const int nt = A->ntiles;
+    int* d_flag = nullptr;
+    KB_TRY(kb_alloc(&A->tile_chunk, (size_t)nt + 1));
+    KB_TRY(kb_alloc(&d_flag, 1));
+    KB_CUDA(cudaMemsetAsync(d_flag, 0, sizeof(int), c->stream));
+    { KbLaunch L(c, KB_K_OTHER); kb_chunk_build<<<(nt + 127) / 128, 128, 0, c->stream>>>(A->row_ptr, (int)A->n, nt, A->tile_chunk, nullptr, nullptr, 0, d_flag); }
+    std::vector<int> cnt((size_t)nt + 1, 0);
+    int flag = 0;
+    KB_CUDA(cudaMemcpyAsync(cnt.data(), A->tile_chunk, nt * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    KB_CUDA(cudaMemcpyAsync(&flag, d_flag, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    KB_CUDA(cudaStreamSynchronize(c->stream));
+    cudaFree(d_flag);
+    if (flag) { KB_FREE(A->tile_chunk); return KB_OK; }   // some row exceeds a stage: keep the plain-load kernel
+    int acc = 0;
+    for (int t = 0; t < nt; ++t) { int k = cnt[t]; cnt[t] = acc; acc += k; }
+    cnt[nt] = acc;
+    A->nchunks = acc;
+    KB_CUDA(cudaMemcpyAsync(A->tile_chunk, cnt.data(), ((size_t)nt + 1) * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    KB_TRY(kb_alloc(&A->chunk_row, (size_t)acc + 1));
+    KB_TRY(kb_alloc(&A->chunk_nz, (size_t)acc + 1));
+    KB_TRY(kb_alloc(&d_flag, 1));
+    { KbLaunch L(c, KB_K_OTHER); kb_chunk_build<<<(nt + 127) / 128, 128, 0, c->stream>>>(A->row_ptr, (int)A->n, nt, A->tile_chunk, A->chunk_row, A->chunk_nz, 1, d_flag); }
+    KB_CUDA(cudaStreamSynchronize(c->stream));
+    cudaFree(d_flag);
+    A->kind = 2;
+    return KB_OK;
+}
+
 static int csr_create_common(kb_ctx c, uint64_t nrows, uint64_t ncols_global, bool dist, uint64_t n_global, uint64_t lo,
                              uint64_t hi, const uint64_t* row_ptr, const uint64_t* col_idx, const double* vals, kb_csr* out) {
     *out = nullptr;
@@ -195,7 +228,8 @@ static int csr_create_common(kb_ctx c, uint64_t nrows, uint64_t ncols_global, bo
     int* d_err = nullptr;
     unsigned long long* d_stats = nullptr;   // [0] first_bad, [1..6] hist, [7] maxlen
     do {
-        if ((st = kb_alloc(&A->row_ptr, nrows + 1)) != KB_OK) break;
+        if ((st = kb_alloc(&A->row_ptr, nrows + 1 + 8)) != KB_OK) break;
+        cudaMemsetAsync(A->row_ptr, 0, (nrows + 9) * sizeof(int), c->stream);
         if ((st = kb_alloc(&A->col, nnz + 8)) != KB_OK) break;
         if ((st = kb_alloc(&A->vals, nnz + 8)) != KB_OK) break;
         if ((st = kb_alloc(&d_err, 1)) != KB_OK) break;
@@ -239,6 +273,7 @@ static int csr_create_common(kb_ctx c, uint64_t nrows, uint64_t ncols_global, bo
             A->vec = mean > 256 ? 32 : mean > 128 ? 16 : 8;
         }
         if (dist && (st = kb_csr_build_dist(A)) != KB_OK) break;
+        if (A->kind == 0 && nrows && (st = build_chunk_table(A)) != KB_OK) break;
     } while (0);
     if (d_err) cudaFree(d_err);
     if (d_stats) cudaFree(d_stats);
@@ -275,6 +310,7 @@ extern "C" int kb_csr_destroy(kb_csr A) {
     kb_gmres_ws_free(A->gmres_ws);
     kb_halo_free(A->halo);
     KB_FREE(A->row_ptr); KB_FREE(A->col); KB_FREE(A->vals); KB_FREE(A->ghosts);
+    KB_FREE(A->tile_chunk); KB_FREE(A->chunk_row); KB_FREE(A->chunk_nz);
     KB_FREE(A->x_tmp); KB_FREE(A->y_tmp);
     delete A;
     return KB_OK;
@@ -295,19 +331,7 @@ extern "C" int kb_csr_get_ghosts(kb_csr A, uint64_t* out) {
 // MatVec::matvec
 // ---------------------------------------------------------------------------------------------
 int kb_csr_spmv_plain(kb_csr_s* A, const double* d_x, double* d_y) {
-    if (A->n == 0) return KB_OK;
-    kb_ctx_s* c = A->ctx;
-    KbSpmvArgs a{};
-    a.row_ptr = A->row_ptr; a.col = A->col; a.vals = A->vals; a.x = d_x; a.y = d_y; a.b = nullptr; a.w = nullptr;
-    a.n = (int)A->n; a.tile0 = 0; a.ntiles_total = A->ntiles; a.tile_list = nullptr; a.finalize = 0;
-    a.partials = nullptr; a.pstride = 0; a.ticket = c->ticket;
-    KbLaunch L(c, KB_K_SPMV);
-    if (A->kind == 0) kb_spmv_stream<KbEpiNone, false><<<A->ntiles, KB_THREADS, 0, c->stream>>>(a, KbEpiNone{});
-    else if (A->vec == 8) kb_spmv_vector<KbEpiNone, false, 8><<<A->ntiles, KB_THREADS, 0, c->stream>>>(a, KbEpiNone{});
-    else if (A->vec == 16) kb_spmv_vector<KbEpiNone, false, 16><<<A->ntiles, KB_THREADS, 0, c->stream>>>(a, KbEpiNone{});
-    else kb_spmv_vector<KbEpiNone, false, 32><<<A->ntiles, KB_THREADS, 0, c->stream>>>(a, KbEpiNone{});
-    KB_CUDA(cudaGetLastError());
-    return KB_OK;
+    return kb_launch_spmv<KbEpiNone, false>(A, d_x, d_y, nullptr, nullptr, nullptr, 0, KbEpiNone{});
 }
 
 extern "C" int kb_csr_matvec_device(kb_csr A, const double* d_x, double* d_y) {

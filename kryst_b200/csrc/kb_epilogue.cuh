@@ -5,8 +5,10 @@
 // Row-block shards: the last block stores its local sums to `slots`; they are all-gathered over
 // NVLink, summed in rank order (deterministic) and the same epilogue runs in a 1-thread kernel.
 #pragma once
+#include <algorithm>
 #include "kb_objects.h"
 #include "kb_spmv.cuh"
+#include "kb_spmv_bulk.cuh"
 
 template <class Fin>
 struct KbFinish {
@@ -51,8 +53,21 @@ static int kb_launch_spmv(kb_csr_s* A, const double* x, double* y, const double*
     kb_ctx_s* c = A->ctx;
     KbSpmvArgs a{};
     a.row_ptr = A->row_ptr; a.col = A->col; a.vals = A->vals; a.x = x; a.y = y; a.b = b; a.w = w;
-    a.n = (int)A->n; a.tile0 = 0; a.ntiles_total = A->ntiles; a.tile_list = nullptr; a.finalize = 1;
+    a.n = (int)A->n; a.tile0 = 0; a.ntiles_launch = A->ntiles; a.ntiles_total = A->ntiles; a.tile_list = nullptr; a.finalize = 1;
     a.partials = partials; a.pstride = pstride; a.ticket = c->ticket;
+    if (A->kind == 2) {
+        auto kfn = kb_spmv_bulk<Epi, RESID>;
+        if (!c->configured.count((const void*)kfn)) {
+            KB_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(KbBulkSmem)));
+            c->configured.insert((const void*)kfn);
+        }
+        KbChunkTable tb{A->tile_chunk, A->chunk_row, A->chunk_nz};
+        const int grid = std::min(2 * c->sm_count, A->ntiles);
+        KbLaunch L(c, KB_K_SPMV);
+        kfn<<<grid, KB_BULK_THREADS, sizeof(KbBulkSmem), c->stream>>>(a, tb, epi);
+        KB_CUDA(cudaGetLastError());
+        return KB_OK;
+    }
     KbLaunch L(c, KB_K_SPMV);
     if (A->kind == 0) kb_spmv_stream<Epi, RESID><<<A->ntiles, KB_THREADS, 0, c->stream>>>(a, epi);
     else if (A->vec == 8) kb_spmv_vector<Epi, RESID, 8><<<A->ntiles, KB_THREADS, 0, c->stream>>>(a, epi);

@@ -17,6 +17,7 @@
 #include <cstdio>
 #include <string>
 #include <vector>
+#include <set>
 #include "kryst_b200.h"
 
 #define KB_TILE 512
@@ -100,6 +101,7 @@ struct kb_ctx_s {
     double* comm_buf = nullptr;          // device scratch for all-gathered partial scalars
     double* host_scalar = nullptr;       // pinned
     int live_handles = 0;
+    std::set<const void*> configured;    // kernels whose dynamic-smem attribute has been raised
 };
 
 // RAII launch bookkeeping: counts the launch and (in profile mode) brackets it with events.

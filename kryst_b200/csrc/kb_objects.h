@@ -17,7 +17,11 @@ struct kb_csr_s {
     int* col = nullptr;          // local column ids, stored order == ascending GLOBAL column
     double* vals = nullptr;
     int ntiles = 0;
-    int kind = 0;                // 0 CSR-stream, 1 vector-per-row
+    int kind = 0;                // 0 CSR-stream (plain loads), 1 vector-per-row, 2 bulk-async staged CSR-stream
+    int* tile_chunk = nullptr;   // kind 2: chunk table (see kb_spmv_bulk.cuh)
+    int* chunk_row = nullptr;
+    int* chunk_nz = nullptr;
+    int nchunks = 0;
     int vec = 8;                 // sub-warp width of the vector kernel
     uint64_t max_row_len = 0;
     uint64_t hist[6] = {0, 0, 0, 0, 0, 0};   // row-length histogram: <=8,<=16,<=32,<=64,<=128,>128

@@ -29,6 +29,7 @@ struct KbSpmvArgs {
     const double* __restrict__ w;     // NDOT>=1: <w, y>
     int n;
     int tile0;                        // first tile handled by this launch
+    int ntiles_launch;                // number of tiles handled by this launch
     int ntiles_total;                 // total tiles of the vector (level-2 length)
     const int* __restrict__ tile_list;// optional indirection (boundary / interior tile sets)
     int finalize;                     // 1: last block of this launch reduces level 2 and runs the epilogue
