@@ -1,7 +1,7 @@
 // kb_internal.cuh — shared internals of libkryst_b200 (not part of the ABI).
 //
 // Numerical contract: every kernel performs the *same sequence of IEEE f64 operations* as
-// the CPU oracle (oracle/kryst_oracle.cpp): separate mul and add (this library MUST be
+// the CPU oracle (see oracle/): separate mul and add (this library MUST be
 // compiled with -fmad=false), ascending-column row sums, and the canonical reduction tree R:
 //   level 1: tiles of 512 elements, lane l of 256 holds e(2l)+e(2l+1); 32-lane xor
 //            butterflies (16,8,4,2,1); the 8 warp sums added sequentially;
