@@ -1,0 +1,71 @@
+// kb_driver.cuh — host loop shared by the Krylov drivers: capture B iterations into a CUDA graph once,
+// replay it, and poll the device control block's `done` flag once per replay.  Kernels issued after
+// `done` is set exit immediately, so over-issued iterations change nothing.
+#pragma once
+#include <cstddef>
+#include "kb_objects.h"
+
+struct KbGraphCache {
+    cudaGraphExec_t exec = nullptr;
+    uint64_t key = 0;
+    int iters = 0;
+    uint64_t launches = 0;
+    void reset() {
+        if (exec) cudaGraphExecDestroy(exec);
+        exec = nullptr; key = 0; iters = 0; launches = 0;
+    }
+};
+
+// launch_iter(): enqueue one iteration's kernels on c->stream, return kb_status.
+// units_cap: upper bound on useful iterations (max_iters); the loop stops when done or after the cap.
+template <class F>
+static int kb_run_iterations(kb_ctx_s* c, KbGraphCache* gc, uint64_t key, int B, uint64_t units_cap, bool use_graph,
+                             KbCtl* d_ctl, KbCtl* h_ctl, F&& launch_iter) {
+    if (units_cap == 0) return KB_OK;
+    if (B < 1) B = 1;
+    if ((uint64_t)B > units_cap) B = (int)units_cap;
+    if (use_graph && (!gc->exec || gc->key != key || gc->iters != B)) {
+        gc->reset();
+        cudaGraph_t g = nullptr;
+        int st = KB_OK;
+        c->capturing = true; c->captured_launches = 0;
+        cudaError_t e = cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal);
+        if (e == cudaSuccess) {
+            for (int k = 0; k < B && st == KB_OK; ++k) st = launch_iter();
+            cudaError_t e2 = cudaStreamEndCapture(c->stream, &g);
+            if (e2 != cudaSuccess) e = e2;
+        }
+        c->capturing = false;
+        if (st != KB_OK) { if (g) cudaGraphDestroy(g); return st; }
+        if (e != cudaSuccess || !g) { kb_set_error("CUDA graph capture failed: %s", cudaGetErrorString(e)); return KB_SOLVE_ERROR; }
+        e = cudaGraphInstantiate(&gc->exec, g, 0);
+        cudaGraphDestroy(g);
+        if (e != cudaSuccess) { gc->exec = nullptr; kb_set_error("CUDA graph instantiate failed: %s", cudaGetErrorString(e)); return KB_SOLVE_ERROR; }
+        gc->key = key; gc->iters = B; gc->launches = c->captured_launches;
+    }
+    uint64_t issued = 0;
+    while (true) {
+        if (use_graph) {
+            cudaError_t e = cudaGraphLaunch(gc->exec, c->stream);
+            if (e != cudaSuccess) { kb_set_error("CUDA graph launch failed: %s", cudaGetErrorString(e)); return KB_SOLVE_ERROR; }
+            c->launches += gc->launches;
+        } else {
+            for (int k = 0; k < B; ++k) KB_TRY(launch_iter());
+        }
+        issued += (uint64_t)B;
+        if (cudaMemcpyAsync(h_ctl, d_ctl, offsetof(KbCtl, rz), cudaMemcpyDeviceToHost, c->stream) != cudaSuccess ||
+            cudaStreamSynchronize(c->stream) != cudaSuccess) {
+            kb_set_error("device error during Krylov iterations: %s", cudaGetErrorString(cudaGetLastError()));
+            return KB_SOLVE_ERROR;
+        }
+        if (h_ctl->done || issued >= units_cap + (uint64_t)B) break;
+    }
+    return KB_OK;
+}
+
+// iterations per replay so that one replay is ~2 ms of work (the host poll is then <1 %)
+static inline int kb_batch_size(double bytes_per_iter, int kernels_per_iter) {
+    double t = bytes_per_iter / 6.0e12 + 3.0e-6 * kernels_per_iter;
+    double b = 2.0e-3 / t;
+    return (int)(b < 4.0 ? 4.0 : (b > 64.0 ? 64.0 : b));
+}

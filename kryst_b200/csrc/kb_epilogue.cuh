@@ -21,26 +21,27 @@ struct KbFinish {
     }
 };
 
-template <class Fin, int ND>
+template <class Fin, bool WD, bool YD>
 struct KbSpmvEpi {
-    static constexpr int NDOT = ND;
+    static constexpr bool WDOT = WD, YDOT = YD;
     KbCtl* ctl;          // may be null (never skip)
+    int early_skip = 0;  // also skip when ctl->early is set (BiCGStab's second SpMV)
     KbFinish<Fin> fin;
-    __device__ bool skip() const { return ctl != nullptr && ctl->done != 0; }
+    __device__ bool skip() const { return ctl != nullptr && (ctl->done != 0 || (early_skip && ctl->early != 0)); }
     __device__ void finish(const double* s) const { fin(s); }
 };
 
 template <class Fin>
-__global__ void kb_fin_kernel(Fin fin, KbCtl* ctl, const double* sums) {
-    if (ctl->done) return;
+__global__ void kb_fin_kernel(Fin fin, KbCtl* ctl, const double* sums, int skip_early) {
+    if (ctl->done || (skip_early && ctl->early)) return;
     fin(sums);
 }
 
 template <class Fin>
-static int kb_finish_dist(kb_ctx_s* c, Fin fin, KbCtl* ctl, double* slots, int nred) {
+static int kb_finish_dist(kb_ctx_s* c, Fin fin, KbCtl* ctl, double* slots, int nred, bool skip_early = false) {
     KB_TRY(kb_allreduce_slots(c, slots, nred));
     KbLaunch L(c, KB_K_SMALL);
-    kb_fin_kernel<Fin><<<1, 1, 0, c->stream>>>(fin, ctl, slots);
+    kb_fin_kernel<Fin><<<1, 1, 0, c->stream>>>(fin, ctl, slots, skip_early ? 1 : 0);
     KB_CUDA(cudaGetLastError());
     return KB_OK;
 }

@@ -62,6 +62,7 @@ struct KbCtl {
     // --- BiCGStab (bicgstab.rs:69-293)
     double rho, rho_prev, omega, omega_prev, alpha_den, thr, rnorm, vv;
     int textbook;
+    int early;                 // ||s|| <= tol: finish with x += alpha p (bicgstab.rs:189-206)
     // --- GMRES (gmres.rs:216-402)
     int j;                     // inner index of the current Arnoldi step
     int m;                     // columns accumulated in this cycle (for back-substitution)

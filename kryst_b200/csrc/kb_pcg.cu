@@ -15,6 +15,7 @@
 #include "kb_objects.h"
 #include "kb_spmv.cuh"
 #include "kb_epilogue.cuh"
+#include "kb_driver.cuh"
 
 // ---- scalar epilogues (device, single thread) ------------------------------------------------
 struct PcgInitFin {   // pcg.rs:132-146
@@ -133,11 +134,11 @@ struct KbPcgWs {
     double* slots = nullptr;          // dist: local sums / gathered sums
     KbCtl* ctl = nullptr; KbCtl* h_ctl = nullptr;
     double* hist = nullptr; uint64_t hist_cap = 0;
-    cudaGraphExec_t graph = nullptr; int graph_iters = 0; const kb_pc_s* graph_pc = nullptr; uint64_t graph_launches = 0;
+    KbGraphCache gc;
 };
 void kb_pcg_ws_free(KbPcgWs* w) {
     if (!w) return;
-    if (w->graph) cudaGraphExecDestroy(w->graph);
+    w->gc.reset();
     KB_FREE(w->x); KB_FREE(w->r); KB_FREE(w->z); KB_FREE(w->p); KB_FREE(w->ap); KB_FREE(w->b);
     KB_FREE(w->partials); KB_FREE(w->slots); KB_FREE(w->ctl); KB_FREE(w->hist);
     if (w->h_ctl) cudaFreeHost(w->h_ctl);
@@ -174,8 +175,8 @@ static int pcg_launch_iteration(kb_csr_s* A, const kb_pc_s* pc, KbPcgWs* w) {
     const double* inv = pc ? pc->inv_diag : nullptr;
     if (DIST) KB_TRY(kb_halo_exchange(A, w->p));
     {   // K2
-        KbSpmvEpi<PcgApFin, 1> epi; epi.ctl = w->ctl; epi.fin.fin = PcgApFin{w->ctl}; epi.fin.slots = DIST ? w->slots : nullptr; epi.fin.nred = 1;
-        KB_TRY((kb_launch_spmv<KbSpmvEpi<PcgApFin, 1>, false>(A, w->p, w->ap, nullptr, w->p, w->partials, w->pstride, epi)));
+        KbSpmvEpi<PcgApFin, true, false> epi; epi.ctl = w->ctl; epi.fin.fin = PcgApFin{w->ctl}; epi.fin.slots = DIST ? w->slots : nullptr; epi.fin.nred = 1;
+        KB_TRY((kb_launch_spmv<KbSpmvEpi<PcgApFin, true, false>, false>(A, w->p, w->ap, nullptr, w->p, w->partials, w->pstride, epi)));
         if (DIST) KB_TRY((kb_finish_dist<PcgApFin>(c, PcgApFin{w->ctl}, w->ctl, w->slots, 1)));
     }
     {   // K3
@@ -235,8 +236,8 @@ extern "C" int kb_pcg_solve(kb_csr A, kb_pc pc, const double* b, double* x, doub
         // r = b - A x  (pcg.rs:119-124)
         if (dist && (st = kb_halo_exchange(A, w->x)) != KB_OK) break;
         {
-            KbSpmvEpi<PcgApFin, 0> epi; epi.ctl = nullptr; epi.fin.fin = PcgApFin{w->ctl}; epi.fin.slots = nullptr; epi.fin.nred = 0;
-            if ((st = kb_launch_spmv<KbSpmvEpi<PcgApFin, 0>, true>(A, w->x, w->r, w->b, nullptr, w->partials, w->pstride, epi)) != KB_OK) break;
+            KbSpmvEpi<PcgApFin, false, false> epi; epi.ctl = nullptr; epi.fin.fin = PcgApFin{w->ctl}; epi.fin.slots = nullptr; epi.fin.nred = 0;
+            if ((st = kb_launch_spmv<KbSpmvEpi<PcgApFin, false, false>, true>(A, w->x, w->r, w->b, nullptr, w->partials, w->pstride, epi)) != KB_OK) break;
         }
         {   // z, p, rz, res0, first history entry (pcg.rs:126-146)
             PcgInitOp<PcgInitFin> op; op.n = (long long)w->n; op.partials = w->partials; op.pstride = w->pstride; op.ticket = c->ticket;
@@ -247,43 +248,9 @@ extern "C" int kb_pcg_solve(kb_csr A, kb_pc pc, const double* b, double* x, doub
             if (dist && (st = kb_finish_dist<PcgInitFin>(c, PcgInitFin{w->ctl}, w->ctl, w->slots, 2)) != KB_OK) break;
         }
         // iterations per graph replay: ~2 ms of work, so the per-replay host poll is amortised
-        const double bytes_iter = 12.0 * (double)A->nnz + 108.0 * (double)A->n;
-        int B = (int)std::min<double>(64.0, std::max<double>(4.0, 2.0e-3 / (bytes_iter / 6.0e12 + 8.0e-6)));
-        if ((uint64_t)B > max_iters) B = (int)std::max<uint64_t>(max_iters, 1);
-        if (use_graph && (!w->graph || w->graph_pc != pc || w->graph_iters != B)) {
-            if (w->graph) { cudaGraphExecDestroy(w->graph); w->graph = nullptr; }
-            cudaGraph_t g = nullptr;
-            c->capturing = true; c->captured_launches = 0;
-            cudaError_t e = cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal);
-            if (e == cudaSuccess) {
-                for (int k = 0; k < B && st == KB_OK; ++k) st = pcg_iteration(A, pc, w);
-                e = cudaStreamEndCapture(c->stream, &g);
-            }
-            c->capturing = false;
-            if (st != KB_OK) { if (g) cudaGraphDestroy(g); break; }
-            if (e != cudaSuccess || !g) { kb_set_error("graph capture failed: %s", cudaGetErrorString(e)); st = KB_SOLVE_ERROR; break; }
-            e = cudaGraphInstantiate(&w->graph, g, 0);
-            cudaGraphDestroy(g);
-            if (e != cudaSuccess) { kb_set_error("graph instantiate failed: %s", cudaGetErrorString(e)); st = KB_SOLVE_ERROR; break; }
-            w->graph_pc = pc; w->graph_iters = B; w->graph_launches = c->captured_launches;
-        }
-        uint64_t issued = 0;
-        while (true) {
-            if (max_iters == 0) break;
-            if (use_graph) {
-                if (cudaGraphLaunch(w->graph, c->stream) != cudaSuccess) { kb_set_error("graph launch failed"); st = KB_SOLVE_ERROR; break; }
-                c->launches += w->graph_launches;
-            } else {
-                for (int k = 0; k < B && st == KB_OK; ++k) st = pcg_iteration(A, pc, w);
-                if (st != KB_OK) break;
-            }
-            issued += (uint64_t)B;
-            if (cudaMemcpyAsync(h, w->ctl, offsetof(KbCtl, rz), cudaMemcpyDeviceToHost, c->stream) != cudaSuccess ||
-                cudaStreamSynchronize(c->stream) != cudaSuccess) {
-                kb_set_error("pcg: device error during iterations: %s", cudaGetErrorString(cudaGetLastError())); st = KB_SOLVE_ERROR; break;
-            }
-            if (h->done || issued >= max_iters + (uint64_t)B) break;
-        }
+        const int B = kb_batch_size(12.0 * (double)A->nnz + 108.0 * (double)A->n, 3);
+        st = kb_run_iterations(c, &w->gc, (uint64_t)(uintptr_t)pc + 1, B, max_iters, use_graph, w->ctl, h,
+                               [&]() { return pcg_iteration(A, pc, w); });
         if (st != KB_OK) break;
         if (cudaMemcpyAsync(h, w->ctl, offsetof(KbCtl, h), cudaMemcpyDeviceToHost, c->stream) != cudaSuccess ||
             cudaStreamSynchronize(c->stream) != cudaSuccess) { kb_set_error("pcg: readback failed"); st = KB_SOLVE_ERROR; break; }

@@ -38,12 +38,14 @@ struct KbSpmvArgs {
     unsigned* ticket;
 };
 
-// Epi: struct with static constexpr int NDOT; __device__ bool skip() const; __device__ void finish(const double* sums) const
+// Epi: struct with static constexpr bool WDOT, YDOT (slot order: <w,y> then <y,y>); __device__ bool skip() const; __device__ void finish(const double* sums) const
 template <class Epi, bool RESID>
 __global__ void __launch_bounds__(KB_THREADS) kb_spmv_stream(KbSpmvArgs a, Epi epi) {
     if (epi.skip()) return;
-    constexpr int NDOT = Epi::NDOT;
+    constexpr bool WD = Epi::WDOT, YD = Epi::YDOT;      // fused <w,y> and/or <y,y>
+    constexpr int NDOT = (WD ? 1 : 0) + (YD ? 1 : 0);
     constexpr int ND = NDOT > 0 ? NDOT : 1;
+    constexpr int YS = WD ? 1 : 0;                      // slot of <y,y>
     __shared__ int s_rp[KB_TILE + 1];
     __shared__ double s_prod[KB_SPMV_CAP];
     __shared__ double s_d[ND][KB_TILE];
@@ -91,8 +93,8 @@ __global__ void __launch_bounds__(KB_THREADS) kb_spmv_stream(KbSpmvArgs a, Epi e
                 const int r = r0 + rs;
                 double yv = RESID ? (a.b[r] - s) : s;
                 a.y[r] = yv;
-                if constexpr (NDOT >= 1) s_d[0][rs] = a.w[r] * yv;
-                if constexpr (NDOT >= 2) s_d[1][rs] = yv * yv;
+                if constexpr (WD) s_d[0][rs] = a.w[r] * yv;
+                if constexpr (YD) s_d[YS][rs] = yv * yv;
             }
             rs = rs + 1;
             continue;
@@ -115,8 +117,8 @@ __global__ void __launch_bounds__(KB_THREADS) kb_spmv_stream(KbSpmvArgs a, Epi e
             const int r = r0 + t;
             double yv = RESID ? (a.b[r] - s) : s;
             a.y[r] = yv;
-            if constexpr (NDOT >= 1) s_d[0][t] = a.w[r] * yv;
-            if constexpr (NDOT >= 2) s_d[1][t] = yv * yv;
+            if constexpr (WD) s_d[0][t] = a.w[r] * yv;
+            if constexpr (YD) s_d[YS][t] = yv * yv;
         }
         __syncthreads();
         rs = re;
@@ -150,8 +152,10 @@ __global__ void __launch_bounds__(KB_THREADS) kb_spmv_stream(KbSpmvArgs a, Epi e
 template <class Epi, bool RESID, int VEC>
 __global__ void __launch_bounds__(KB_THREADS) kb_spmv_vector(KbSpmvArgs a, Epi epi) {
     if (epi.skip()) return;
-    constexpr int NDOT = Epi::NDOT;
+    constexpr bool WD = Epi::WDOT, YD = Epi::YDOT;      // fused <w,y> and/or <y,y>
+    constexpr int NDOT = (WD ? 1 : 0) + (YD ? 1 : 0);
     constexpr int ND = NDOT > 0 ? NDOT : 1;
+    constexpr int YS = WD ? 1 : 0;                      // slot of <y,y>
     __shared__ double s_d[ND][KB_TILE];
     __shared__ double s_red[ND * 8];
     __shared__ int sflag;
@@ -178,8 +182,8 @@ __global__ void __launch_bounds__(KB_THREADS) kb_spmv_vector(KbSpmvArgs a, Epi e
         if (sl == 0) {
             double yv = RESID ? (a.b[r] - s) : s;
             a.y[r] = yv;
-            if constexpr (NDOT >= 1) s_d[0][t] = a.w[r] * yv;
-            if constexpr (NDOT >= 2) s_d[1][t] = yv * yv;
+            if constexpr (WD) s_d[0][t] = a.w[r] * yv;
+            if constexpr (YD) s_d[YS][t] = yv * yv;
         }
     }
     if constexpr (NDOT > 0) {
@@ -203,7 +207,7 @@ __global__ void __launch_bounds__(KB_THREADS) kb_spmv_vector(KbSpmvArgs a, Epi e
 
 // Plain y = A x epilogue (MatVec::matvec)
 struct KbEpiNone {
-    static constexpr int NDOT = 0;
+    static constexpr bool WDOT = false, YDOT = false;
     __device__ bool skip() const { return false; }
     __device__ void finish(const double*) const {}
 };

@@ -110,8 +110,10 @@ struct KbChunkTable {
 template <class Epi, bool RESID>
 __global__ void __launch_bounds__(KB_BULK_THREADS, 2) kb_spmv_bulk(KbSpmvArgs a, KbChunkTable tb, Epi epi) {
     if (epi.skip()) return;
-    constexpr int NDOT = Epi::NDOT;
+    constexpr bool WD = Epi::WDOT, YD = Epi::YDOT;      // fused <w,y> and/or <y,y>
+    constexpr int NDOT = (WD ? 1 : 0) + (YD ? 1 : 0);
     constexpr int ND = NDOT > 0 ? NDOT : 1;
+    constexpr int YS = WD ? 1 : 0;                      // slot of <y,y>
     extern __shared__ __align__(128) unsigned char kb_smem_raw[];
     KbBulkSmem& S = *reinterpret_cast<KbBulkSmem*>(kb_smem_raw);
     const int tid = threadIdx.x;
@@ -196,14 +198,14 @@ __global__ void __launch_bounds__(KB_BULK_THREADS, 2) kb_spmv_bulk(KbSpmvArgs a,
             if (hA) {
                 double yv = RESID ? (a.b[rA] - sA) : sA;
                 a.y[rA] = yv;
-                if constexpr (NDOT >= 1) S.d[0][rA - r0] = a.w[rA] * yv;
-                if constexpr (NDOT >= 2) S.d[1][rA - r0] = yv * yv;
+                if constexpr (WD) S.d[0][rA - r0] = a.w[rA] * yv;
+                if constexpr (YD) S.d[YS][rA - r0] = yv * yv;
             }
             if (hB) {
                 double yv = RESID ? (a.b[rB] - sB) : sB;
                 a.y[rB] = yv;
-                if constexpr (NDOT >= 1) S.d[0][rB - r0] = a.w[rB] * yv;
-                if constexpr (NDOT >= 2) S.d[1][rB - r0] = yv * yv;
+                if constexpr (WD) S.d[0][rB - r0] = a.w[rB] * yv;
+                if constexpr (YD) S.d[YS][rB - r0] = yv * yv;
             }
         } while (!last);
         if constexpr (NDOT > 0) {
