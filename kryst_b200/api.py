@@ -329,10 +329,13 @@ class _Pc:
         self.close()
         h = C.c_void_p()
         st = getattr(_ffi.lib(), self._create)(a.handle, C.byref(h))
-        if st == 5:
+        if st != 0:
+            msg = _ffi.last_error()
             row = int(_ffi.lib().kb_pc_bad_row(h)) if h else 0
-            _check(st, row)
-        _check(st)
+            if h:
+                _ffi.lib().kb_pc_destroy(h)
+            cls = _ERRORS.get(st, SolveError)
+            raise ZeroPivot(msg, row) if cls is ZeroPivot else cls(msg)
         self._h, self._a = h, a
         return self
 

@@ -245,7 +245,7 @@ static int bicg_iteration(kb_csr_s* A, kb_pc_s* pc, KbBicgWs* w, int mode, bool 
     }
     {   // Kt (skipped on early exit)
         if (dist) KB_TRY(kb_halo_exchange(A, sh));
-        KbSpmvEpi<BicgTFin, true, true> epi; epi.ctl = w->ctl; epi.early_skip = 1; epi.fin.fin = BicgTFin{w->ctl}; epi.fin.slots = slots; epi.fin.nred = 2;
+        KbSpmvEpi<BicgTFin, true, true> epi; epi.ctl = w->ctl; epi.skip_mask = 1; epi.fin.fin = BicgTFin{w->ctl}; epi.fin.slots = slots; epi.fin.nred = 2;
         KB_TRY((kb_launch_spmv<KbSpmvEpi<BicgTFin, true, true>, false>(A, sh, w->t, nullptr, w->s, w->partials, w->pstride, epi)));
         if (dist) KB_TRY((kb_finish_dist<BicgTFin>(c, BicgTFin{w->ctl}, w->ctl, w->slots, 2, true)));
     }

@@ -421,8 +421,8 @@ __global__ void k_jacobi_setup(const int* __restrict__ rp, const int* __restrict
 }
 struct JacobiApplyOp : KbRedBase {
     static constexpr int NRED = 0;
-    const double* inv; const double* r; double* z;
-    __device__ bool skip() const { return false; }
+    const double* inv; const double* r; double* z; const KbCtl* sc; int sm;
+    __device__ bool skip() const { return kb_skip(sc, sm); }
     __device__ void pair(long long i, bool has1, double*) const {
         if (has1) { double2 a = kb_ld2(inv + i), b = kb_ld2(r + i); kb_st2(z + i, make_double2(a.x * b.x, a.y * b.y)); }
         else z[i] = inv[i] * r[i];
@@ -447,21 +447,21 @@ extern "C" int kb_pc_create_jacobi(kb_csr A, kb_pc* out) {
     return KB_OK;
 }
 
-int kb_ilu0_apply_dev(kb_pc_s* pc, const double* d_r, double* d_z);
+int kb_ilu0_apply_dev(kb_pc_s* pc, const double* d_r, double* d_z, const KbCtl* skip_ctl, int skip_mask);
 
-int kb_pc_apply_dev(kb_pc_s* pc, const double* d_r, double* d_z) {
+int kb_pc_apply_dev(kb_pc_s* pc, const double* d_r, double* d_z, const KbCtl* skip_ctl, int skip_mask) {
     kb_csr_s* A = pc->a;
     kb_ctx_s* c = A->ctx;
     if (A->n == 0) return KB_OK;
     if (pc->kind == KB_PC_JACOBI) {
         JacobiApplyOp op; op.n = (long long)A->n; op.partials = nullptr; op.pstride = 0; op.ticket = c->ticket;
-        op.inv = pc->inv_diag; op.r = d_r; op.z = d_z;
+        op.inv = pc->inv_diag; op.r = d_r; op.z = d_z; op.sc = skip_ctl; op.sm = skip_mask;
         KbLaunch L(c, KB_K_SMALL);
         kb_tile_kernel<JacobiApplyOp><<<A->ntiles, KB_THREADS, 0, c->stream>>>(op);
         KB_CUDA(cudaGetLastError());
         return KB_OK;
     }
-    if (pc->kind == KB_PC_ILU0) return kb_ilu0_apply_dev(pc, d_r, d_z);
+    if (pc->kind == KB_PC_ILU0) return kb_ilu0_apply_dev(pc, d_r, d_z, skip_ctl, skip_mask);
     kb_set_error("unknown preconditioner kind");
     return KB_UNSUPPORTED;
 }

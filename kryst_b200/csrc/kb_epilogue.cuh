@@ -25,9 +25,11 @@ template <class Fin, bool WD, bool YD>
 struct KbSpmvEpi {
     static constexpr bool WDOT = WD, YDOT = YD;
     KbCtl* ctl;          // may be null (never skip)
-    int early_skip = 0;  // also skip when ctl->early is set (BiCGStab's second SpMV)
+    int skip_mask = 0;   // bit 0: also skip when ctl->early (BiCGStab's 2nd SpMV); bit 1: when ctl->cycle_break (GMRES)
     KbFinish<Fin> fin;
-    __device__ bool skip() const { return ctl != nullptr && (ctl->done != 0 || (early_skip && ctl->early != 0)); }
+    __device__ bool skip() const {
+        return ctl != nullptr && (ctl->done != 0 || ((skip_mask & 1) && ctl->early != 0) || ((skip_mask & 2) && ctl->cycle_break != 0));
+    }
     __device__ void finish(const double* s) const { fin(s); }
 };
 

@@ -1,0 +1,473 @@
+// kb_gmres.cu — restarted GMRES(m), device-resident (replaces src/solver/gmres.rs:216-402).
+//
+// Orthogonalisation is classical Gram-Schmidt with reorthogonalisation done as block GEMVs over the
+// Krylov basis (north_star item 3) instead of the reference's 2(j+1) sequential dot+axpy pairs
+// (gmres.rs:83-96):   h1 = V^T w ; w -= V h1 ; h2 = V^T w ; w -= V h2 (fused with ||w||^2) ; H[:,j] = h1 + h2.
+// The basis is column-major V[ld x (m+1)] (each column contiguous, with ghost space on a shard).
+// Givens rotations (gmres.rs:154-176), the stop test (Convergence::check, :348-354), back-substitution
+// (:180-192) and the per-cycle true-residual test (:388-398, strict <) run on the device in single-block
+// epilogues, so a whole restart cycle is one CUDA-graph replay with no host round trip.
+// Preconditioned modes use the textbook formulation (Tier T, SURVEY §8c: the reference's Left/Right
+// branches are mathematically inconsistent, F7): Left = Arnoldi on M^-1 A started from M^-1 r0 with the
+// inner test on ||M^-1 r||; Right = Arnoldi on A M^-1, x += M^-1 (V y).
+#include <cstring>
+#include <algorithm>
+#include "kb_objects.h"
+#include "kb_epilogue.cuh"
+#include "kb_driver.cuh"
+
+#define KB_GM_EPS 1e-14     // gmres.rs:233
+
+struct KbGmresDev {       // device pointers shared by the kernels
+    KbCtl* ctl;
+    double* V; size_t ld;
+    const double* h1src; const double* h2src;   // where the (all-reduced) CGS coefficients live
+};
+
+// ---- multi-column dot: partial[c][tile] = canonical tile sum of V_c . w, c = 0..j ----------------------
+__global__ void __launch_bounds__(KB_THREADS) kb_gs_dot(KbGmresDev g, const double* __restrict__ w, long long n, double* partials, size_t pstride,
+                                                        int ncols) {
+    KbCtl* ctl = g.ctl;
+    if (ctl->done || ctl->cycle_break) return;
+    __shared__ double sm[(KB_MAX_RESTART + 1) * 8];
+    const int tid = threadIdx.x, lane = tid & 31, wp = tid >> 5;
+    const long long i = (long long)blockIdx.x * KB_TILE + 2 * tid;
+    double w0 = 0.0, w1 = 0.0;
+    const bool h0 = i < n, h1 = i + 1 < n;
+    if (h1) { double2 t = kb_ld2(w + i); w0 = t.x; w1 = t.y; }
+    else if (h0) w0 = w[i];
+#pragma unroll 4
+    for (int c = 0; c < ncols; ++c) {
+        const double* vc = g.V + (size_t)c * g.ld;
+        double e0 = 0.0, e1 = 0.0;
+        if (h1) { double2 t = kb_ld2(vc + i); e0 = t.x * w0; e1 = t.y * w1; }
+        else if (h0) e0 = vc[i] * w0;
+        double v = kb_warp_butterfly(e0 + e1);
+        if (lane == 0) sm[c * 8 + wp] = v;
+    }
+    __syncthreads();
+    for (int c = tid; c < ncols; c += KB_THREADS) {
+        double s = sm[c * 8];
+#pragma unroll
+        for (int k = 1; k < 8; ++k) s = s + sm[c * 8 + k];
+        partials[(size_t)c * pstride + blockIdx.x] = s;
+    }
+}
+// level 2 for every column in parallel: block c reduces partial[c][0..P)
+__global__ void __launch_bounds__(KB_THREADS) kb_gs_level2(KbCtl* ctl, const double* partials, size_t pstride, int P, double* dst) {
+    if (ctl->done || ctl->cycle_break) return;
+    __shared__ double sm[8];
+    double s = kb_level2(partials + (size_t)blockIdx.x * pstride, P, sm);
+    if (threadIdx.x == 0) dst[blockIdx.x] = s;
+}
+
+// ---- Arnoldi step epilogue: H column, Givens, stop test (all threads of one block) ----------------------
+__device__ void kb_arnoldi_fin(const KbGmresDev& g, double ww, int j) {
+    KbCtl* c = g.ctl;
+    __shared__ double hcol[KB_MAX_RESTART + 2], scs[KB_MAX_RESTART], ssn[KB_MAX_RESTART];
+    for (int k = threadIdx.x; k <= j; k += blockDim.x) hcol[k] = g.h1src[k] + g.h2src[k];
+    for (int k = threadIdx.x; k < j; k += blockDim.x) { scs[k] = c->cs[k]; ssn[k] = c->sn[k]; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const int ldh = c->restart + 1;
+        const double hn = sqrt(ww);
+        hcol[j + 1] = hn;
+        c->hnorm = hn;
+        const int happy = fabs(hn) < KB_GM_EPS;
+        for (int i = 0; i < j; ++i) {                       // gmres.rs:155-159
+            const double temp = scs[i] * hcol[i] + ssn[i] * hcol[i + 1];
+            hcol[i + 1] = -ssn[i] * hcol[i] + scs[i] * hcol[i + 1];
+            hcol[i] = temp;
+        }
+        const double hkk = hcol[j], hk1k = hcol[j + 1];
+        const double r = sqrt(hkk * hkk + hk1k * hk1k);
+        double cj, sj;
+        if (fabs(r) < KB_GM_EPS) { cj = 1.0; sj = 0.0; } else { cj = hkk / r; sj = hk1k / r; }
+        hcol[j] = cj * hkk + sj * hk1k;
+        hcol[j + 1] = 0.0;
+        c->cs[j] = cj; c->sn[j] = sj;
+        const double gj = c->g[j], gj1 = c->g[j + 1];
+        const double temp = cj * gj + sj * gj1;
+        c->g[j + 1] = -sj * gj + cj * gj1;
+        c->g[j] = temp;
+        for (int i = 0; i <= j + 1; ++i) c->h[i + (size_t)ldh * j] = hcol[i];
+        const double res_norm = fabs(c->g[j + 1]);
+        const unsigned long long it = c->iter + 1;
+        c->iter = it;
+        const double rel = res_norm / c->res0;              // Convergence::check (convergence.rs:18-34)
+        const int stop = (rel <= c->tol) || (it >= c->max_iters);
+        c->res = res_norm; c->converged = stop;
+        c->m = j + 1; c->happy = happy;
+        if (stop || happy) c->cycle_break = 1;
+        c->j = j + 1;
+    }
+}
+__global__ void kb_arnoldi_fin_kernel(KbGmresDev g, const double* sums, int j) {
+    if (g.ctl->done || g.ctl->cycle_break) return;
+    kb_arnoldi_fin(g, sums[0], j);
+}
+
+// w -= V h (sequential in c: t = t - V[c][i]*h[c]); NORM: fused ||w||^2 and the Arnoldi epilogue
+template <bool NORM>
+struct GsUpdateOp : KbRedBase {
+    static constexpr int NRED = NORM ? 1 : 0;
+    static constexpr bool COOP = true;
+    KbGmresDev g; double* w; const double* hsrc; double* slots; int ncols;
+    __device__ bool skip() const { return g.ctl->done != 0 || g.ctl->cycle_break != 0; }
+    __device__ void pair(long long i, bool has1, double* red) const {
+        if (has1) {
+            double2 t = kb_ld2(w + i);
+#pragma unroll 4
+            for (int c = 0; c < ncols; ++c) {
+                const double2 v = kb_ld2(g.V + (size_t)c * g.ld + i);
+                const double h = hsrc[c];
+                t.x = t.x - v.x * h; t.y = t.y - v.y * h;
+            }
+            kb_st2(w + i, t);
+            if (NORM) red[0] = t.x * t.x + t.y * t.y;
+        } else {
+            double t = w[i];
+            for (int c = 0; c < ncols; ++c) t = t - g.V[(size_t)c * g.ld + i] * hsrc[c];
+            w[i] = t;
+            if (NORM) red[0] = t * t + 0.0;
+        }
+    }
+    __device__ void finish_coop(const double* sums) const {
+        if (slots) { if (threadIdx.x == 0) slots[0] = sums[0]; }
+        else kb_arnoldi_fin(g, sums[0], ncols - 1);
+    }
+};
+
+// dst = src / *div  (v_{j+1} = w / h_{j+1,j}: gmres.rs:102-103 ; v_0 = r / beta)
+struct ScaleOp : KbRedBase {
+    static constexpr int NRED = 0;
+    KbGmresDev g; const double* src; double* dst; int start_vec;   // start_vec: divide by beta_g (column 0), else by hnorm (column j+1)
+    __device__ bool skip() const {
+        const KbCtl* c = g.ctl;
+        if (c->done) return true;
+        return start_vec ? false : (c->happy != 0 || c->cycle_break != 0);
+    }
+    __device__ void pair(long long i, bool has1, double*) const {
+        const KbCtl* c = g.ctl;
+        const double d = start_vec ? c->beta_g : c->hnorm;
+        if (has1) { double2 t = kb_ld2(src + i); kb_st2(dst + i, make_double2(t.x / d, t.y / d)); }
+        else dst[i] = src[i] / d;
+    }
+    __device__ void finish(const double*) const {}
+};
+
+// back-substitution (gmres.rs:180-192), one block; y -> ctl->y
+__global__ void kb_gmres_backsubst(KbCtl* c) {
+    if (c->done) return;
+    extern __shared__ double sh[];   // h: m*m (row-major copy), g: m, y: m
+    const int m = c->m, ldh = c->restart + 1;
+    double* H = sh; double* G = sh + (size_t)m * m; double* Y = G + m;
+    for (int k = threadIdx.x; k < m * m; k += blockDim.x) { int i = k / m, j = k % m; H[k] = c->h[i + (size_t)ldh * j]; }
+    for (int k = threadIdx.x; k < m; k += blockDim.x) G[k] = c->g[k];
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int i = m - 1; i >= 0; --i) {
+            double yi = G[i];
+            for (int j = i + 1; j < m; ++j) yi = yi - H[i * m + j] * Y[j];
+            if (fabs(H[i * m + i]) > KB_GM_EPS) yi = yi / H[i * m + i]; else yi = 0.0;
+            Y[i] = yi; c->y[i] = yi;
+        }
+    }
+}
+
+// x += sum_j y_j V_j (gmres.rs:362-386); RIGHT: out = sum_j y_j V_j (then x += M^-1 out)
+template <bool RIGHT>
+struct UpdateXOp : KbRedBase {
+    static constexpr int NRED = 0;
+    KbGmresDev g; double* x; double* out;
+    __device__ bool skip() const { return g.ctl->done != 0; }
+    __device__ void pair(long long i, bool has1, double*) const {
+        const KbCtl* c = g.ctl;
+        const int m = c->m;
+        if (has1) {
+            double2 t = RIGHT ? make_double2(0.0, 0.0) : kb_ld2(x + i);
+#pragma unroll 4
+            for (int j = 0; j < m; ++j) {
+                const double2 v = kb_ld2(g.V + (size_t)j * g.ld + i);
+                const double y = c->y[j];
+                t.x = t.x + y * v.x; t.y = t.y + y * v.y;
+            }
+            kb_st2((RIGHT ? out : x) + i, t);
+        } else {
+            double t = RIGHT ? 0.0 : x[i];
+            for (int j = 0; j < m; ++j) t = t + c->y[j] * g.V[(size_t)j * g.ld + i];
+            (RIGHT ? out : x)[i] = t;
+        }
+    }
+    __device__ void finish(const double*) const {}
+};
+struct AddOp : KbRedBase {            // x += z
+    static constexpr int NRED = 0;
+    KbCtl* ctl; double* x; const double* z;
+    __device__ bool skip() const { return ctl->done != 0; }
+    __device__ void pair(long long i, bool has1, double*) const {
+        if (has1) { double2 a = kb_ld2(x + i), b = kb_ld2(z + i); kb_st2(x + i, make_double2(a.x + b.x, a.y + b.y)); }
+        else x[i] = x[i] + z[i];
+    }
+    __device__ void finish(const double*) const {}
+};
+
+// ---- scalar epilogues of the residual / norm kernels -------------------------------------------------------
+__device__ __forceinline__ void gm_reset_cycle(KbCtl* c, double r0_norm) {
+    c->beta_g = r0_norm;
+    c->j = 0; c->m = 0; c->cycle_break = 0; c->happy = 0;
+    c->g[0] = r0_norm;
+    for (int k = 1; k <= c->restart; ++k) c->g[k] = 0.0;
+}
+struct GmInitFin {     // gmres.rs:221-233
+    KbCtl* ctl;
+    __device__ void operator()(const double* s) const {
+        KbCtl* c = ctl;
+        const double beta = sqrt(s[0]);
+        c->res0_true = beta; c->res0 = beta; c->res = beta; c->converged = 0; c->iter = 0; c->outer = 0;
+        if (c->n_outer == 0) { c->done = 1; return; }
+        gm_reset_cycle(c, beta);
+    }
+};
+struct GmCycleFin {    // gmres.rs:388-398
+    KbCtl* ctl;
+    __device__ void operator()(const double* s) const {
+        KbCtl* c = ctl;
+        const double beta = sqrt(s[0]);
+        c->res = beta;
+        c->converged = (beta < c->tol * c->res0_true) ? 1 : 0;
+        c->outer = c->outer + 1;
+        if (c->converged || c->iter >= c->max_iters || c->outer >= c->n_outer) { c->done = 1; return; }
+        gm_reset_cycle(c, beta);
+    }
+};
+struct GmLeftNormFin { // textbook left: r0_norm = ||M^-1 r||, inner denominator from the first cycle
+    KbCtl* ctl;
+    __device__ void operator()(const double* s) const {
+        KbCtl* c = ctl;
+        const double r0n = sqrt(s[0]);
+        c->beta_g = r0n; c->g[0] = r0n;
+        if (c->outer == 0) c->res0 = r0n;
+    }
+};
+template <class Fin>
+struct NormOp : KbRedBase {
+    static constexpr int NRED = 1;
+    const double* z; KbCtl* ctl; KbFinish<Fin> fin;
+    __device__ bool skip() const { return ctl->done != 0; }
+    __device__ void pair(long long i, bool has1, double* red) const {
+        if (has1) { double2 t = kb_ld2(z + i); red[0] = t.x * t.x + t.y * t.y; }
+        else red[0] = z[i] * z[i] + 0.0;
+    }
+    __device__ void finish(const double* s) const { fin(s); }
+};
+
+// ---- workspace --------------------------------------------------------------------------------------------
+struct KbGmresWs {
+    uint64_t n = 0, nx = 0; int restart = 0; size_t ld = 0;
+    double *V = nullptr, *x = nullptr, *b = nullptr, *r = nullptr, *w = nullptr, *t = nullptr, *z = nullptr;
+    double* partials = nullptr; size_t pstride = 0;
+    double* slots = nullptr;
+    KbCtl* ctl = nullptr; KbCtl* h_ctl = nullptr;
+    KbGraphCache gc;
+};
+void kb_gmres_ws_free(KbGmresWs* w) {
+    if (!w) return;
+    w->gc.reset();
+    KB_FREE(w->V); KB_FREE(w->x); KB_FREE(w->b); KB_FREE(w->r); KB_FREE(w->w); KB_FREE(w->t); KB_FREE(w->z);
+    KB_FREE(w->partials); KB_FREE(w->slots); KB_FREE(w->ctl);
+    if (w->h_ctl) cudaFreeHost(w->h_ctl);
+    delete w;
+}
+static int gmres_ws_get(kb_csr_s* A, int restart, KbGmresWs** out) {
+    KbGmresWs* w = A->gmres_ws;
+    if (w && w->restart < restart) { kb_gmres_ws_free(w); w = nullptr; A->gmres_ws = nullptr; }
+    if (!w) {
+        w = new KbGmresWs; A->gmres_ws = w;
+        w->n = A->n; w->nx = A->ncols_local; w->restart = restart;
+        w->ld = ((size_t)w->nx + 2 + 31) & ~(size_t)31;
+        KB_TRY(kb_alloc(&w->V, w->ld * (size_t)(restart + 1)));
+        KB_TRY(kb_alloc(&w->x, w->nx + 2)); KB_TRY(kb_alloc(&w->b, w->n + 2)); KB_TRY(kb_alloc(&w->r, w->n + 2));
+        KB_TRY(kb_alloc(&w->w, w->n + 2)); KB_TRY(kb_alloc(&w->t, w->nx + 2)); KB_TRY(kb_alloc(&w->z, w->n + 2));
+        w->pstride = (size_t)A->ntiles + 1;
+        KB_TRY(kb_alloc(&w->partials, (size_t)(restart + 2) * w->pstride));
+        KB_TRY(kb_alloc(&w->slots, 3 * (KB_MAX_RESTART + 8)));
+        KB_TRY(kb_alloc(&w->ctl, 1));
+        KB_CUDA(cudaMallocHost((void**)&w->h_ctl, sizeof(KbCtl)));
+    }
+    *out = w;
+    return KB_OK;
+}
+
+template <class Op>
+static int gm_tile(kb_csr_s* A, Op& op, int cls) {
+    kb_ctx_s* c = A->ctx;
+    op.n = (long long)A->n; op.ticket = c->ticket;
+    { KbLaunch L(c, cls); kb_tile_kernel<<<A->ntiles, KB_THREADS, 0, c->stream>>>(op); }
+    KB_CUDA(cudaGetLastError());
+    return KB_OK;
+}
+
+struct GmPlan { kb_csr_s* A; kb_pc_s* pc; KbGmresWs* w; int side; bool dist; int restart; KbGmresDev g; };
+struct GmNoFin { __device__ void operator()(const double*) const {} };
+
+// start vector of a cycle: (Left: z = M^-1 r, ||z||) ; V_0 = (z | r) / r0_norm
+static int gm_start_vector(GmPlan& P) {
+    kb_csr_s* A = P.A; KbGmresWs* w = P.w; kb_ctx_s* c = A->ctx;
+    const double* src = w->r;
+    if (P.side == KB_SIDE_LEFT) {
+        KB_TRY(kb_pc_apply_dev(P.pc, w->r, w->z, w->ctl, 0));
+        NormOp<GmLeftNormFin> op; op.partials = w->partials; op.pstride = w->pstride; op.z = w->z; op.ctl = w->ctl;
+        op.fin.fin = GmLeftNormFin{w->ctl}; op.fin.slots = P.dist ? w->slots : nullptr; op.fin.nred = 1;
+        KB_TRY(gm_tile(A, op, KB_K_SMALL));
+        if (P.dist) KB_TRY((kb_finish_dist<GmLeftNormFin>(c, GmLeftNormFin{w->ctl}, w->ctl, w->slots, 1)));
+        src = w->z;
+    }
+    ScaleOp op; op.partials = nullptr; op.pstride = 0; op.g = P.g; op.src = src; op.dst = w->V; op.start_vec = 1;
+    return gm_tile(A, op, KB_K_SMALL);
+}
+
+// inner Arnoldi step j.  j is a host constant: a replayed cycle always starts at j = 0, and once the
+// device sets cycle_break every later step of the replay is skipped, so step k of the graph has j == k.
+static int gm_inner_iteration(GmPlan& P, int j) {
+    kb_csr_s* A = P.A; KbGmresWs* w = P.w; kb_ctx_s* c = A->ctx;
+    KbCtl* ctl = w->ctl;
+    double* vj = w->V + (size_t)j * w->ld;
+    const int ncols = j + 1;
+    typedef KbSpmvEpi<GmNoFin, false, false> Epi;
+    Epi epi; epi.ctl = ctl; epi.skip_mask = 2; epi.fin.fin = GmNoFin{}; epi.fin.slots = nullptr; epi.fin.nred = 0;
+    if (P.side == KB_SIDE_LEFT) {            // w = M^-1 (A v_j)
+        if (P.dist) KB_TRY(kb_halo_exchange(A, vj));
+        KB_TRY((kb_launch_spmv<Epi, false>(A, vj, w->z, nullptr, nullptr, nullptr, 0, epi)));
+        KB_TRY(kb_pc_apply_dev(P.pc, w->z, w->w, ctl, 2));
+    } else if (P.side == KB_SIDE_RIGHT) {    // w = A (M^-1 v_j)
+        KB_TRY(kb_pc_apply_dev(P.pc, vj, w->t, ctl, 2));
+        if (P.dist) KB_TRY(kb_halo_exchange(A, w->t));
+        KB_TRY((kb_launch_spmv<Epi, false>(A, w->t, w->w, nullptr, nullptr, nullptr, 0, epi)));
+    } else {                                 // w = A v_j   (gmres.rs:80-81)
+        if (P.dist) KB_TRY(kb_halo_exchange(A, vj));
+        KB_TRY((kb_launch_spmv<Epi, false>(A, vj, w->w, nullptr, nullptr, nullptr, 0, epi)));
+    }
+    {   // h1 = V^T w ; w -= V h1
+        { KbLaunch L(c, KB_K_GS_DOT); kb_gs_dot<<<A->ntiles, KB_THREADS, 0, c->stream>>>(P.g, w->w, (long long)A->n, w->partials, w->pstride, ncols); }
+        double* dst = P.dist ? w->slots : &ctl->h1[0];
+        { KbLaunch L(c, KB_K_SMALL); kb_gs_level2<<<ncols, KB_THREADS, 0, c->stream>>>(ctl, w->partials, w->pstride, A->ntiles, dst); }
+        if (P.dist) KB_TRY(kb_allreduce_slots(c, w->slots, ncols));
+        GsUpdateOp<false> op; op.partials = nullptr; op.pstride = 0; op.g = P.g; op.w = w->w; op.hsrc = P.g.h1src; op.slots = nullptr; op.ncols = ncols;
+        KB_TRY(gm_tile(A, op, KB_K_GS_UPDATE));
+    }
+    {   // h2 = V^T w ; w -= V h2 fused with ||w||^2 ; Arnoldi epilogue (H column, Givens, stop test)
+        { KbLaunch L(c, KB_K_GS_DOT); kb_gs_dot<<<A->ntiles, KB_THREADS, 0, c->stream>>>(P.g, w->w, (long long)A->n, w->partials, w->pstride, ncols); }
+        double* s2 = w->slots + (KB_MAX_RESTART + 8);
+        double* dst = P.dist ? s2 : &ctl->h2[0];
+        { KbLaunch L(c, KB_K_SMALL); kb_gs_level2<<<ncols, KB_THREADS, 0, c->stream>>>(ctl, w->partials, w->pstride, A->ntiles, dst); }
+        if (P.dist) KB_TRY(kb_allreduce_slots(c, s2, ncols));
+        double* s3 = w->slots + 2 * (KB_MAX_RESTART + 8);
+        GsUpdateOp<true> op; op.partials = w->partials; op.pstride = w->pstride; op.g = P.g; op.w = w->w; op.hsrc = P.g.h2src;
+        op.slots = P.dist ? s3 : nullptr; op.ncols = ncols;
+        KB_TRY(gm_tile(A, op, KB_K_GS_UPDATE));
+        if (P.dist) {
+            KB_TRY(kb_allreduce_slots(c, s3, 1));
+            KbLaunch L(c, KB_K_SMALL);
+            kb_arnoldi_fin_kernel<<<1, KB_THREADS, 0, c->stream>>>(P.g, s3, j);
+            KB_CUDA(cudaGetLastError());
+        }
+    }
+    {   // v_{j+1} = w / h_{j+1,j}   (skipped on happy breakdown / stop)
+        ScaleOp op; op.partials = nullptr; op.pstride = 0; op.g = P.g; op.src = w->w; op.dst = w->V + (size_t)(j + 1) * w->ld; op.start_vec = 0;
+        KB_TRY(gm_tile(A, op, KB_K_SMALL));
+    }
+    return KB_OK;
+}
+
+// one restart cycle = `restart` inner steps, least-squares solve, x update, true residual + cycle test,
+// and the next cycle's start vector
+static int gm_cycle(GmPlan& P) {
+    kb_csr_s* A = P.A; KbGmresWs* w = P.w; kb_ctx_s* c = A->ctx;
+    for (int j = 0; j < P.restart; ++j) KB_TRY(gm_inner_iteration(P, j));
+    {
+        KbLaunch L(c, KB_K_SMALL);
+        const size_t sh = ((size_t)P.restart * P.restart + 2 * (size_t)P.restart) * sizeof(double);
+        if (sh > 48 * 1024 && !c->configured.count((const void*)kb_gmres_backsubst)) {
+            KB_CUDA(cudaFuncSetAttribute(kb_gmres_backsubst, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((KB_MAX_RESTART * KB_MAX_RESTART + 2 * KB_MAX_RESTART) * sizeof(double))));
+            c->configured.insert((const void*)kb_gmres_backsubst);
+        }
+        kb_gmres_backsubst<<<1, KB_THREADS, sh, c->stream>>>(w->ctl);
+        KB_CUDA(cudaGetLastError());
+    }
+    if (P.side == KB_SIDE_RIGHT) {           // x += M^-1 (V y)
+        UpdateXOp<true> op; op.partials = nullptr; op.pstride = 0; op.g = P.g; op.x = w->x; op.out = w->w;
+        KB_TRY(gm_tile(A, op, KB_K_GS_UPDATE));
+        KB_TRY(kb_pc_apply_dev(P.pc, w->w, w->z, w->ctl, 0));
+        AddOp add; add.partials = nullptr; add.pstride = 0; add.ctl = w->ctl; add.x = w->x; add.z = w->z;
+        KB_TRY(gm_tile(A, add, KB_K_SMALL));
+    } else {
+        UpdateXOp<false> op; op.partials = nullptr; op.pstride = 0; op.g = P.g; op.x = w->x; op.out = nullptr;
+        KB_TRY(gm_tile(A, op, KB_K_GS_UPDATE));
+    }
+    {   // r = b - A x ; beta = ||r|| ; converged = beta < tol * res0 (gmres.rs:388-398)
+        if (P.dist) KB_TRY(kb_halo_exchange(A, w->x));
+        typedef KbSpmvEpi<GmCycleFin, false, true> Epi;
+        Epi epi; epi.ctl = w->ctl; epi.fin.fin = GmCycleFin{w->ctl}; epi.fin.slots = P.dist ? w->slots : nullptr; epi.fin.nred = 1;
+        KB_TRY((kb_launch_spmv<Epi, true>(A, w->x, w->r, w->b, nullptr, w->partials, w->pstride, epi)));
+        if (P.dist) KB_TRY((kb_finish_dist<GmCycleFin>(c, GmCycleFin{w->ctl}, w->ctl, w->slots, 1)));
+    }
+    return gm_start_vector(P);
+}
+
+extern "C" int kb_gmres_solve(kb_csr A, kb_pc pc, const double* b, double* x, uint64_t restart, double tol, uint64_t max_iters, int side,
+                              uint32_t flags, kb_stats* stats) {
+    if (!A || !b || !x || !stats) { kb_set_error("kb_gmres_solve: null argument"); return KB_SOLVE_ERROR; }
+    if (pc && pc->a != A) { kb_set_error("preconditioner was set up for a different operator"); return KB_SOLVE_ERROR; }
+    if (restart < 1 || restart > KB_MAX_RESTART) { kb_set_error("restart must be in [1,%d]", KB_MAX_RESTART); return KB_UNSUPPORTED; }
+    if (side < 0 || side > 2) { kb_set_error("bad preconditioning side"); return KB_SOLVE_ERROR; }
+    if (!pc) side = KB_SIDE_NONE;               // gmres.rs:262: `_ =>` branch when pc is None
+    kb_ctx_s* c = A->ctx;
+    KB_CUDA(cudaSetDevice(c->device));
+    const bool dev = (flags & KB_FLAG_DEVICE_PTRS) != 0;
+    const bool dist = A->dist && c->size > 1;
+    KbGmresWs* w = nullptr;
+    KB_TRY(gmres_ws_get(A, (int)restart, &w));
+    memset(stats, 0, sizeof(*stats));
+    if (A->n == 0 && !dist) return KB_OK;
+    KB_TRY(kb_upload_or_alias(c, b, w->b, w->n, dev));
+    KB_TRY(kb_upload_or_alias(c, x, w->x, w->n, dev));
+    KbCtl* h = w->h_ctl;
+    memset(h, 0, offsetof(KbCtl, h));
+    h->max_iters = max_iters; h->tol = tol; h->restart = (int)restart; h->side = side;
+    h->n_outer = (int)std::min<uint64_t>((max_iters + restart - 1) / restart, 0x7fffffffull);
+    KB_CUDA(cudaMemcpyAsync(w->ctl, h, offsetof(KbCtl, h), cudaMemcpyHostToDevice, c->stream));
+    GmPlan P{A, pc, w, side, dist, (int)restart, {}};
+    P.g.ctl = w->ctl; P.g.V = w->V; P.g.ld = w->ld;
+    P.g.h1src = dist ? w->slots : &w->ctl->h1[0];
+    P.g.h2src = dist ? w->slots + (KB_MAX_RESTART + 8) : &w->ctl->h2[0];
+    const bool profile = (flags & KB_FLAG_PROFILE) != 0;
+    const bool use_graph = !(flags & (KB_FLAG_NO_GRAPH | KB_FLAG_PROFILE));
+    const bool was_prof = c->profiling;
+    c->profiling = profile;
+    int st = KB_OK;
+    do {
+        if (dist && (st = kb_halo_exchange(A, w->x)) != KB_OK) break;
+        {   // r0 = b - A x ; beta = ||r0|| (gmres.rs:221-229)
+            typedef KbSpmvEpi<GmInitFin, false, true> Epi;
+            Epi epi; epi.ctl = nullptr; epi.fin.fin = GmInitFin{w->ctl}; epi.fin.slots = dist ? w->slots : nullptr; epi.fin.nred = 1;
+            if ((st = kb_launch_spmv<Epi, true>(A, w->x, w->r, w->b, nullptr, w->partials, w->pstride, epi)) != KB_OK) break;
+            if (dist && (st = kb_finish_dist<GmInitFin>(c, GmInitFin{w->ctl}, w->ctl, w->slots, 1)) != KB_OK) break;
+        }
+        if ((st = gm_start_vector(P)) != KB_OK) break;
+        const uint64_t key = (((uint64_t)(uintptr_t)pc + 1) * 4 + (uint64_t)side) * 256 + restart;
+        st = kb_run_iterations(c, &w->gc, key, 1, (uint64_t)h->n_outer, use_graph, w->ctl, h, [&]() { return gm_cycle(P); });
+        if (st != KB_OK) break;
+        if (cudaMemcpyAsync(h, w->ctl, offsetof(KbCtl, h), cudaMemcpyDeviceToHost, c->stream) != cudaSuccess ||
+            cudaStreamSynchronize(c->stream) != cudaSuccess) { kb_set_error("gmres: readback failed"); st = KB_SOLVE_ERROR; break; }
+        stats->iterations = h->iter; stats->final_residual = h->res; stats->converged = h->converged; stats->breakdown = h->happy;
+        st = h->status;
+        if (st == KB_OK) {
+            if (cudaMemcpyAsync(x, w->x, w->n * sizeof(double), dev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, c->stream) != cudaSuccess ||
+                cudaStreamSynchronize(c->stream) != cudaSuccess) { kb_set_error("gmres: copy-out of x failed"); st = KB_SOLVE_ERROR; }
+        }
+    } while (0);
+    c->profiling = was_prof;
+    if (profile) kb_prof_collect(c);
+    return st;
+}

@@ -1,0 +1,408 @@
+// kb_ilu0.cu — textbook ILU(0) on the CSR pattern, all on the device (K9-K11 of SURVEY §7.2).
+//
+// Replaces src/preconditioner/ilu.rs:59-122, which is dense, O(n^3) and numerically not an ILU
+// (SURVEY F5).  Specification = Saad Alg. 10.4 (IKJ) on the sorted pattern, unit-lower L, U with stored
+// inverse diagonal; on a row-block shard couplings to ghost columns are dropped (block-Jacobi ILU(0) ==
+// AdditiveSchwarz with overlap 0 over the chunk partition, asm.rs:34-57).
+//   symbolic : diag_ptr; level sets lev_L[i] = 1 + max lev_L[k<i in pattern] (lev_U mirrored) by monotone
+//              relaxation sweeps on the device; rows bucketed per level with a stable radix sort so each
+//              level lists its rows ascending -> integer structures bit-exact vs the oracle.
+//   numeric  : one launch per level, a thread per row runs the row's IKJ updates in the oracle's order
+//              (k ascending, j ascending; mul then sub) -> factors bit-exact vs the oracle.
+//   apply    : two sync-free triangular solves (forward unit-L, backward U).  Rows are laid out in level
+//              order (levels padded to warp multiples); a thread owns a row and spins on its dependencies,
+//              which always belong to earlier logical blocks (atomic block tickets), so wavefronts of
+//              successive levels pipeline through the resident CTAs without grid-wide barriers.  The
+//              "not ready" marker is the all-ones NaN pattern stored in the solution vector itself.
+#include <algorithm>
+#include <vector>
+#include <cub/cub.cuh>
+#include "kb_objects.h"
+
+#define KB_SENTINEL 0xFFFFFFFFFFFFFFFFull
+
+__global__ void k_ilu_count_local(const int* __restrict__ rp, const int* __restrict__ col, int n, int* __restrict__ cnt) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int c = 0;
+    for (int p = rp[i]; p < rp[i + 1]; ++p) c += (col[p] < n);
+    cnt[i] = c;
+}
+__global__ void k_ilu_fill_local(const int* __restrict__ rp, const int* __restrict__ col, const double* __restrict__ vals, int n,
+                                 const int* __restrict__ lrp, int* __restrict__ lcol, double* __restrict__ lu) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int q = lrp[i];
+    for (int p = rp[i]; p < rp[i + 1]; ++p)
+        if (col[p] < n) { lcol[q] = col[p]; lu[q] = vals[p]; ++q; }
+}
+__global__ void k_ilu_diag_ptr(const int* __restrict__ lrp, const int* __restrict__ lcol, int n, int* __restrict__ dp,
+                               unsigned long long* bad) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int d = -1;
+    for (int p = lrp[i]; p < lrp[i + 1]; ++p)
+        if (lcol[p] == i) { d = p; break; }
+    dp[i] = d < 0 ? lrp[i + 1] : d;
+    if (d < 0) atomicMin(bad, (unsigned long long)i);
+}
+// one relaxation sweep of lev[i] = 1 + max(lev[k]) over the strictly lower (upper) pattern
+__global__ void k_ilu_level_sweep(const int* __restrict__ lrp, const int* __restrict__ lcol, const int* __restrict__ dp, int n,
+                                  int upper, int* lev, int* changed) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int lv = 0;
+    const int a = upper ? dp[i] + 1 : lrp[i], b = upper ? lrp[i + 1] : dp[i];
+    for (int p = a; p < b; ++p) {
+        int k = lcol[p];
+        int t = ((volatile int*)lev)[k] + 1;
+        lv = t > lv ? t : lv;
+    }
+    if (lv > lev[i]) { lev[i] = lv; *changed = 1; }
+}
+__global__ void k_iota(int* a, int n) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) a[i] = i;
+}
+__global__ void k_level_ptr(const int* __restrict__ sorted_lev, int n, int nlev, int* __restrict__ level_ptr) {
+    int l = blockIdx.x * blockDim.x + threadIdx.x;
+    if (l > nlev) return;
+    int lo = 0, hi = n;   // first position with sorted_lev >= l
+    while (lo < hi) { int mid = (lo + hi) >> 1; if (sorted_lev[mid] < l) lo = mid + 1; else hi = mid; }
+    level_ptr[l] = lo;
+}
+// warp-padded schedule: level l occupies [spad[l], spad[l+1]) with -1 fill
+__global__ void k_sched_fill(const int* __restrict__ order, const int* __restrict__ level_ptr, const int* __restrict__ spad,
+                             int nlev, int* __restrict__ sched) {
+    int l = blockIdx.x;
+    if (l >= nlev) return;
+    const int a = level_ptr[l], cnt = level_ptr[l + 1] - a, o = spad[l], e = spad[l + 1];
+    for (int t = threadIdx.x; t < e - o; t += blockDim.x) sched[o + t] = t < cnt ? order[a + t] : -1;
+}
+
+// numeric factorisation of the rows of one level (thread per row) — Saad Alg. 10.4, IKJ
+__global__ void k_ilu_factor_level(const int* __restrict__ rows, int nrows, const int* __restrict__ lrp, const int* __restrict__ lcol,
+                                   const int* __restrict__ dp, double* lu, double* __restrict__ inv_ud, unsigned long long* bad) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nrows) return;
+    const int i = rows[t];
+    const int rb = lrp[i], re = lrp[i + 1], di = dp[i];
+    for (int p = rb; p < di; ++p) {
+        const int k = lcol[p];
+        const double lik = lu[p] / lu[dp[k]];
+        lu[p] = lik;
+        int pos = p + 1;
+        const int ke = lrp[k + 1];
+        for (int q = dp[k] + 1; q < ke; ++q) {
+            const int j = lcol[q];
+            while (pos < re && lcol[pos] < j) ++pos;
+            if (pos < re && lcol[pos] == j) lu[pos] = lu[pos] - lik * lu[q];
+        }
+    }
+    const double piv = lu[di];
+    if (piv == 0.0 || piv != piv) atomicMin(bad, (unsigned long long)i);
+    inv_ud[i] = 1.0 / piv;
+}
+
+// ---- sync-free triangular solves ------------------------------------------------------------------------
+struct KbTrsvArgs {
+    const int* __restrict__ sched; int sched_len;
+    const int* __restrict__ lrp; const int* __restrict__ lcol; const int* __restrict__ dp;
+    const double* __restrict__ lu; const double* __restrict__ inv_ud;
+    const double* __restrict__ rhs;   // forward: r ; backward: y
+    double* out;                      // forward: y ; backward: z   (pre-filled with the NaN sentinel)
+    unsigned* counters;               // [0] block ticket, [1] finished blocks, [2] error flag
+    const KbCtl* skip_ctl; int skip_mask;
+    double* fill;                     // forward solve also marks the backward solve's output "not ready"
+};
+
+__device__ __forceinline__ double kb_wait_value(const double* p, unsigned* err) {
+    const volatile unsigned long long* q = reinterpret_cast<const volatile unsigned long long*>(p);
+    unsigned long long v = *q;
+    unsigned spins = 0;
+    while (v == KB_SENTINEL) {
+        v = *q;
+        if (++spins > (1u << 26)) { atomicExch(err, 1u); break; }   // never hang the GPU on a broken dependency graph
+    }
+    return __longlong_as_double((long long)v);
+}
+
+// mark both solution vectors "not ready" (replaces two memsets; skippable inside solver graphs)
+__global__ void kb_trsv_fill(double* a, double* b, long long n, const KbCtl* skip_ctl, int skip_mask) {
+    if (kb_skip(skip_ctl, skip_mask)) return;
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        reinterpret_cast<unsigned long long*>(a)[i] = KB_SENTINEL;
+        reinterpret_cast<unsigned long long*>(b)[i] = KB_SENTINEL;
+    }
+}
+
+template <bool UPPER>
+__global__ void __launch_bounds__(KB_THREADS) kb_trsv_syncfree(KbTrsvArgs a) {
+    if (kb_skip(a.skip_ctl, a.skip_mask)) return;
+    __shared__ unsigned s_blk;
+    if (threadIdx.x == 0) s_blk = atomicAdd(&a.counters[0], 1u);
+    __syncthreads();
+    const int t = (int)s_blk * KB_THREADS + threadIdx.x;
+    if (t < a.sched_len) {
+        const int i = a.sched[t];
+        if (i >= 0) {
+            double s = a.rhs[i];
+            if (!UPPER) {
+                const int pe = a.dp[i];
+                for (int p = a.lrp[i]; p < pe; ++p) s = s - a.lu[p] * kb_wait_value(a.out + a.lcol[p], &a.counters[2]);
+            } else {
+                const int pe = a.lrp[i + 1];
+                for (int p = a.dp[i] + 1; p < pe; ++p) s = s - a.lu[p] * kb_wait_value(a.out + a.lcol[p], &a.counters[2]);
+                s = s * a.inv_ud[i];
+            }
+            // publish: a single 64-bit store is the data and the ready flag at once
+            *reinterpret_cast<volatile unsigned long long*>(a.out + i) = (unsigned long long)__double_as_longlong(s);
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned f = atomicAdd(&a.counters[1], 1u);
+        if (f == gridDim.x - 1u) { a.counters[0] = 0u; a.counters[1] = 0u; __threadfence(); }
+    }
+}
+
+// ---- host ---------------------------------------------------------------------------------------------
+struct KbIluExtra {   // bookkeeping that is not needed by the hot path
+    int* level[2] = {nullptr, nullptr};
+    unsigned* counters = nullptr;
+    bool owns_pattern = false;
+};
+static KbIluExtra* extra_of(kb_pc_s* pc) { return reinterpret_cast<KbIluExtra*>(pc->extra); }
+
+void kb_ilu0_free(kb_pc_s* pc) {
+    if (!pc || pc->kind != KB_PC_ILU0) return;
+    KbIluExtra* x = extra_of(pc);
+    if (x) {
+        if (x->owns_pattern) { KB_FREE(pc->l_rp); KB_FREE(pc->l_col); }
+        KB_FREE(x->level[0]); KB_FREE(x->level[1]); KB_FREE(x->counters);
+        delete x;
+        pc->extra = nullptr;
+    }
+    KB_FREE(pc->lu); KB_FREE(pc->diag_ptr); KB_FREE(pc->tmp);
+    for (int u = 0; u < 2; ++u) { KB_FREE(pc->level_ptr[u]); KB_FREE(pc->order[u]); KB_FREE(pc->sched[u]); }
+}
+
+static int build_levels(kb_pc_s* pc, int upper) {
+    kb_csr_s* A = pc->a;
+    kb_ctx_s* c = A->ctx;
+    KbIluExtra* x = extra_of(pc);
+    const int n = (int)A->n;
+    const unsigned nb = (unsigned)((n + 255) / 256);
+    int* lev = nullptr;
+    KB_TRY(kb_alloc(&lev, (size_t)n + 1));
+    x->level[upper] = lev;
+    KB_CUDA(cudaMemsetAsync(lev, 0, ((size_t)n + 1) * sizeof(int), c->stream));
+    int* d_changed = nullptr;
+    KB_TRY(kb_alloc(&d_changed, 1));
+    // monotone relaxation to the fixpoint (<= nlevels sweeps; in-place reads make it converge faster)
+    for (int round = 0;; ++round) {
+        KB_CUDA(cudaMemsetAsync(d_changed, 0, sizeof(int), c->stream));
+        for (int k = 0; k < 32; ++k) {
+            KbLaunch L(c, KB_K_OTHER);
+            k_ilu_level_sweep<<<nb, 256, 0, c->stream>>>(pc->l_rp, pc->l_col, pc->diag_ptr, n, upper, lev, d_changed);
+        }
+        int h = 0;
+        KB_CUDA(cudaMemcpyAsync(&h, d_changed, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        KB_CUDA(cudaStreamSynchronize(c->stream));
+        if (!h) break;
+        if (round > (n / 32) + 8) { cudaFree(d_changed); kb_set_error("ilu0: level construction did not converge"); return KB_FACTOR_ERROR; }
+    }
+    cudaFree(d_changed);
+    // stable sort rows by level (ascending row inside a level)
+    int *keys_out = nullptr, *rows_in = nullptr, *rows_out = nullptr;
+    KB_TRY(kb_alloc(&keys_out, (size_t)n)); KB_TRY(kb_alloc(&rows_in, (size_t)n)); KB_TRY(kb_alloc(&rows_out, (size_t)n));
+    { KbLaunch L(c, KB_K_OTHER); k_iota<<<nb, 256, 0, c->stream>>>(rows_in, n); }
+    int* d_max = nullptr;
+    KB_TRY(kb_alloc(&d_max, 1));
+    size_t tb = 0, tb2 = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, tb, lev, keys_out, rows_in, rows_out, n, 0, 32, c->stream);
+    cub::DeviceReduce::Max(nullptr, tb2, lev, d_max, n, c->stream);
+    void* tmp = nullptr;
+    KB_CUDA(cudaMalloc(&tmp, std::max(tb, tb2) + 16));
+    cub::DeviceReduce::Max(tmp, tb2, lev, d_max, n, c->stream);
+    int hmax = 0;
+    KB_CUDA(cudaMemcpyAsync(&hmax, d_max, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    KB_CUDA(cudaStreamSynchronize(c->stream));
+    int end_bit = 1;
+    while ((1ll << end_bit) <= (long long)hmax) ++end_bit;
+    cub::DeviceRadixSort::SortPairs(tmp, tb, lev, keys_out, rows_in, rows_out, n, 0, end_bit, c->stream);
+    c->launches += 4;
+    const int nlev = hmax + 1;
+    pc->nlev[upper] = nlev;
+    pc->order[upper] = rows_out;
+    KB_TRY(kb_alloc(&pc->level_ptr[upper], (size_t)nlev + 1));
+    { KbLaunch L(c, KB_K_OTHER); k_level_ptr<<<(unsigned)((nlev + 256) / 256), 256, 0, c->stream>>>(keys_out, n, nlev, pc->level_ptr[upper]); }
+    // warp-padded schedule for the sync-free solves
+    std::vector<int> lp((size_t)nlev + 1), sp((size_t)nlev + 1);
+    KB_CUDA(cudaMemcpyAsync(lp.data(), pc->level_ptr[upper], ((size_t)nlev + 1) * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    KB_CUDA(cudaStreamSynchronize(c->stream));
+    sp[0] = 0;
+    for (int l = 0; l < nlev; ++l) sp[l + 1] = sp[l] + ((lp[l + 1] - lp[l] + 31) / 32) * 32;
+    pc->sched_len[upper] = sp[nlev];
+    int* d_sp = nullptr;
+    KB_TRY(kb_alloc(&d_sp, (size_t)nlev + 1));
+    KB_CUDA(cudaMemcpyAsync(d_sp, sp.data(), ((size_t)nlev + 1) * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    KB_TRY(kb_alloc(&pc->sched[upper], (size_t)sp[nlev] + 1));
+    { KbLaunch L(c, KB_K_OTHER); k_sched_fill<<<nlev, 256, 0, c->stream>>>(rows_out, pc->level_ptr[upper], d_sp, nlev, pc->sched[upper]); }
+    KB_CUDA(cudaStreamSynchronize(c->stream));
+    cudaFree(d_sp); cudaFree(tmp); cudaFree(d_max); cudaFree(keys_out); cudaFree(rows_in);
+    return KB_OK;
+}
+
+int kb_ilu0_build(kb_pc_s* pc) {
+    kb_csr_s* A = pc->a;
+    kb_ctx_s* c = A->ctx;
+    const int n = (int)A->n;
+    const unsigned nb = (unsigned)((n + 255) / 256);
+    KbIluExtra* x = new KbIluExtra;
+    pc->extra = x;
+    KB_TRY(kb_alloc(&x->counters, 4));
+    KB_CUDA(cudaMemsetAsync(x->counters, 0, 4 * sizeof(unsigned), c->stream));
+    if (n == 0) return KB_OK;
+    // 1. block-local pattern: ghost couplings dropped on a shard, aliased otherwise
+    if (A->dist && A->ncols_local > A->n) {
+        x->owns_pattern = true;
+        int* cnt = nullptr;
+        KB_TRY(kb_alloc(&cnt, (size_t)n + 1));
+        KB_TRY(kb_alloc(&pc->l_rp, (size_t)n + 1));
+        KB_CUDA(cudaMemsetAsync(cnt, 0, ((size_t)n + 1) * sizeof(int), c->stream));
+        { KbLaunch L(c, KB_K_OTHER); k_ilu_count_local<<<nb, 256, 0, c->stream>>>(A->row_ptr, A->col, n, cnt); }
+        size_t tb = 0;
+        cub::DeviceScan::ExclusiveSum(nullptr, tb, cnt, pc->l_rp, n + 1, c->stream);
+        void* tmp = nullptr;
+        KB_CUDA(cudaMalloc(&tmp, tb + 16));
+        cub::DeviceScan::ExclusiveSum(tmp, tb, cnt, pc->l_rp, n + 1, c->stream);
+        c->launches += 1;
+        int lnnz = 0;
+        KB_CUDA(cudaMemcpyAsync(&lnnz, pc->l_rp + n, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        KB_CUDA(cudaStreamSynchronize(c->stream));
+        cudaFree(tmp); cudaFree(cnt);
+        pc->l_nnz = (uint64_t)lnnz;
+        KB_TRY(kb_alloc(&pc->l_col, (size_t)lnnz + 8));
+        KB_TRY(kb_alloc(&pc->lu, (size_t)lnnz + 8));
+        { KbLaunch L(c, KB_K_OTHER); k_ilu_fill_local<<<nb, 256, 0, c->stream>>>(A->row_ptr, A->col, A->vals, n, pc->l_rp, pc->l_col, pc->lu); }
+    } else {
+        pc->l_rp = A->row_ptr; pc->l_col = A->col; pc->l_nnz = A->nnz;
+        KB_TRY(kb_alloc(&pc->lu, (size_t)A->nnz + 8));
+        KB_CUDA(cudaMemcpyAsync(pc->lu, A->vals, A->nnz * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+    }
+    // 2. diagonal positions (a row without a stored diagonal is a FactorError)
+    unsigned long long* d_bad = nullptr;
+    KB_TRY(kb_alloc(&d_bad, 1));
+    KB_CUDA(cudaMemsetAsync(d_bad, 0xFF, sizeof(unsigned long long), c->stream));
+    KB_TRY(kb_alloc(&pc->diag_ptr, (size_t)n + 1));
+    KB_TRY(kb_alloc(&pc->inv_diag, (size_t)n + 2));
+    KB_TRY(kb_alloc(&pc->tmp, (size_t)n + 2));
+    { KbLaunch L(c, KB_K_OTHER); k_ilu_diag_ptr<<<nb, 256, 0, c->stream>>>(pc->l_rp, pc->l_col, n, pc->diag_ptr, d_bad); }
+    unsigned long long h_bad = ~0ull;
+    KB_CUDA(cudaMemcpyAsync(&h_bad, d_bad, sizeof(h_bad), cudaMemcpyDeviceToHost, c->stream));
+    KB_CUDA(cudaStreamSynchronize(c->stream));
+    if (h_bad != ~0ull) {
+        cudaFree(d_bad);
+        pc->bad_row = A->row_lo + h_bad;
+        kb_set_error("ilu0: row %llu has no stored diagonal entry", (unsigned long long)pc->bad_row);
+        return KB_FACTOR_ERROR;
+    }
+    // 3. level sets, built on the device
+    KB_TRY(build_levels(pc, 0));
+    KB_TRY(build_levels(pc, 1));
+    // 4. numeric factorisation, one launch per lower level (a row needs only finished rows k < i of its pattern)
+    {
+        std::vector<int> lp((size_t)pc->nlev[0] + 1);
+        KB_CUDA(cudaMemcpyAsync(lp.data(), pc->level_ptr[0], lp.size() * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        KB_CUDA(cudaStreamSynchronize(c->stream));
+        for (int l = 0; l < pc->nlev[0]; ++l) {
+            const int cnt = lp[l + 1] - lp[l];
+            if (cnt <= 0) continue;
+            KbLaunch L(c, KB_K_OTHER);
+            k_ilu_factor_level<<<(unsigned)((cnt + 127) / 128), 128, 0, c->stream>>>(pc->order[0] + lp[l], cnt, pc->l_rp, pc->l_col, pc->diag_ptr,
+                                                                                pc->lu, pc->inv_diag, d_bad);
+        }
+    }
+    KB_CUDA(cudaMemcpyAsync(&h_bad, d_bad, sizeof(h_bad), cudaMemcpyDeviceToHost, c->stream));
+    KB_CUDA(cudaStreamSynchronize(c->stream));
+    cudaFree(d_bad);
+    if (h_bad != ~0ull) {
+        pc->bad_row = A->row_lo + h_bad;
+        kb_set_error("zero pivot at row %llu", (unsigned long long)pc->bad_row);
+        return KB_ZERO_PIVOT;
+    }
+    return KB_OK;
+}
+
+int kb_ilu0_apply_dev(kb_pc_s* pc, const double* d_r, double* d_z, const KbCtl* skip_ctl, int skip_mask) {
+    kb_csr_s* A = pc->a;
+    kb_ctx_s* c = A->ctx;
+    if (A->n == 0) return KB_OK;
+    KbIluExtra* x = extra_of(pc);
+    {
+        KbLaunch L(c, KB_K_TRSV);
+        kb_trsv_fill<<<(unsigned)((A->n + 255) / 256), 256, 0, c->stream>>>(pc->tmp, d_z, (long long)A->n, skip_ctl, skip_mask);
+    }
+    KbTrsvArgs a{};
+    a.skip_ctl = skip_ctl; a.skip_mask = skip_mask;
+    a.lrp = pc->l_rp; a.lcol = pc->l_col; a.dp = pc->diag_ptr; a.lu = pc->lu; a.inv_ud = pc->inv_diag; a.counters = x->counters;
+    {
+        a.sched = pc->sched[0]; a.sched_len = pc->sched_len[0]; a.rhs = d_r; a.out = pc->tmp;
+        KbLaunch L(c, KB_K_TRSV);
+        kb_trsv_syncfree<false><<<(unsigned)((a.sched_len + KB_THREADS - 1) / KB_THREADS), KB_THREADS, 0, c->stream>>>(a);
+    }
+    {
+        a.sched = pc->sched[1]; a.sched_len = pc->sched_len[1]; a.rhs = pc->tmp; a.out = d_z;
+        KbLaunch L(c, KB_K_TRSV);
+        kb_trsv_syncfree<true><<<(unsigned)((a.sched_len + KB_THREADS - 1) / KB_THREADS), KB_THREADS, 0, c->stream>>>(a);
+    }
+    KB_CUDA(cudaGetLastError());
+    return KB_OK;
+}
+
+extern "C" int kb_pc_create_ilu0(kb_csr A, kb_pc* out) {
+    *out = nullptr;
+    if (!A) { kb_set_error("null operator"); return KB_SOLVE_ERROR; }
+    kb_ctx_s* c = A->ctx;
+    KB_CUDA(cudaSetDevice(c->device));
+    if (A->n != A->ncols_global && !A->dist) { kb_set_error("ilu0 needs a square operator"); return KB_FACTOR_ERROR; }
+    kb_pc_s* pc = new kb_pc_s;
+    pc->a = A; pc->kind = KB_PC_ILU0;
+    int st = kb_ilu0_build(pc);
+    if (st != KB_OK) {
+        if (st == KB_ZERO_PIVOT || st == KB_FACTOR_ERROR) { *out = pc; return st; }   // caller may query kb_pc_bad_row, then destroy
+        kb_pc_destroy(pc);
+        return st;
+    }
+    *out = pc;
+    return KB_OK;
+}
+
+extern "C" int kb_pc_ilu0_get_factors(kb_pc pc, double* lu, uint64_t* diag_ptr) {
+    if (!pc || pc->kind != KB_PC_ILU0) { kb_set_error("not an ILU(0) preconditioner"); return KB_SOLVE_ERROR; }
+    kb_csr_s* A = pc->a;
+    KB_CUDA(cudaSetDevice(A->ctx->device));
+    if (lu && pc->l_nnz) KB_CUDA(cudaMemcpy(lu, pc->lu, pc->l_nnz * sizeof(double), cudaMemcpyDeviceToHost));
+    if (diag_ptr && A->n) {
+        std::vector<int> dp(A->n);
+        KB_CUDA(cudaMemcpy(dp.data(), pc->diag_ptr, A->n * sizeof(int), cudaMemcpyDeviceToHost));
+        for (uint64_t i = 0; i < A->n; ++i) diag_ptr[i] = (uint64_t)dp[i];
+    }
+    return KB_OK;
+}
+extern "C" int kb_pc_ilu0_get_levels(kb_pc pc, int upper, uint64_t* nlevels, uint64_t* level_ptr, uint64_t* order) {
+    if (!pc || pc->kind != KB_PC_ILU0) { kb_set_error("not an ILU(0) preconditioner"); return KB_SOLVE_ERROR; }
+    kb_csr_s* A = pc->a;
+    KB_CUDA(cudaSetDevice(A->ctx->device));
+    const int u = upper ? 1 : 0;
+    *nlevels = (uint64_t)pc->nlev[u];
+    if (A->n == 0) return KB_OK;
+    std::vector<int> lp((size_t)pc->nlev[u] + 1), od(A->n);
+    KB_CUDA(cudaMemcpy(lp.data(), pc->level_ptr[u], lp.size() * sizeof(int), cudaMemcpyDeviceToHost));
+    KB_CUDA(cudaMemcpy(od.data(), pc->order[u], od.size() * sizeof(int), cudaMemcpyDeviceToHost));
+    for (size_t l = 0; l < lp.size(); ++l) level_ptr[l] = (uint64_t)lp[l];
+    for (size_t i = 0; i < od.size(); ++i) order[i] = (uint64_t)od[i];
+    return KB_OK;
+}

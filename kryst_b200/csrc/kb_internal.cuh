@@ -70,6 +70,7 @@ struct KbCtl {
     int cycle_break;           // inner loop of this cycle has exited
     int happy;
     int side;
+    int outer, n_outer;
     double res0_true, beta_g, hnorm;
     double h[(KB_MAX_RESTART + 1) * KB_MAX_RESTART];   // column-major: h[i + (restart+1)*j]
     double g[KB_MAX_RESTART + 1], cs[KB_MAX_RESTART], sn[KB_MAX_RESTART], y[KB_MAX_RESTART];
@@ -176,6 +177,11 @@ __device__ __forceinline__ bool kb_arrive_last(unsigned* ticket, unsigned nblock
 //   void Op::pair(i, has1, red)   process elements i (and i+1 if has1); red[r] = e_r(i) + e_r(i+1)
 //   void Op::finish(sums)         scalar epilogue, thread 0 of the last block
 // ---------------------------------------------------------------------------------------------
+template <class T, class = void>
+struct kb_is_coop { static constexpr bool value = false; };
+template <class T>
+struct kb_is_coop<T, decltype((void)T::COOP)> { static constexpr bool value = T::COOP; };
+
 template <class Op>
 __global__ void __launch_bounds__(KB_THREADS) kb_tile_kernel(Op op) {
     if (op.skip()) return;
@@ -203,9 +209,24 @@ __global__ void __launch_bounds__(KB_THREADS) kb_tile_kernel(Op op) {
             double sums[NR];
 #pragma unroll
             for (int r = 0; r < NR; ++r) sums[r] = kb_level2(op.partials + (size_t)r * op.pstride, (int)gridDim.x, sm);
-            if (threadIdx.x == 0) op.finish(sums);
+            if constexpr (kb_is_coop<Op>::value) {
+                __shared__ double ssum[NR];
+                if (threadIdx.x == 0) {
+#pragma unroll
+                    for (int r = 0; r < NR; ++r) ssum[r] = sums[r];
+                }
+                __syncthreads();
+                op.finish_coop(ssum);      // every thread of the last block (small dense epilogues)
+            } else {
+                if (threadIdx.x == 0) op.finish(sums);
+            }
         }
     }
+}
+
+// shared skip predicate of solver-embedded helper kernels
+__device__ __forceinline__ bool kb_skip(const KbCtl* c, int mask) {
+    return c != nullptr && (c->done != 0 || ((mask & 1) && c->early != 0) || ((mask & 2) && c->cycle_break != 0));
 }
 
 struct KbRedBase {

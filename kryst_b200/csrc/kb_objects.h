@@ -60,6 +60,7 @@ struct kb_pc_s {
     uint64_t bad_row = 0;
     double* r_tmp = nullptr;
     double* z_tmp = nullptr;
+    void* extra = nullptr;            // ILU(0) bookkeeping (kb_ilu0.cu)
 };
 
 // allocation helpers
@@ -80,7 +81,8 @@ static inline int kb_alloc(T** p, size_t count) {
 int kb_csr_spmv_plain(kb_csr_s* A, const double* d_x, double* d_y);
 int kb_halo_exchange(kb_csr_s* A, double* d_x);   // fills ghost entries of d_x (no-op when !dist)
 int kb_allreduce_slots(kb_ctx_s* c, double* d_vals, int count);   // rank-ordered sum, in place
-int kb_pc_apply_dev(kb_pc_s* pc, const double* d_r, double* d_z);
+// z = M^-1 r on the device; kernels are no-ops when skip_ctl->done (or, per skip_mask, early / cycle_break) is set
+int kb_pc_apply_dev(kb_pc_s* pc, const double* d_r, double* d_z, const KbCtl* skip_ctl = nullptr, int skip_mask = 0);
 void kb_pcg_ws_free(KbPcgWs* w);
 void kb_bicg_ws_free(KbBicgWs* w);
 void kb_gmres_ws_free(KbGmresWs* w);

@@ -1,0 +1,131 @@
+"""ILU(0) (factors, level sets, triangular solves) and GMRES parity: GPU vs oracle, bit-exact."""
+import numpy as np
+import pytest
+
+import oracle_ffi as o
+
+pytestmark = pytest.mark.gpu
+
+
+def _mk(kind, N, ctx):
+    import kryst_b200 as kb
+    from kryst_b200 import stencils
+    n, rp, ci, v = stencils.stencil(kind, N)
+    return kb.DeviceCsr.from_csr(n, n, rp, ci, v, ctx), o.OCsr(n, n, rp, ci, v)
+
+
+ILU_CASES = [("convdiff2d", 24), ("poisson2d", 33), ("convdiff3d", 12), ("poisson3d", 16), ("varcoef27", 8)]
+
+
+@pytest.mark.parametrize("kind,N", ILU_CASES)
+def test_ilu0_factors_levels_apply_bit_exact(ctx, kind, N):
+    import kryst_b200 as kb
+    A, Ao = _mk(kind, N, ctx)
+    pc = kb.Ilu0().setup(A)
+    st, lu_o, dp_o, iud_o, bad = o.ilu0_factor(Ao)
+    assert st == 0
+    lu, dp = pc.factors(Ao.nnz)
+    assert np.array_equal(dp, dp_o)                     # index construction: bit-exact
+    assert np.array_equal(lu, lu_o)                     # factors: bit-exact (stronger than the 1e-12 bar)
+    assert np.array_equal(pc.inv_diag, iud_o)
+    for upper in (False, True):
+        nl, lp, order = pc.levels(upper)
+        nl_o, lev_o, order_o, lp_o = o.levels(Ao, upper)
+        assert nl == nl_o and np.array_equal(lp, lp_o) and np.array_equal(order, order_o)
+    r = np.random.default_rng(11).standard_normal(Ao.n)
+    z = np.zeros(Ao.n)
+    pc.apply(r, z)
+    assert np.array_equal(z, o.ilu0_apply(Ao, lu_o, dp_o, iud_o, r))
+
+
+def test_ilu0_level_counts(ctx):
+    import kryst_b200 as kb
+    for kind, N, expect in (("poisson2d", 20, 39), ("poisson3d", 10, 28)):
+        A, Ao = _mk(kind, N, ctx)
+        pc = kb.Ilu0().setup(A)
+        assert pc.levels(False)[0] == expect and pc.levels(True)[0] == expect
+
+
+def test_ilu0_error_paths(ctx):
+    import kryst_b200 as kb
+    A = kb.DeviceCsr.from_csr(2, 2, [0, 2, 4], [0, 1, 0, 1], [1.0, 1.0, 1.0, 1.0], ctx)
+    with pytest.raises(kb.ZeroPivot) as e:
+        kb.Ilu0().setup(A)
+    assert e.value.row == 1
+    B = kb.DeviceCsr.from_csr(2, 2, [0, 1, 2], [1, 0], [1.0, 1.0], ctx)
+    with pytest.raises(kb.FactorError):
+        kb.Ilu0().setup(B)
+
+
+GM = [("convdiff2d", 24, 30), ("convdiff2d", 48, 30), ("convdiff3d", 10, 12), ("poisson3d", 12, 7)]
+
+
+@pytest.mark.parametrize("kind,N,restart", GM)
+@pytest.mark.parametrize("mode,pcname", [(0, None), (1, "jacobi"), (1, "ilu0"), (2, "jacobi"), (2, "ilu0")])
+def test_gmres_bit_exact(ctx, kind, N, restart, mode, pcname):
+    import kryst_b200 as kb
+    A, Ao = _mk(kind, N, ctx)
+    b = o.spmv(Ao, np.ones(Ao.n))
+    pc = {None: None, "jacobi": kb.Jacobi, "ilu0": kb.Ilu0}[pcname]
+    pc = pc().setup(A) if pc else None
+    pco = {None: None, "jacobi": o.OPc.jacobi, "ilu0": o.OPc.ilu0}[pcname]
+    pco = pco(Ao) if pco else None
+    x = np.zeros(Ao.n)
+    st = kb.GmresSolver(restart, 1e-8, 3000).with_preconditioning(mode).solve(A, pc, b, x)
+    rc, xo, so = o.gmres(Ao, pco, b, np.zeros(Ao.n), restart, 1e-8, 3000, mode=mode, variant=o.GMRES_CGS2)
+    assert (st.iterations, st.converged) == (so.iterations, bool(so.converged))
+    assert st.final_residual == so.final_residual
+    assert np.array_equal(x, xo)
+    assert st.converged and np.abs(x - 1.0).max() < 1e-5
+
+
+@pytest.mark.parametrize("kind,N", [("convdiff2d", 48), ("convdiff3d", 12)])
+def test_gmres_none_iterations_match_literal_mgs(ctx, kind, N):
+    """Tier L: unpreconditioned GMRES, GPU CGS2 vs the reference's MGS + second pass: iteration count within 2 %."""
+    import kryst_b200 as kb
+    A, Ao = _mk(kind, N, ctx)
+    b = o.spmv(Ao, np.ones(Ao.n))
+    x = np.zeros(Ao.n)
+    st = kb.GmresSolver(30, 1e-8, 20000).solve(A, None, b, x)
+    rc, xo, so = o.gmres(Ao, None, b, np.zeros(Ao.n), 30, 1e-8, 20000, mode=0, variant=o.GMRES_LITERAL)
+    assert st.converged and so.converged
+    assert abs(st.iterations - so.iterations) <= max(1, 0.02 * so.iterations)
+    assert np.allclose(x, xo, rtol=1e-6, atol=1e-8)
+
+
+def test_gmres_reference_fixtures(ctx):
+    import kryst_b200 as kb
+    a = np.array([[4.0, 1, 0, 0], [1, 3, 1, 0], [0, 1, 2, 1], [0, 0, 1, 3]])       # gmres.rs:439-528
+    Ao = o.OCsr.from_dense(a)
+    A = kb.DeviceCsr.from_csr(4, 4, Ao.row_ptr, Ao.col_idx, Ao.vals, ctx)
+    xt = np.array([1.0, 2, 3, 4])
+    for mode in (0, 1, 2):
+        x = np.zeros(4)
+        st = kb.GmresSolver(4, 1e-10, 100).with_preconditioning(mode).solve(A, kb.Jacobi().setup(A), a @ xt, x)
+        assert st.converged and np.abs(x - xt).max() < 1e-8
+    n = 10                                                                         # tests/preconditioner_integration.rs:156-179
+    t = np.zeros((n, n))
+    for i in range(n):
+        t[i, i] = 2.0
+        if i > 0:
+            t[i, i - 1] = -1.0
+        if i + 1 < n:
+            t[i, i + 1] = 0.5
+    To = o.OCsr.from_dense(t)
+    T = kb.DeviceCsr.from_csr(n, n, To.row_ptr, To.col_idx, To.vals, ctx)
+    for pc in (None, kb.Ilu0().setup(T)):
+        x = np.zeros(n)
+        st = kb.GmresSolver(10, 1e-12, 100).solve(T, pc, t @ np.ones(n), x)
+        assert st.converged and np.linalg.norm(x - 1) / np.sqrt(n) < 1e-10
+
+
+def test_gmres_limits(ctx):
+    import kryst_b200 as kb
+    A, Ao = _mk("convdiff2d", 24, ctx)
+    b = o.spmv(Ao, np.ones(Ao.n))
+    for restart, tol, mi in ((5, 1e-8, 12), (5, 1e-8, 0), (7, 1e-30, 20), (30, 1e-2, 100)):
+        x = np.zeros(Ao.n)
+        st = kb.GmresSolver(restart, tol, mi).solve(A, None, b, x)
+        rc, xo, so = o.gmres(Ao, None, b, np.zeros(Ao.n), restart, tol, mi, mode=0, variant=o.GMRES_CGS2)
+        assert (st.iterations, st.converged) == (so.iterations, bool(so.converged)), (restart, tol, mi)
+        assert st.final_residual == so.final_residual and np.array_equal(x, xo)
