@@ -336,14 +336,14 @@ class _Pc:
                 _ffi.lib().kb_pc_destroy(h)
             cls = _ERRORS.get(st, SolveError)
             raise ZeroPivot(msg, row) if cls is ZeroPivot else cls(msg)
-        self._h, self._a = h, a
+        self._h, self._a, self._n = h, a, a.nrows()
         return self
 
     def apply(self, r, z):
         """Preconditioner::apply(&self, r, z): z = M^-1 r."""
         if not self._h:
             raise SolveError("preconditioner used before setup()")
-        n = self._a.nrows()
+        n = self._n
         pr, dr, kr, _ = _vec_arg(r, n, "r")
         pz, dz, kz, wb = _vec_arg(z, n, "z", writable=True)
         if dr != dz:
@@ -374,7 +374,7 @@ class Jacobi(_Pc):
 
     @property
     def inv_diag(self):
-        out = np.zeros(self._a.nrows())
+        out = np.zeros(self._n)
         _check(_ffi.lib().kb_pc_get_inv_diag(self._h, _f(out)))
         return out
 
@@ -387,18 +387,18 @@ class Ilu0(_Pc):
 
     @property
     def inv_diag(self):
-        out = np.zeros(self._a.nrows())
+        out = np.zeros(self._n)
         _check(_ffi.lib().kb_pc_get_inv_diag(self._h, _f(out)))
         return out
 
     def factors(self, nnz):
         lu = np.zeros(nnz)
-        dp = np.zeros(self._a.nrows(), dtype=np.uint64)
+        dp = np.zeros(self._n, dtype=np.uint64)
         _check(_ffi.lib().kb_pc_ilu0_get_factors(self._h, _f(lu), _u(dp)))
         return lu, dp
 
     def levels(self, upper=False):
-        n = self._a.nrows()
+        n = self._n
         nl = C.c_uint64(0)
         lp = np.zeros(n + 2, dtype=np.uint64)
         order = np.zeros(max(n, 1), dtype=np.uint64)

@@ -96,8 +96,15 @@ extern "C" int kb_ctx_create(int device, kb_ctx* out) {
     return KB_OK;
 }
 int kb_comm_destroy_internal(kb_ctx_s* c);
+// Handles keep a reference on what they depend on (pc -> operator -> context), so destroying a
+// parent handle first is safe: the object is released when its last dependant goes away.
 extern "C" int kb_ctx_destroy(kb_ctx c) {
     if (!c) return KB_OK;
+    kb_ctx_unref(c);
+    return KB_OK;
+}
+void kb_ctx_unref(kb_ctx_s* c) {
+    if (--c->refs > 0) return;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     kb_comm_destroy_internal(c);
@@ -108,7 +115,6 @@ extern "C" int kb_ctx_destroy(kb_ctx c) {
     if (c->host_scalar) cudaFreeHost(c->host_scalar);
     cudaStreamDestroy(c->stream);
     delete c;
-    return KB_OK;
 }
 extern "C" void* kb_ctx_stream(kb_ctx c) { return (void*)c->stream; }
 extern "C" int kb_ctx_device(kb_ctx c) { return c->device; }
@@ -277,8 +283,8 @@ static int csr_create_common(kb_ctx c, uint64_t nrows, uint64_t ncols_global, bo
     } while (0);
     if (d_err) cudaFree(d_err);
     if (d_stats) cudaFree(d_stats);
+    c->refs++;
     if (st != KB_OK) { kb_csr_destroy(A); return st; }
-    c->live_handles++;
     *out = A;
     return KB_OK;
 }
@@ -303,6 +309,11 @@ extern "C" int kb_csr_create_dist(kb_ctx c, uint64_t n_global, uint64_t row_lo, 
 
 extern "C" int kb_csr_destroy(kb_csr A) {
     if (!A) return KB_OK;
+    kb_csr_unref(A);
+    return KB_OK;
+}
+void kb_csr_unref(kb_csr_s* A) {
+    if (--A->refs > 0) return;
     cudaSetDevice(A->ctx->device);
     cudaStreamSynchronize(A->ctx->stream);
     kb_pcg_ws_free(A->pcg_ws);
@@ -312,8 +323,9 @@ extern "C" int kb_csr_destroy(kb_csr A) {
     KB_FREE(A->row_ptr); KB_FREE(A->col); KB_FREE(A->vals); KB_FREE(A->ghosts);
     KB_FREE(A->tile_chunk); KB_FREE(A->chunk_row); KB_FREE(A->chunk_nz);
     KB_FREE(A->x_tmp); KB_FREE(A->y_tmp);
+    kb_ctx_s* c = A->ctx;
     delete A;
-    return KB_OK;
+    kb_ctx_unref(c);
 }
 extern "C" uint64_t kb_csr_nrows(kb_csr A) { return A->n; }
 extern "C" uint64_t kb_csr_ncols(kb_csr A) { return A->ncols_global; }
@@ -435,9 +447,10 @@ extern "C" int kb_pc_create_jacobi(kb_csr A, kb_pc* out) {
     kb_ctx_s* c = A->ctx;
     KB_CUDA(cudaSetDevice(c->device));
     kb_pc_s* pc = new kb_pc_s;
-    pc->a = A; pc->kind = KB_PC_JACOBI;
+    pc->a = A; pc->ctx = c; pc->kind = KB_PC_JACOBI;
     int st = kb_alloc(&pc->inv_diag, A->n + 2);
     if (st != KB_OK) { delete pc; return st; }
+    A->refs++;
     if (A->n) {
         KbLaunch L(c, KB_K_OTHER);
         k_jacobi_setup<<<(unsigned)((A->n + 255) / 256), 256, 0, c->stream>>>(A->row_ptr, A->col, A->vals, (int)A->n, pc->inv_diag);
@@ -485,11 +498,13 @@ extern "C" int kb_pc_apply(kb_pc pc, const double* r, double* z) {
 }
 extern "C" int kb_pc_destroy(kb_pc pc) {
     if (!pc) return KB_OK;
-    cudaSetDevice(pc->a->ctx->device);
-    cudaStreamSynchronize(pc->a->ctx->stream);
+    cudaSetDevice(pc->ctx->device);
+    cudaStreamSynchronize(pc->ctx->stream);
     kb_ilu0_free(pc);
     KB_FREE(pc->inv_diag); KB_FREE(pc->r_tmp); KB_FREE(pc->z_tmp);
+    kb_csr_s* A = pc->a;
     delete pc;
+    kb_csr_unref(A);
     return KB_OK;
 }
 extern "C" uint64_t kb_pc_bad_row(kb_pc pc) { return pc->bad_row; }

@@ -369,7 +369,8 @@ extern "C" int kb_pc_create_ilu0(kb_csr A, kb_pc* out) {
     KB_CUDA(cudaSetDevice(c->device));
     if (A->n != A->ncols_global && !A->dist) { kb_set_error("ilu0 needs a square operator"); return KB_FACTOR_ERROR; }
     kb_pc_s* pc = new kb_pc_s;
-    pc->a = A; pc->kind = KB_PC_ILU0;
+    pc->a = A; pc->ctx = c; pc->kind = KB_PC_ILU0;
+    A->refs++;
     int st = kb_ilu0_build(pc);
     if (st != KB_OK) {
         if (st == KB_ZERO_PIVOT || st == KB_FACTOR_ERROR) { *out = pc; return st; }   // caller may query kb_pc_bad_row, then destroy

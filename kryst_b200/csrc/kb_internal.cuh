@@ -102,7 +102,7 @@ struct kb_ctx_s {
     void* nccl = nullptr;                // ncclComm_t
     double* comm_buf = nullptr;          // device scratch for all-gathered partial scalars
     double* host_scalar = nullptr;       // pinned
-    int live_handles = 0;
+    int refs = 1;                        // the user handle + one per operator created on this context
     std::set<const void*> configured;    // kernels whose dynamic-smem attribute has been raised
 };
 

@@ -9,6 +9,7 @@ struct KbHalo;
 
 struct kb_csr_s {
     kb_ctx_s* ctx = nullptr;
+    int refs = 1;                // the user handle + one per preconditioner set up for this operator
     uint64_t n = 0;              // owned rows (Indexing::nrows)
     uint64_t ncols_global = 0;   // MatShape::ncols
     uint64_t ncols_local = 0;    // owned + ghost columns: length of the x operand of the kernels
@@ -42,7 +43,8 @@ struct kb_csr_s {
 enum { KB_PC_JACOBI = 1, KB_PC_ILU0 = 2 };
 
 struct kb_pc_s {
-    kb_csr_s* a = nullptr;
+    kb_csr_s* a = nullptr;           // operator it was set up for (must outlive every apply/solve using this pc)
+    kb_ctx_s* ctx = nullptr;         // kept separately so that destroy is safe after the operator is gone
     int kind = 0;
     double* inv_diag = nullptr;       // Jacobi: 1/a_ii (0 if a_ii == 0); ILU(0): 1/u_ii
     // ILU(0) on the owned diagonal block (pattern = A restricted to owned columns)
@@ -76,6 +78,9 @@ static inline int kb_alloc(T** p, size_t count) {
         if (p) cudaFree(p);   \
         p = nullptr;          \
     } while (0)
+
+void kb_ctx_unref(kb_ctx_s* c);
+void kb_csr_unref(kb_csr_s* A);
 
 // ---- internal launch API (implemented across the .cu files) ---------------------------------
 int kb_csr_spmv_plain(kb_csr_s* A, const double* d_x, double* d_y);

@@ -62,6 +62,7 @@ def main():
                                  mode=mode, variant=o.GMRES_CGS2, nshards=world)
             assert (st.iterations, st.converged) == (so.iterations, bool(so.converged)), ("dist gmres", kind, mode, st.iterations, so.iterations)
             assert st.final_residual == so.final_residual and np.array_equal(x, xo[lo:hi]), "dist gmres"
+        pc = None
         A.close()
     dist.barrier()
     ctx.close()

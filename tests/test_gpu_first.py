@@ -64,3 +64,23 @@ def test_pcg_bit_exact(ctx, kind, N, use_pc):
     assert st.final_residual == so.final_residual
     assert np.array_equal(x, xo)
     assert np.array_equal(np.array(s.residual_history), ho)
+
+
+def test_handle_lifetimes_any_destroy_order(built):
+    """pc -> operator -> context references: destroying parents first must be safe."""
+    import kryst_b200 as kb
+    from kryst_b200 import stencils
+    c = kb.Context(0)
+    n, rp, ci, v = stencils.stencil("poisson2d", 10)
+    A = kb.DeviceCsr.from_csr(n, n, rp, ci, v, c)
+    pc = kb.Jacobi().setup(A)
+    ilu = kb.Ilu0().setup(A)
+    c.close()
+    A.close()
+    r = np.ones(n)
+    z = np.zeros(n)
+    pc.apply(r, z)            # still valid: the pc keeps its operator and context alive
+    assert np.all(z == 0.25)
+    ilu.apply(r, z)
+    pc.close()
+    ilu.close()
