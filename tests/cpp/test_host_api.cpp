@@ -1,0 +1,80 @@
+// C++ host-layer tests written like the reference's own tests (tests/preconditioner_integration.rs,
+// src/solver/{pcg,gmres,bicgstab}.rs test modules), through include/kryst_b200.hpp -> C ABI -> CUDA kernels.
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include "kryst_b200.hpp"
+using namespace kryst;
+
+#define REQUIRE(c) do { if (!(c)) { std::fprintf(stderr, "FAILED %s:%d: %s\n", __FILE__, __LINE__, #c); std::exit(1); } } while (0)
+
+struct Csr { size_t n; std::vector<uint64_t> rp, ci; std::vector<double> v; };
+static Csr tridiag(size_t n, double lo, double d, double up) {
+    Csr m; m.n = n; m.rp.push_back(0);
+    for (size_t i = 0; i < n; ++i) {
+        if (i > 0) { m.ci.push_back(i - 1); m.v.push_back(lo); }
+        m.ci.push_back(i); m.v.push_back(d);
+        if (i + 1 < n) { m.ci.push_back(i + 1); m.v.push_back(up); }
+        m.rp.push_back(m.ci.size());
+    }
+    return m;
+}
+static double rel_error(const std::vector<double>& x, double t) {
+    double num = 0, den = 0;
+    for (double xi : x) { num += (xi - t) * (xi - t); den += t * t; }
+    return std::sqrt(num / den);
+}
+
+int main() {
+    Context ctx(0);
+    {   // spd_jacobi_pcg_converges (tests/preconditioner_integration.rs:127-138)
+        const size_t n = 10;
+        Csr m = tridiag(n, -1, 2, -1);
+        DeviceCsr a = DeviceCsr::from_csr(ctx, n, n, m.rp, m.ci, m.v);
+        std::vector<double> ones(n, 1.0), b(n), x(n, 0.0);
+        a.matvec(ones, b);
+        Jacobi pc; pc.setup(a);
+        PcgSolver solver(1e-12, n);
+        SolveStats st = solver.solve(a, &pc, b, x);
+        REQUIRE(st.converged); REQUIRE(rel_error(x, 1.0) < 1e-10); REQUIRE(st.iterations <= n);
+        REQUIRE(a.nrows() == n && a.ncols() == n);
+    }
+    {   // nonsym GMRES(10), none and left+ILU(0) (tests/preconditioner_integration.rs:156-179)
+        const size_t n = 10;
+        Csr m = tridiag(n, -1, 2, 0.5);
+        DeviceCsr a = DeviceCsr::from_csr(ctx, n, n, m.rp, m.ci, m.v);
+        std::vector<double> ones(n, 1.0), b(n), x(n, 0.0);
+        a.matvec(ones, b);
+        GmresSolver s1(10, 1e-12, 100);
+        SolveStats st = s1.solve(a, nullptr, b, x);
+        REQUIRE(st.converged); REQUIRE(rel_error(x, 1.0) < 1e-10);
+        Ilu0 ilu; ilu.setup(a);
+        std::fill(x.begin(), x.end(), 0.0);
+        GmresSolver s2 = GmresSolver(10, 1e-12, 100).with_preconditioning(Preconditioning::Left);
+        st = s2.solve(a, &ilu, b, x);
+        REQUIRE(st.converged); REQUIRE(rel_error(x, 1.0) < 1e-10);
+    }
+    {   // bicgstab_solves_well_conditioned_nonsym (src/solver/bicgstab.rs:303-328)
+        Csr m; m.n = 3; m.rp = {0, 3, 6, 9}; m.ci = {0, 1, 2, 0, 1, 2, 0, 1, 2};
+        for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) m.v.push_back(i == j ? 4.0 : double(i + 2 * j + 1));
+        DeviceCsr a = DeviceCsr::from_csr(ctx, 3, 3, m.rp, m.ci, m.v);
+        std::vector<double> xt = {1, 2, 3}, b(3), x(3, 0.0);
+        a.matvec(xt, b);
+        BiCgStabSolver solver(1e-10, 100);
+        SolveStats st = solver.solve(a, nullptr, b, x);
+        REQUIRE(st.converged);
+        for (int i = 0; i < 3; ++i) REQUIRE(std::fabs(x[i] - xt[i]) < 1e-8);
+    }
+    {   // error behaviour: IndefiniteMatrix leaves x untouched (pcg.rs:162-172); dot / norm (tests/core_dense.rs:38-47)
+        Csr m; m.n = 3; m.rp = {0, 1, 2, 3}; m.ci = {0, 1, 2}; m.v = {1.0, -1.0, 2.0};
+        DeviceCsr a = DeviceCsr::from_csr(ctx, 3, 3, m.rp, m.ci, m.v);
+        std::vector<double> b = {1, 1, 1}, x(3, 0.0);
+        bool threw = false;
+        try { PcgSolver(1e-10, 50).solve(a, nullptr, b, x); } catch (const KError& e) { threw = (e.kind == KError::IndefiniteMatrix); }
+        REQUIRE(threw); REQUIRE(x[0] == 0.0 && x[1] == 0.0 && x[2] == 0.0);
+        REQUIRE(std::fabs(ctx.dot({1, 2, 3}, {4, -5, 6}) - 12.0) < 1e-12);
+        REQUIRE(std::fabs(ctx.norm({1, 2, 3}) - std::sqrt(14.0)) < 1e-12);
+    }
+    std::puts("CPP_HOST_API_OK");
+    return 0;
+}
