@@ -93,7 +93,7 @@ struct BicgInitOp : KbRedBase {      // r^ = r ; p = r ; v = 0
         if (has1) { double2 rr = kb_ld2(r + i); kb_st2(rhat + i, rr); kb_st2(p + i, rr); kb_st2(v + i, make_double2(0.0, 0.0)); }
         else { rhat[i] = r[i]; p[i] = r[i]; v[i] = 0.0; }
     }
-    __device__ void finish(const double*) const {}
+    __device__ void finish_block(double*) const {}
 };
 struct BicgPOp : KbRedBase {         // Kp
     static constexpr int NRED = 0;
@@ -112,7 +112,7 @@ struct BicgPOp : KbRedBase {         // Kp
             if (inv) ph[i] = inv[i] * pp;
         }
     }
-    __device__ void finish(const double*) const {}
+    __device__ void finish_block(double*) const {}
 };
 template <class Fin>
 struct BicgSOp : KbRedBase {         // Ks
@@ -134,7 +134,7 @@ struct BicgSOp : KbRedBase {         // Ks
             red[0] = ss * ss + 0.0;
         }
     }
-    __device__ void finish(const double* sums) const { fin(sums); }
+    __device__ void finish_block(double* sums) const { fin.template coop<0>(sums); }
 };
 template <class Fin>
 struct BicgXrOp : KbRedBase {        // Kxr (also the early-exit x += alpha p^, bicgstab.rs:189-206)
@@ -166,9 +166,9 @@ struct BicgXrOp : KbRedBase {        // Kxr (also the early-exit x += alpha p^, 
             red[1] = rhat[i] * rr + 0.0;
         }
     }
-    __device__ void finish(const double* sums) const {
-        if (ctl->early) { ctl->done = 1; return; }
-        fin(sums);
+    __device__ void finish_block(double* sums) const {
+        if (ctl->early) { if (threadIdx.x == 0) ctl->done = 1; return; }   // identical on every rank: nobody enters the collective
+        fin.template coop<0>(sums);
     }
 };
 
@@ -221,7 +221,6 @@ static int launch_tile(kb_csr_s* A, Op& op, int cls) {
 // mode: 0 literal/unpreconditioned, 1 textbook + Jacobi (fused), 2 textbook + generic pc apply
 static int bicg_iteration(kb_csr_s* A, kb_pc_s* pc, KbBicgWs* w, int mode, bool dist) {
     kb_ctx_s* c = A->ctx;
-    double* slots = dist ? w->slots : nullptr;
     const double* inv = (mode == 1) ? pc->inv_diag : nullptr;
     double* ph = (mode == 0) ? w->p : w->ph;
     double* sh = (mode == 0) ? w->s : w->sh;
@@ -231,27 +230,25 @@ static int bicg_iteration(kb_csr_s* A, kb_pc_s* pc, KbBicgWs* w, int mode, bool 
         if (mode == 2) KB_TRY(kb_pc_apply_dev(pc, w->p, w->ph));
     }
     {   // Kv
-        if (dist) KB_TRY(kb_halo_exchange(A, ph));
-        KbSpmvEpi<BicgVFin, true, true> epi; epi.ctl = w->ctl; epi.fin.fin = BicgVFin{w->ctl}; epi.fin.slots = slots; epi.fin.nred = 2;
-        KB_TRY((kb_launch_spmv<KbSpmvEpi<BicgVFin, true, true>, false>(A, ph, w->v, nullptr, w->rhat, w->partials, w->pstride, epi)));
+        KbSpmvEpi<BicgVFin, true, true> epi; epi.ctl = w->ctl; epi.fin = kb_make_fin(c, BicgVFin{w->ctl}, dist, w->slots, 2);
+        KB_TRY((kb_launch_spmv<KbSpmvEpi<BicgVFin, true, true>, false>(A, ph, w->v, nullptr, w->rhat, w->partials, w->pstride, epi, dist ? ph : nullptr)));
         if (dist) KB_TRY((kb_finish_dist<BicgVFin>(c, BicgVFin{w->ctl}, w->ctl, w->slots, 2)));
     }
     {   // Ks
         BicgSOp<BicgSFin> op; op.partials = w->partials; op.pstride = w->pstride; op.r = w->r; op.v = w->v; op.s = w->s; op.inv = inv; op.sh = w->sh;
-        op.ctl = w->ctl; op.fin.fin = BicgSFin{w->ctl}; op.fin.slots = slots; op.fin.nred = 1;
+        op.ctl = w->ctl; op.fin = kb_make_fin(c, BicgSFin{w->ctl}, dist, w->slots, 1);
         KB_TRY(launch_tile(A, op, KB_K_BICG));
         if (dist) KB_TRY((kb_finish_dist<BicgSFin>(c, BicgSFin{w->ctl}, w->ctl, w->slots, 1)));
         if (mode == 2) KB_TRY(kb_pc_apply_dev(pc, w->s, w->sh));
     }
     {   // Kt (skipped on early exit)
-        if (dist) KB_TRY(kb_halo_exchange(A, sh));
-        KbSpmvEpi<BicgTFin, true, true> epi; epi.ctl = w->ctl; epi.skip_mask = 1; epi.fin.fin = BicgTFin{w->ctl}; epi.fin.slots = slots; epi.fin.nred = 2;
-        KB_TRY((kb_launch_spmv<KbSpmvEpi<BicgTFin, true, true>, false>(A, sh, w->t, nullptr, w->s, w->partials, w->pstride, epi)));
+        KbSpmvEpi<BicgTFin, true, true> epi; epi.ctl = w->ctl; epi.skip_mask = 1; epi.fin = kb_make_fin(c, BicgTFin{w->ctl}, dist, w->slots, 2);
+        KB_TRY((kb_launch_spmv<KbSpmvEpi<BicgTFin, true, true>, false>(A, sh, w->t, nullptr, w->s, w->partials, w->pstride, epi, dist ? sh : nullptr)));
         if (dist) KB_TRY((kb_finish_dist<BicgTFin>(c, BicgTFin{w->ctl}, w->ctl, w->slots, 2, true)));
     }
     {   // Kxr
         BicgXrOp<BicgXrFin> op; op.partials = w->partials; op.pstride = w->pstride; op.x = w->x; op.ph = ph; op.sh = sh; op.s = w->s; op.t = w->t;
-        op.r = w->r; op.rhat = w->rhat; op.ctl = w->ctl; op.fin.fin = BicgXrFin{w->ctl}; op.fin.slots = slots; op.fin.nred = 2;
+        op.r = w->r; op.rhat = w->rhat; op.ctl = w->ctl; op.fin = kb_make_fin(c, BicgXrFin{w->ctl}, dist, w->slots, 2);
         KB_TRY(launch_tile(A, op, KB_K_BICG));
         if (dist) KB_TRY((kb_finish_dist<BicgXrFin>(c, BicgXrFin{w->ctl}, w->ctl, w->slots, 2)));
     }
@@ -287,10 +284,9 @@ extern "C" int kb_bicgstab_solve(kb_csr A, kb_pc pc, const double* b, double* x,
     int st = KB_OK;
     do {
         // r = b - A x ; res0 = ||r|| (bicgstab.rs:73-102)
-        if (dist && (st = kb_halo_exchange(A, w->x)) != KB_OK) break;
         {
-            KbSpmvEpi<BicgInitFin, false, true> epi; epi.ctl = nullptr; epi.fin.fin = BicgInitFin{w->ctl}; epi.fin.slots = dist ? w->slots : nullptr; epi.fin.nred = 1;
-            if ((st = kb_launch_spmv<KbSpmvEpi<BicgInitFin, false, true>, true>(A, w->x, w->r, w->b, nullptr, w->partials, w->pstride, epi)) != KB_OK) break;
+            KbSpmvEpi<BicgInitFin, false, true> epi; epi.ctl = nullptr; epi.fin = kb_make_fin(c, BicgInitFin{w->ctl}, dist, w->slots, 1);
+            if ((st = kb_launch_spmv<KbSpmvEpi<BicgInitFin, false, true>, true>(A, w->x, w->r, w->b, nullptr, w->partials, w->pstride, epi, dist ? w->x : nullptr)) != KB_OK) break;
             if (dist && (st = kb_finish_dist<BicgInitFin>(c, BicgInitFin{w->ctl}, w->ctl, w->slots, 1)) != KB_OK) break;
         }
         {
@@ -306,6 +302,7 @@ extern "C" int kb_bicgstab_solve(kb_csr A, kb_pc pc, const double* b, double* x,
             cudaStreamSynchronize(c->stream) != cudaSuccess) { kb_set_error("bicgstab: readback failed"); st = KB_SOLVE_ERROR; break; }
         stats->iterations = h->iter; stats->final_residual = h->res; stats->converged = h->converged; stats->breakdown = h->breakdown;
         st = h->status;
+        if (dist && kb_p2p_error(c)) { kb_set_error("%s: peer-memory collective timed out", "bicgstab"); st = KB_SOLVE_ERROR; break; }
         if (st == KB_OK) {
             if (cudaMemcpyAsync(x, w->x, w->n * sizeof(double), dev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, c->stream) != cudaSuccess ||
                 cudaStreamSynchronize(c->stream) != cudaSuccess) { kb_set_error("bicgstab: copy-out of x failed"); st = KB_SOLVE_ERROR; }

@@ -321,7 +321,7 @@ void kb_csr_unref(kb_csr_s* A) {
     kb_gmres_ws_free(A->gmres_ws);
     kb_halo_free(A->halo);
     KB_FREE(A->row_ptr); KB_FREE(A->col); KB_FREE(A->vals); KB_FREE(A->ghosts);
-    KB_FREE(A->tile_chunk); KB_FREE(A->chunk_row); KB_FREE(A->chunk_nz);
+    KB_FREE(A->tile_chunk); KB_FREE(A->chunk_row); KB_FREE(A->chunk_nz); KB_FREE(A->tiles_interior); KB_FREE(A->tiles_boundary);
     KB_FREE(A->x_tmp); KB_FREE(A->y_tmp);
     kb_ctx_s* c = A->ctx;
     delete A;
@@ -387,7 +387,7 @@ struct DotOp : KbRedBase {
         double e1 = has1 ? x[i + 1] * y[i + 1] : 0.0;
         red[0] = e0 + e1;
     }
-    __device__ void finish(const double* s) const { out[0] = s[0]; }
+    __device__ void finish_block(double* s) const { if (threadIdx.x == 0) out[0] = s[0]; }
 };
 
 static int dot_host(kb_ctx c, uint64_t n, const double* x, const double* y, double* out) {
@@ -439,7 +439,7 @@ struct JacobiApplyOp : KbRedBase {
         if (has1) { double2 a = kb_ld2(inv + i), b = kb_ld2(r + i); kb_st2(z + i, make_double2(a.x * b.x, a.y * b.y)); }
         else z[i] = inv[i] * r[i];
     }
-    __device__ void finish(const double*) const {}
+    __device__ void finish_block(double*) const {}
 };
 
 extern "C" int kb_pc_create_jacobi(kb_csr A, kb_pc* out) {

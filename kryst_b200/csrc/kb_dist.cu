@@ -18,6 +18,7 @@
 #include <vector>
 #include <cub/cub.cuh>
 #include "kb_objects.h"
+#include "kb_p2p.cuh"
 
 // ---- NCCL through dlopen ----------------------------------------------------------------------------------
 struct NcclApi {
@@ -59,6 +60,103 @@ static int nccl_load() {
         }                                                                                                     \
     } while (0)
 
+// ---- CUDA-IPC peer mapping -----------------------------------------------------------------------------------
+struct KbP2PHost {
+    KbP2PDev dev{};
+    KbP2PDev* dev_copy = nullptr;          // device-resident copy handed to kernels by pointer
+    void* local = nullptr;                 // my mailbox (cudaMalloc)
+    void* peers[KB_MAX_RANKS] = {nullptr}; // opened handles (peers[rank] == local)
+};
+static size_t mailbox_bytes(int size) { return (size_t)2 * size * KB_AR_MAX * sizeof(double) + (size_t)2 * size * sizeof(unsigned long long) + 64; }
+
+// collective: allocate `bytes` locally (zeroed), export it, and map every peer's allocation.
+// ptrs[q] = address of rank q's allocation in this process (ptrs[me] = local).
+static int kb_ipc_alloc_exchange(kb_ctx_s* c, size_t bytes, void** ptrs) {
+    void* local = nullptr;
+    KB_CUDA(cudaMalloc(&local, bytes));
+    KB_CUDA(cudaMemsetAsync(local, 0, bytes, c->stream));
+    cudaIpcMemHandle_t h;
+    KB_CUDA(cudaIpcGetMemHandle(&h, local));
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "ipc handle size");
+    double* d_mine = c->comm_buf + 3000;
+    KB_CUDA(cudaMemcpyAsync(d_mine, &h, 64, cudaMemcpyHostToDevice, c->stream));
+    KB_NCCL(g_nccl.AllGather(d_mine, c->comm_buf, 8, ncclDouble, (ncclComm_t)c->nccl, c->stream));
+    std::vector<cudaIpcMemHandle_t> all((size_t)c->size);
+    KB_CUDA(cudaMemcpyAsync(all.data(), c->comm_buf, (size_t)c->size * 64, cudaMemcpyDeviceToHost, c->stream));
+    KB_CUDA(cudaStreamSynchronize(c->stream));
+    int ok = 1;
+    for (int q = 0; q < c->size; ++q) {
+        if (q == c->rank) { ptrs[q] = local; continue; }
+        void* pp = nullptr;
+        if (cudaIpcOpenMemHandle(&pp, all[q], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); ok = 0; pp = nullptr; }
+        ptrs[q] = pp;
+    }
+    // agree on success (a single failing mapping disables the peer path everywhere)
+    double okd = (double)ok, sum = 0.0;
+    {
+        double* d = c->comm_buf + 3100;
+        KB_CUDA(cudaMemcpyAsync(d, &okd, sizeof(double), cudaMemcpyHostToDevice, c->stream));
+        KB_NCCL(g_nccl.AllGather(d, c->comm_buf, 1, ncclDouble, (ncclComm_t)c->nccl, c->stream));
+        std::vector<double> oks((size_t)c->size);
+        KB_CUDA(cudaMemcpyAsync(oks.data(), c->comm_buf, (size_t)c->size * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        KB_CUDA(cudaStreamSynchronize(c->stream));
+        for (double v : oks) sum += v;
+    }
+    if ((int)sum != c->size) {
+        for (int q = 0; q < c->size; ++q) if (q != c->rank && ptrs[q]) cudaIpcCloseMemHandle(ptrs[q]);
+        cudaFree(local);
+        for (int q = 0; q < c->size; ++q) ptrs[q] = nullptr;
+        return KB_UNSUPPORTED;
+    }
+    return KB_OK;
+}
+static void kb_ipc_release(kb_ctx_s* c, void** ptrs) {
+    for (int q = 0; q < c->size; ++q) {
+        if (!ptrs[q]) continue;
+        if (q == c->rank) cudaFree(ptrs[q]); else cudaIpcCloseMemHandle(ptrs[q]);
+        ptrs[q] = nullptr;
+    }
+}
+
+static int kb_p2p_setup(kb_ctx_s* c) {
+    const char* mode = getenv("KB_COMM");
+    if (mode && strcmp(mode, "nccl") == 0) return KB_OK;
+    if (c->size > KB_MAX_RANKS) return KB_OK;
+    KbP2PHost* P = new KbP2PHost;
+    void* ptrs[KB_MAX_RANKS] = {nullptr};
+    const size_t bytes = mailbox_bytes(c->size);
+    if (kb_ipc_alloc_exchange(c, bytes, ptrs) != KB_OK) { delete P; return KB_OK; }   // stay on the NCCL path
+    for (int q = 0; q < c->size; ++q) {
+        P->peers[q] = ptrs[q];
+        P->dev.vals[q] = reinterpret_cast<double*>(ptrs[q]);
+        P->dev.flags[q] = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(ptrs[q]) + (size_t)2 * c->size * KB_AR_MAX * sizeof(double));
+    }
+    P->local = ptrs[c->rank];
+    P->dev.rank = c->rank; P->dev.size = c->size;
+    unsigned long long* seq = nullptr;
+    KB_TRY(kb_alloc(&seq, 4));
+    KB_CUDA(cudaMemsetAsync(seq, 0, 4 * sizeof(unsigned long long), c->stream));
+    P->dev.seq = seq;
+    P->dev.err = reinterpret_cast<unsigned*>(seq + 2);
+    KB_TRY(kb_alloc(&P->dev_copy, 1));
+    KB_CUDA(cudaMemcpyAsync(P->dev_copy, &P->dev, sizeof(KbP2PDev), cudaMemcpyHostToDevice, c->stream));
+    KB_CUDA(cudaStreamSynchronize(c->stream));
+    c->p2p = P;
+    return KB_OK;
+}
+
+__global__ void __launch_bounds__(KB_THREADS) kb_p2p_allreduce_kernel(KbP2PDev p, double* vals, int count) {
+    kb_p2p_allreduce_block<0>(p, vals, count);
+}
+const KbP2PDev* kb_p2p_dev(kb_ctx_s* c) { return c->p2p ? &reinterpret_cast<KbP2PHost*>(c->p2p)->dev : nullptr; }
+const KbP2PDev* kb_p2p_dev_ptr(kb_ctx_s* c) { return c->p2p ? reinterpret_cast<KbP2PHost*>(c->p2p)->dev_copy : nullptr; }
+int kb_p2p_error(kb_ctx_s* c) {
+    if (!c->p2p) return 0;
+    unsigned e = 0;
+    cudaMemcpy(&e, reinterpret_cast<KbP2PHost*>(c->p2p)->dev.err, sizeof(unsigned), cudaMemcpyDeviceToHost);
+    return (int)e;
+}
+
 extern "C" int kb_comm_unique_id(void* id128) {
     KB_TRY(nccl_load());
     ncclUniqueId id;
@@ -80,9 +178,18 @@ extern "C" int kb_comm_init(kb_ctx c, int rank, int size, const void* id128) {
         c->nccl = comm;
     }
     c->rank = rank; c->size = size;
+    if (size > 1) KB_TRY(kb_p2p_setup(c));
     return KB_OK;
 }
 int kb_comm_destroy_internal(kb_ctx_s* c) {
+    if (c->p2p) {
+        KbP2PHost* P = reinterpret_cast<KbP2PHost*>(c->p2p);
+        kb_ipc_release(c, P->peers);
+        cudaFree(P->dev.seq);
+        cudaFree(P->dev_copy);
+        delete P;
+        c->p2p = nullptr;
+    }
     if (c->nccl && g_nccl.so) { g_nccl.CommDestroy((ncclComm_t)c->nccl); c->nccl = nullptr; }
     return KB_OK;
 }
@@ -100,6 +207,12 @@ __global__ void k_rank_ordered_sum(const double* __restrict__ gathered, double* 
 int kb_allreduce_slots(kb_ctx_s* c, double* d_vals, int count) {
     if (c->size == 1) return KB_OK;
     if (!c->nccl) { kb_set_error("communicator not initialised"); return KB_SOLVE_ERROR; }
+    if (c->p2p && count <= KB_AR_MAX) {
+        KbLaunch L(c, KB_K_ALLREDUCE);
+        kb_p2p_allreduce_kernel<<<1, KB_THREADS, 0, c->stream>>>(reinterpret_cast<KbP2PHost*>(c->p2p)->dev, d_vals, count);
+        KB_CUDA(cudaGetLastError());
+        return KB_OK;
+    }
     if ((size_t)count * c->size > 4096) { kb_set_error("allreduce of %d values exceeds the scratch buffer", count); return KB_SOLVE_ERROR; }
     {
         KbLaunch L(c, KB_K_ALLREDUCE);
@@ -126,17 +239,119 @@ extern "C" int kb_comm_barrier(kb_ctx c) {
 }
 
 // ---- partition maps ----------------------------------------------------------------------------------------
+struct KbHaloDev {                 // device view of the peer-memory halo exchange
+    int rank, size, nsend, nghost, n_loc;
+    long long gstride;                           // my ghost_in parity stride (doubles)
+    long long peer_gstride[KB_MAX_RANKS];
+    double* ghost[KB_MAX_RANKS];                 // rank q's ghost_in[2][gstride_q]
+    unsigned long long* flags[KB_MAX_RANKS];     // rank q's flags[2][size]   : flags[q][par*size + src] = seq pushed by src
+    unsigned long long* acks[KB_MAX_RANKS];      // rank q's acks[size]       : acks[q][dst] = last push of q consumed by dst
+    int is_dest[KB_MAX_RANKS], is_src[KB_MAX_RANKS];
+    const int* send_idx; const int* send_q; const int* send_pos;
+    unsigned long long* seqs;                    // [0] pushes done, [1] receives done (device counters)
+    unsigned* tickets;                           // [0] push, [1] recv last-block tickets
+    unsigned* err;
+};
 struct KbHalo {
     int p = 1;
     std::vector<int> send_cnt, send_off, recv_cnt, recv_off;   // per peer rank
     int nsend = 0;
     int* send_idx = nullptr;      // device: local row index of every value to send, grouped by destination
-    double* send_buf = nullptr;   // device
+    double* send_buf = nullptr;   // device (NCCL path)
+    // peer-memory path
+    bool p2p = false;
+    void* ptrs[KB_MAX_RANKS] = {nullptr};
+    int* send_q = nullptr; int* send_pos = nullptr;
+    unsigned long long* seqs = nullptr; unsigned* tickets = nullptr;
+    KbHaloDev dev{};
+    int push_grid = 1, recv_grid = 1;
+    kb_ctx_s* ctx = nullptr;
 };
 void kb_halo_free(KbHalo* h) {
     if (!h) return;
-    KB_FREE(h->send_idx); KB_FREE(h->send_buf);
+    if (h->p2p && h->ctx) kb_ipc_release(h->ctx, h->ptrs);
+    KB_FREE(h->send_idx); KB_FREE(h->send_buf); KB_FREE(h->send_q); KB_FREE(h->send_pos); KB_FREE(h->seqs); KB_FREE(h->tickets);
     delete h;
+}
+
+// ---- peer-memory halo kernels --------------------------------------------------------------------------------
+// push #seq: every boundary value is stored straight into the destination GPU's ghost_in[parity] over NVLink;
+// the last CTA publishes the sequence number in the destination's flag slot.  Flow control: before reusing
+// a parity buffer the pusher checks that the destination acknowledged push seq-2.
+__global__ void __launch_bounds__(KB_THREADS) kb_halo_push(KbHaloDev h, const double* __restrict__ x) {
+    __shared__ int s_last;
+    const int tid = threadIdx.x;
+    const unsigned long long seq = h.seqs[0] + 1ull;
+    const size_t par = (size_t)(seq & 1ull);
+    if (tid < h.size && h.is_dest[tid]) {
+        const volatile unsigned long long* a = h.acks[h.rank] + tid;
+        unsigned spins = 0;
+        while (*a + 2ull < seq) { if (++spins > KB_SPIN_LIMIT) { atomicExch(h.err, 1u); break; } }
+    }
+    __syncthreads();
+    for (int k = blockIdx.x * KB_THREADS + tid; k < h.nsend; k += gridDim.x * KB_THREADS) {
+        const int q = h.send_q[k];
+        h.ghost[q][par * h.peer_gstride[q] + h.send_pos[k]] = x[h.send_idx[k]];
+    }
+    __syncthreads();
+    if (tid == 0) {
+        __threadfence_system();
+        const unsigned t = atomicAdd(&h.tickets[0], 1u);
+        s_last = (t == gridDim.x - 1u);
+        __threadfence_system();
+    }
+    __syncthreads();
+    if (s_last) {
+        if (tid < h.size && h.is_dest[tid]) {
+            __threadfence_system();
+            *reinterpret_cast<volatile unsigned long long*>(h.flags[tid] + par * h.size + h.rank) = seq;
+        }
+        if (tid == 0) { h.seqs[0] = seq; h.tickets[0] = 0u; }
+    }
+}
+// receive #seq: wait for every source's flag, copy ghost_in[parity] into the operand's ghost tail, acknowledge.
+__global__ void __launch_bounds__(KB_THREADS) kb_halo_recv(KbHaloDev h, double* __restrict__ x) {
+    __shared__ int s_last;
+    const int tid = threadIdx.x;
+    const unsigned long long seq = h.seqs[1] + 1ull;
+    const size_t par = (size_t)(seq & 1ull);
+    if (tid < h.size && h.is_src[tid]) {
+        const volatile unsigned long long* f = h.flags[h.rank] + par * h.size + tid;
+        unsigned spins = 0;
+        while (*f < seq) { if (++spins > KB_SPIN_LIMIT) { atomicExch(h.err, 1u); break; } }
+        __threadfence_system();
+    }
+    __syncthreads();
+    const double* g = h.ghost[h.rank] + par * h.gstride;
+    for (int k = blockIdx.x * KB_THREADS + tid; k < h.nghost; k += gridDim.x * KB_THREADS) x[h.n_loc + k] = __ldcv(g + k);
+    __syncthreads();
+    if (tid == 0) {
+        __threadfence();
+        const unsigned t = atomicAdd(&h.tickets[1], 1u);
+        s_last = (t == gridDim.x - 1u);
+    }
+    __syncthreads();
+    if (s_last) {
+        if (tid < h.size && h.is_src[tid]) {
+            __threadfence_system();
+            *reinterpret_cast<volatile unsigned long long*>(h.acks[tid] + h.rank) = seq;
+        }
+        if (tid == 0) { h.seqs[1] = seq; h.tickets[1] = 0u; }
+    }
+}
+__global__ void k_tile_boundary_flags(const int* __restrict__ rp, const int* __restrict__ col, int n, int nloc, int ntiles, int* __restrict__ flag) {
+    const int tile = blockIdx.x;
+    if (tile >= ntiles) return;
+    __shared__ int s_any;
+    if (threadIdx.x == 0) s_any = 0;
+    __syncthreads();
+    const int r0 = tile * KB_TILE, r1 = min(n, r0 + KB_TILE);
+    const int a = rp[r0], b = rp[r1];
+    int any = 0;
+    for (int k = a + threadIdx.x; k < b; k += blockDim.x) any |= (col[k] >= nloc);
+    if (any) s_any = 1;
+    __syncthreads();
+    if (threadIdx.x == 0) flag[tile] = s_any;
 }
 
 struct OffRange {
@@ -248,15 +463,84 @@ int kb_csr_build_dist(kb_csr_s* A) {
         if (H->nsend) { KbLaunch L(c, KB_K_OTHER); k_to_local_rows<<<(H->nsend + 255) / 256, 256, 0, c->stream>>>(d_req, H->send_idx, H->nsend, (unsigned long long)lo); }
         KB_CUDA(cudaStreamSynchronize(c->stream));
         cudaFree(d_req);
+        // ---- peer-memory path: ghost_in / flags / acks of every rank mapped through CUDA IPC
+        H->ctx = c;
+        if (c->p2p) {
+            std::vector<long long> ngh(p, 0), gstr(p, 0);
+            for (int q = 0; q < p; ++q) { for (int r = 0; r < p; ++r) ngh[q] += (long long)need_all[(size_t)q * p + r]; gstr[q] = ((ngh[q] + 31) / 32) * 32 + 32; }
+            long long gmax = 0;
+            for (int q = 0; q < p; ++q) gmax = std::max(gmax, gstr[q]);
+            // same allocation size on every rank keeps the exchange symmetric
+            const size_t off_flags = (size_t)2 * gmax * sizeof(double);
+            const size_t off_acks = off_flags + (size_t)2 * p * sizeof(unsigned long long);
+            const size_t bytes = off_acks + (size_t)p * sizeof(unsigned long long) + 64;
+            if (kb_ipc_alloc_exchange(c, bytes, H->ptrs) == KB_OK) {
+                H->p2p = true;
+                KbHaloDev& D = H->dev;
+                D.rank = me; D.size = p; D.nsend = H->nsend; D.nghost = ng; D.n_loc = nloc; D.gstride = gmax;
+                for (int q = 0; q < p; ++q) {
+                    D.peer_gstride[q] = gmax;
+                    D.ghost[q] = reinterpret_cast<double*>(H->ptrs[q]);
+                    D.flags[q] = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(H->ptrs[q]) + off_flags);
+                    D.acks[q] = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(H->ptrs[q]) + off_acks);
+                    D.is_dest[q] = H->send_cnt[q] > 0; D.is_src[q] = H->recv_cnt[q] > 0;
+                }
+                // destination rank and position (in the destination's ghost ordering) of every value I send
+                std::vector<int> hq((size_t)H->nsend), hp((size_t)H->nsend);
+                for (int q = 0; q < p; ++q) {
+                    long long roff = 0;   // where rank q stores ghosts owned by me: after those of ranks r < me
+                    for (int r = 0; r < me; ++r) roff += (long long)need_all[(size_t)q * p + r];
+                    for (int j = 0; j < H->send_cnt[q]; ++j) { hq[(size_t)H->send_off[q] + j] = q; hp[(size_t)H->send_off[q] + j] = (int)(roff + j); }
+                }
+                KB_TRY(kb_alloc(&H->send_q, (size_t)H->nsend + 1)); KB_TRY(kb_alloc(&H->send_pos, (size_t)H->nsend + 1));
+                KB_TRY(kb_alloc(&H->seqs, 4)); KB_TRY(kb_alloc(&H->tickets, 4));
+                KB_CUDA(cudaMemsetAsync(H->seqs, 0, 4 * sizeof(unsigned long long), c->stream));
+                KB_CUDA(cudaMemsetAsync(H->tickets, 0, 4 * sizeof(unsigned), c->stream));
+                if (H->nsend) {
+                    KB_CUDA(cudaMemcpyAsync(H->send_q, hq.data(), (size_t)H->nsend * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+                    KB_CUDA(cudaMemcpyAsync(H->send_pos, hp.data(), (size_t)H->nsend * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+                }
+                D.send_idx = H->send_idx; D.send_q = H->send_q; D.send_pos = H->send_pos;
+                D.seqs = H->seqs; D.tickets = H->tickets;
+                D.err = reinterpret_cast<KbP2PHost*>(c->p2p)->dev.err;
+                H->push_grid = std::max(1, std::min(32, (H->nsend + 4 * KB_THREADS - 1) / (4 * KB_THREADS)));
+                H->recv_grid = std::max(1, std::min(32, (ng + 4 * KB_THREADS - 1) / (4 * KB_THREADS)));
+                KB_CUDA(cudaStreamSynchronize(c->stream));
+            }
+        }
+        // ---- interior / boundary tiles: interior rows are multiplied while the halo is in flight
+        if (A->ntiles > 0) {
+            int* d_flag = nullptr;
+            KB_TRY(kb_alloc(&d_flag, (size_t)A->ntiles));
+            { KbLaunch L(c, KB_K_OTHER); k_tile_boundary_flags<<<A->ntiles, 128, 0, c->stream>>>(A->row_ptr, A->col, nloc, nloc, A->ntiles, d_flag); }
+            std::vector<int> hf((size_t)A->ntiles);
+            KB_CUDA(cudaMemcpyAsync(hf.data(), d_flag, hf.size() * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+            KB_CUDA(cudaStreamSynchronize(c->stream));
+            cudaFree(d_flag);
+            std::vector<int> ti, tb;
+            for (int t = 0; t < A->ntiles; ++t) (hf[t] ? tb : ti).push_back(t);
+            A->n_interior = (int)ti.size(); A->n_boundary = (int)tb.size();
+            KB_TRY(kb_alloc(&A->tiles_interior, ti.size() + 1)); KB_TRY(kb_alloc(&A->tiles_boundary, tb.size() + 1));
+            if (!ti.empty()) KB_CUDA(cudaMemcpyAsync(A->tiles_interior, ti.data(), ti.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+            if (!tb.empty()) KB_CUDA(cudaMemcpyAsync(A->tiles_boundary, tb.data(), tb.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+            KB_CUDA(cudaStreamSynchronize(c->stream));
+        }
     }
     return KB_OK;
 }
 
-// fill the ghost tail of the operand vector d_x (length n_loc + n_ghost) from the owners
-int kb_halo_exchange(kb_csr_s* A, double* d_x) {
+// Halo exchange of the SpMV operand d_x (length n_loc + n_ghost), split so that interior rows can be
+// multiplied between the two calls:  begin = start the transfer, end = ghost tail of d_x is valid.
+int kb_halo_begin(kb_csr_s* A, double* d_x) {
     if (!A->dist || A->ctx->size == 1) return KB_OK;
     kb_ctx_s* c = A->ctx;
     KbHalo* H = A->halo;
+    if (H->p2p) {
+        KbLaunch L(c, KB_K_HALO);
+        kb_halo_push<<<H->push_grid, KB_THREADS, 0, c->stream>>>(H->dev, d_x);
+        KB_CUDA(cudaGetLastError());
+        return KB_OK;
+    }
     const int p = H->p;
     if (H->nsend) {
         KbLaunch L(c, KB_K_HALO);
@@ -270,4 +554,18 @@ int kb_halo_exchange(kb_csr_s* A, double* d_x) {
     }
     KB_NCCL(g_nccl.GroupEnd());
     return KB_OK;
+}
+int kb_halo_end(kb_csr_s* A, double* d_x) {
+    if (!A->dist || A->ctx->size == 1) return KB_OK;
+    KbHalo* H = A->halo;
+    if (!H->p2p) return KB_OK;
+    kb_ctx_s* c = A->ctx;
+    KbLaunch L(c, KB_K_HALO);
+    kb_halo_recv<<<H->recv_grid, KB_THREADS, 0, c->stream>>>(H->dev, d_x);
+    KB_CUDA(cudaGetLastError());
+    return KB_OK;
+}
+int kb_halo_exchange(kb_csr_s* A, double* d_x) {
+    KB_TRY(kb_halo_begin(A, d_x));
+    return kb_halo_end(A, d_x);
 }

@@ -6,20 +6,46 @@
 // NVLink, summed in rank order (deterministic) and the same epilogue runs in a 1-thread kernel.
 #pragma once
 #include <algorithm>
+#include <cstdlib>
 #include "kb_objects.h"
 #include "kb_spmv.cuh"
 #include "kb_spmv_bulk.cuh"
+#include "kb_p2p.cuh"
 
+const KbP2PDev* kb_p2p_dev(kb_ctx_s* c);        // host copy
+const KbP2PDev* kb_p2p_dev_ptr(kb_ctx_s* c);    // device-resident copy (kernel argument)
+
+// What the last CTA of a reducing kernel does with the local canonical sums (called by ALL its threads):
+//   single GPU            : thread 0 runs the scalar epilogue `fin`
+//   shard, peer path (p2p): NVLink all-reduce INSIDE this kernel, then `fin` — compute + collective in one launch
+//   shard, NCCL path      : store the local sums to `slots`; all-gather + epilogue follow as separate launches
 template <class Fin>
 struct KbFinish {
     Fin fin;
-    double* slots;   // nullptr => run the epilogue inline
-    int nred;
-    __device__ void operator()(const double* s) const {
-        if (slots) { for (int r = 0; r < nred; ++r) slots[r] = s[r]; }
-        else fin(s);
+    double* slots = nullptr;
+    int nred = 0;
+    const KbP2PDev* p2p = nullptr;
+    template <int BAR>
+    __device__ void coop(double* ssum) const {
+        if (p2p) {
+            kb_p2p_allreduce_block<BAR>(*p2p, ssum, nred);
+            if (threadIdx.x == 0) fin(ssum);
+        } else if (threadIdx.x == 0) {
+            if (slots) { for (int r = 0; r < nred; ++r) slots[r] = ssum[r]; }
+            else fin(ssum);
+        }
     }
 };
+template <class Fin>
+static KbFinish<Fin> kb_make_fin(kb_ctx_s* c, Fin fin, bool dist, double* slots, int nred) {
+    KbFinish<Fin> f;
+    f.fin = fin; f.nred = nred;
+    if (dist && c->size > 1) {
+        f.p2p = kb_p2p_dev_ptr(c);
+        f.slots = f.p2p ? nullptr : slots;
+    }
+    return f;
+}
 
 template <class Fin, bool WD, bool YD>
 struct KbSpmvEpi {
@@ -30,7 +56,8 @@ struct KbSpmvEpi {
     __device__ bool skip() const {
         return ctl != nullptr && (ctl->done != 0 || ((skip_mask & 1) && ctl->early != 0) || ((skip_mask & 2) && ctl->cycle_break != 0));
     }
-    __device__ void finish(const double* s) const { fin(s); }
+    template <int BAR>
+    __device__ void finish_block(double* ssum) const { fin.template coop<BAR>(ssum); }
 };
 
 template <class Fin>
@@ -41,6 +68,7 @@ __global__ void kb_fin_kernel(Fin fin, KbCtl* ctl, const double* sums, int skip_
 
 template <class Fin>
 static int kb_finish_dist(kb_ctx_s* c, Fin fin, KbCtl* ctl, double* slots, int nred, bool skip_early = false) {
+    if (kb_p2p_dev_ptr(c)) return KB_OK;   // peer path: all-reduce + epilogue already ran inside the reducing kernel
     KB_TRY(kb_allreduce_slots(c, slots, nred));
     KbLaunch L(c, KB_K_SMALL);
     kb_fin_kernel<Fin><<<1, 1, 0, c->stream>>>(fin, ctl, slots, skip_early ? 1 : 0);
@@ -48,16 +76,12 @@ static int kb_finish_dist(kb_ctx_s* c, Fin fin, KbCtl* ctl, double* slots, int n
     return KB_OK;
 }
 
-// y = A x | y = b - A x with fused dots; dispatches on the kernel kind chosen at upload.
+// one launch over a set of canonical tiles (all tiles when list == nullptr); dispatches on the kernel kind
 template <class Epi, bool RESID>
-static int kb_launch_spmv(kb_csr_s* A, const double* x, double* y, const double* b, const double* w, double* partials,
-                          size_t pstride, Epi epi) {
-    if (A->n == 0) return KB_OK;
+static int kb_launch_spmv_tiles(kb_csr_s* A, KbSpmvArgs a, Epi epi, const int* list, int count, int finalize) {
+    if (count <= 0) return KB_OK;
     kb_ctx_s* c = A->ctx;
-    KbSpmvArgs a{};
-    a.row_ptr = A->row_ptr; a.col = A->col; a.vals = A->vals; a.x = x; a.y = y; a.b = b; a.w = w;
-    a.n = (int)A->n; a.tile0 = 0; a.ntiles_launch = A->ntiles; a.ntiles_total = A->ntiles; a.tile_list = nullptr; a.finalize = 1;
-    a.partials = partials; a.pstride = pstride; a.ticket = c->ticket;
+    a.tile_list = list; a.tile0 = 0; a.ntiles_launch = count; a.finalize = finalize;
     if (A->kind == 2) {
         auto kfn = kb_spmv_bulk<Epi, RESID>;
         if (!c->configured.count((const void*)kfn)) {
@@ -65,17 +89,44 @@ static int kb_launch_spmv(kb_csr_s* A, const double* x, double* y, const double*
             c->configured.insert((const void*)kfn);
         }
         KbChunkTable tb{A->tile_chunk, A->chunk_row, A->chunk_nz};
-        const int grid = std::min(2 * c->sm_count, A->ntiles);
+        const int grid = std::min(2 * c->sm_count, count);
         KbLaunch L(c, KB_K_SPMV);
         kfn<<<grid, KB_BULK_THREADS, sizeof(KbBulkSmem), c->stream>>>(a, tb, epi);
         KB_CUDA(cudaGetLastError());
         return KB_OK;
     }
     KbLaunch L(c, KB_K_SPMV);
-    if (A->kind == 0) kb_spmv_stream<Epi, RESID><<<A->ntiles, KB_THREADS, 0, c->stream>>>(a, epi);
-    else if (A->vec == 8) kb_spmv_vector<Epi, RESID, 8><<<A->ntiles, KB_THREADS, 0, c->stream>>>(a, epi);
-    else if (A->vec == 16) kb_spmv_vector<Epi, RESID, 16><<<A->ntiles, KB_THREADS, 0, c->stream>>>(a, epi);
-    else kb_spmv_vector<Epi, RESID, 32><<<A->ntiles, KB_THREADS, 0, c->stream>>>(a, epi);
+    if (A->kind == 0) kb_spmv_stream<Epi, RESID><<<count, KB_THREADS, 0, c->stream>>>(a, epi);
+    else if (A->vec == 8) kb_spmv_vector<Epi, RESID, 8><<<count, KB_THREADS, 0, c->stream>>>(a, epi);
+    else if (A->vec == 16) kb_spmv_vector<Epi, RESID, 16><<<count, KB_THREADS, 0, c->stream>>>(a, epi);
+    else kb_spmv_vector<Epi, RESID, 32><<<count, KB_THREADS, 0, c->stream>>>(a, epi);
     KB_CUDA(cudaGetLastError());
     return KB_OK;
+}
+
+// y = A x | y = b - A x with fused dots.  On a shard (halo_x != nullptr: the operand with its ghost tail) the
+// halo transfer is started first, the tiles without ghost columns are multiplied while it is in flight, and
+// the boundary tiles follow once the ghosts have landed; the dot partials of both launches meet in the last
+// CTA of the second one, so the reduction tree is unchanged.
+template <class Epi, bool RESID>
+static int kb_launch_spmv(kb_csr_s* A, const double* x, double* y, const double* b, const double* w, double* partials,
+                          size_t pstride, Epi epi, double* halo_x = nullptr) {
+    kb_ctx_s* c = A->ctx;
+    const bool dist = halo_x != nullptr && A->dist && c->size > 1;
+    if (A->n == 0) { if (dist) return kb_halo_exchange(A, halo_x); return KB_OK; }
+    KbSpmvArgs a{};
+    a.row_ptr = A->row_ptr; a.col = A->col; a.vals = A->vals; a.x = x; a.y = y; a.b = b; a.w = w;
+    a.n = (int)A->n; a.ntiles_total = A->ntiles;
+    a.partials = partials; a.pstride = pstride; a.ticket = c->ticket;
+    if (dist) KB_TRY(kb_halo_begin(A, halo_x));
+    static const int split_env = getenv("KB_HALO_SPLIT") ? atoi(getenv("KB_HALO_SPLIT")) : -1;
+    // splitting costs one more launch: worth it only while the interior is much larger than the boundary
+    const bool split = split_env >= 0 ? (split_env != 0) : (A->n_interior >= 24 * A->n_boundary);
+    if (dist && split && A->n_interior > 0 && A->n_boundary > 0) {
+        KB_TRY((kb_launch_spmv_tiles<Epi, RESID>(A, a, epi, A->tiles_interior, A->n_interior, 0)));
+        KB_TRY(kb_halo_end(A, halo_x));
+        return kb_launch_spmv_tiles<Epi, RESID>(A, a, epi, A->tiles_boundary, A->n_boundary, 1);
+    }
+    if (dist) KB_TRY(kb_halo_end(A, halo_x));
+    return kb_launch_spmv_tiles<Epi, RESID>(A, a, epi, nullptr, A->ntiles, 1);
 }

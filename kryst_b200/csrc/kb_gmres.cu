@@ -111,8 +111,7 @@ __global__ void kb_arnoldi_fin_kernel(KbGmresDev g, const double* sums, int j) {
 template <bool NORM>
 struct GsUpdateOp : KbRedBase {
     static constexpr int NRED = NORM ? 1 : 0;
-    static constexpr bool COOP = true;
-    KbGmresDev g; double* w; const double* hsrc; double* slots; int ncols;
+    KbGmresDev g; double* w; const double* hsrc; double* slots; int ncols; const KbP2PDev* p2p;
     __device__ bool skip() const { return g.ctl->done != 0 || g.ctl->cycle_break != 0; }
     __device__ void pair(long long i, bool has1, double* red) const {
         if (has1) {
@@ -132,8 +131,9 @@ struct GsUpdateOp : KbRedBase {
             if (NORM) red[0] = t * t + 0.0;
         }
     }
-    __device__ void finish_coop(const double* sums) const {
-        if (slots) { if (threadIdx.x == 0) slots[0] = sums[0]; }
+    __device__ void finish_block(double* sums) const {
+        if (p2p) { kb_p2p_allreduce_block<0>(*p2p, sums, 1); kb_arnoldi_fin(g, sums[0], ncols - 1); }
+        else if (slots) { if (threadIdx.x == 0) slots[0] = sums[0]; }
         else kb_arnoldi_fin(g, sums[0], ncols - 1);
     }
 };
@@ -153,7 +153,7 @@ struct ScaleOp : KbRedBase {
         if (has1) { double2 t = kb_ld2(src + i); kb_st2(dst + i, make_double2(t.x / d, t.y / d)); }
         else dst[i] = src[i] / d;
     }
-    __device__ void finish(const double*) const {}
+    __device__ void finish_block(double*) const {}
 };
 
 // back-substitution (gmres.rs:180-192), one block; y -> ctl->y
@@ -199,7 +199,7 @@ struct UpdateXOp : KbRedBase {
             (RIGHT ? out : x)[i] = t;
         }
     }
-    __device__ void finish(const double*) const {}
+    __device__ void finish_block(double*) const {}
 };
 struct AddOp : KbRedBase {            // x += z
     static constexpr int NRED = 0;
@@ -209,7 +209,7 @@ struct AddOp : KbRedBase {            // x += z
         if (has1) { double2 a = kb_ld2(x + i), b = kb_ld2(z + i); kb_st2(x + i, make_double2(a.x + b.x, a.y + b.y)); }
         else x[i] = x[i] + z[i];
     }
-    __device__ void finish(const double*) const {}
+    __device__ void finish_block(double*) const {}
 };
 
 // ---- scalar epilogues of the residual / norm kernels -------------------------------------------------------
@@ -259,7 +259,7 @@ struct NormOp : KbRedBase {
         if (has1) { double2 t = kb_ld2(z + i); red[0] = t.x * t.x + t.y * t.y; }
         else red[0] = z[i] * z[i] + 0.0;
     }
-    __device__ void finish(const double* s) const { fin(s); }
+    __device__ void finish_block(double* s) const { fin.template coop<0>(s); }
 };
 
 // ---- workspace --------------------------------------------------------------------------------------------
@@ -318,7 +318,7 @@ static int gm_start_vector(GmPlan& P) {
     if (P.side == KB_SIDE_LEFT) {
         KB_TRY(kb_pc_apply_dev(P.pc, w->r, w->z, w->ctl, 0));
         NormOp<GmLeftNormFin> op; op.partials = w->partials; op.pstride = w->pstride; op.z = w->z; op.ctl = w->ctl;
-        op.fin.fin = GmLeftNormFin{w->ctl}; op.fin.slots = P.dist ? w->slots : nullptr; op.fin.nred = 1;
+        op.fin = kb_make_fin(c, GmLeftNormFin{w->ctl}, P.dist, w->slots, 1);
         KB_TRY(gm_tile(A, op, KB_K_SMALL));
         if (P.dist) KB_TRY((kb_finish_dist<GmLeftNormFin>(c, GmLeftNormFin{w->ctl}, w->ctl, w->slots, 1)));
         src = w->z;
@@ -335,25 +335,22 @@ static int gm_inner_iteration(GmPlan& P, int j) {
     double* vj = w->V + (size_t)j * w->ld;
     const int ncols = j + 1;
     typedef KbSpmvEpi<GmNoFin, false, false> Epi;
-    Epi epi; epi.ctl = ctl; epi.skip_mask = 2; epi.fin.fin = GmNoFin{}; epi.fin.slots = nullptr; epi.fin.nred = 0;
+    Epi epi; epi.ctl = ctl; epi.skip_mask = 2; epi.fin = kb_make_fin(c, GmNoFin{}, false, nullptr, 0);
     if (P.side == KB_SIDE_LEFT) {            // w = M^-1 (A v_j)
-        if (P.dist) KB_TRY(kb_halo_exchange(A, vj));
-        KB_TRY((kb_launch_spmv<Epi, false>(A, vj, w->z, nullptr, nullptr, nullptr, 0, epi)));
+        KB_TRY((kb_launch_spmv<Epi, false>(A, vj, w->z, nullptr, nullptr, nullptr, 0, epi, P.dist ? vj : nullptr)));
         KB_TRY(kb_pc_apply_dev(P.pc, w->z, w->w, ctl, 2));
     } else if (P.side == KB_SIDE_RIGHT) {    // w = A (M^-1 v_j)
         KB_TRY(kb_pc_apply_dev(P.pc, vj, w->t, ctl, 2));
-        if (P.dist) KB_TRY(kb_halo_exchange(A, w->t));
-        KB_TRY((kb_launch_spmv<Epi, false>(A, w->t, w->w, nullptr, nullptr, nullptr, 0, epi)));
+        KB_TRY((kb_launch_spmv<Epi, false>(A, w->t, w->w, nullptr, nullptr, nullptr, 0, epi, P.dist ? w->t : nullptr)));
     } else {                                 // w = A v_j   (gmres.rs:80-81)
-        if (P.dist) KB_TRY(kb_halo_exchange(A, vj));
-        KB_TRY((kb_launch_spmv<Epi, false>(A, vj, w->w, nullptr, nullptr, nullptr, 0, epi)));
+        KB_TRY((kb_launch_spmv<Epi, false>(A, vj, w->w, nullptr, nullptr, nullptr, 0, epi, P.dist ? vj : nullptr)));
     }
     {   // h1 = V^T w ; w -= V h1
         { KbLaunch L(c, KB_K_GS_DOT); kb_gs_dot<<<A->ntiles, KB_THREADS, 0, c->stream>>>(P.g, w->w, (long long)A->n, w->partials, w->pstride, ncols); }
         double* dst = P.dist ? w->slots : &ctl->h1[0];
         { KbLaunch L(c, KB_K_SMALL); kb_gs_level2<<<ncols, KB_THREADS, 0, c->stream>>>(ctl, w->partials, w->pstride, A->ntiles, dst); }
         if (P.dist) KB_TRY(kb_allreduce_slots(c, w->slots, ncols));
-        GsUpdateOp<false> op; op.partials = nullptr; op.pstride = 0; op.g = P.g; op.w = w->w; op.hsrc = P.g.h1src; op.slots = nullptr; op.ncols = ncols;
+        GsUpdateOp<false> op; op.partials = nullptr; op.pstride = 0; op.g = P.g; op.w = w->w; op.hsrc = P.g.h1src; op.slots = nullptr; op.ncols = ncols; op.p2p = nullptr;
         KB_TRY(gm_tile(A, op, KB_K_GS_UPDATE));
     }
     {   // h2 = V^T w ; w -= V h2 fused with ||w||^2 ; Arnoldi epilogue (H column, Givens, stop test)
@@ -364,9 +361,10 @@ static int gm_inner_iteration(GmPlan& P, int j) {
         if (P.dist) KB_TRY(kb_allreduce_slots(c, s2, ncols));
         double* s3 = w->slots + 2 * (KB_MAX_RESTART + 8);
         GsUpdateOp<true> op; op.partials = w->partials; op.pstride = w->pstride; op.g = P.g; op.w = w->w; op.hsrc = P.g.h2src;
-        op.slots = P.dist ? s3 : nullptr; op.ncols = ncols;
+        op.p2p = P.dist ? kb_p2p_dev_ptr(c) : nullptr;
+        op.slots = (P.dist && !op.p2p) ? s3 : nullptr; op.ncols = ncols;
         KB_TRY(gm_tile(A, op, KB_K_GS_UPDATE));
-        if (P.dist) {
+        if (P.dist && !op.p2p) {
             KB_TRY(kb_allreduce_slots(c, s3, 1));
             KbLaunch L(c, KB_K_SMALL);
             kb_arnoldi_fin_kernel<<<1, KB_THREADS, 0, c->stream>>>(P.g, s3, j);
@@ -406,10 +404,9 @@ static int gm_cycle(GmPlan& P) {
         KB_TRY(gm_tile(A, op, KB_K_GS_UPDATE));
     }
     {   // r = b - A x ; beta = ||r|| ; converged = beta < tol * res0 (gmres.rs:388-398)
-        if (P.dist) KB_TRY(kb_halo_exchange(A, w->x));
         typedef KbSpmvEpi<GmCycleFin, false, true> Epi;
-        Epi epi; epi.ctl = w->ctl; epi.fin.fin = GmCycleFin{w->ctl}; epi.fin.slots = P.dist ? w->slots : nullptr; epi.fin.nred = 1;
-        KB_TRY((kb_launch_spmv<Epi, true>(A, w->x, w->r, w->b, nullptr, w->partials, w->pstride, epi)));
+        Epi epi; epi.ctl = w->ctl; epi.fin = kb_make_fin(c, GmCycleFin{w->ctl}, P.dist, w->slots, 1);
+        KB_TRY((kb_launch_spmv<Epi, true>(A, w->x, w->r, w->b, nullptr, w->partials, w->pstride, epi, P.dist ? w->x : nullptr)));
         if (P.dist) KB_TRY((kb_finish_dist<GmCycleFin>(c, GmCycleFin{w->ctl}, w->ctl, w->slots, 1)));
     }
     return gm_start_vector(P);
@@ -447,11 +444,10 @@ extern "C" int kb_gmres_solve(kb_csr A, kb_pc pc, const double* b, double* x, ui
     c->profiling = profile;
     int st = KB_OK;
     do {
-        if (dist && (st = kb_halo_exchange(A, w->x)) != KB_OK) break;
         {   // r0 = b - A x ; beta = ||r0|| (gmres.rs:221-229)
             typedef KbSpmvEpi<GmInitFin, false, true> Epi;
-            Epi epi; epi.ctl = nullptr; epi.fin.fin = GmInitFin{w->ctl}; epi.fin.slots = dist ? w->slots : nullptr; epi.fin.nred = 1;
-            if ((st = kb_launch_spmv<Epi, true>(A, w->x, w->r, w->b, nullptr, w->partials, w->pstride, epi)) != KB_OK) break;
+            Epi epi; epi.ctl = nullptr; epi.fin = kb_make_fin(c, GmInitFin{w->ctl}, dist, w->slots, 1);
+            if ((st = kb_launch_spmv<Epi, true>(A, w->x, w->r, w->b, nullptr, w->partials, w->pstride, epi, dist ? w->x : nullptr)) != KB_OK) break;
             if (dist && (st = kb_finish_dist<GmInitFin>(c, GmInitFin{w->ctl}, w->ctl, w->slots, 1)) != KB_OK) break;
         }
         if ((st = gm_start_vector(P)) != KB_OK) break;
@@ -462,6 +458,7 @@ extern "C" int kb_gmres_solve(kb_csr A, kb_pc pc, const double* b, double* x, ui
             cudaStreamSynchronize(c->stream) != cudaSuccess) { kb_set_error("gmres: readback failed"); st = KB_SOLVE_ERROR; break; }
         stats->iterations = h->iter; stats->final_residual = h->res; stats->converged = h->converged; stats->breakdown = h->happy;
         st = h->status;
+        if (dist && kb_p2p_error(c)) { kb_set_error("%s: peer-memory collective timed out", "gmres"); st = KB_SOLVE_ERROR; break; }
         if (st == KB_OK) {
             if (cudaMemcpyAsync(x, w->x, w->n * sizeof(double), dev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, c->stream) != cudaSuccess ||
                 cudaStreamSynchronize(c->stream) != cudaSuccess) { kb_set_error("gmres: copy-out of x failed"); st = KB_SOLVE_ERROR; }

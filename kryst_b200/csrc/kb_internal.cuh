@@ -100,6 +100,7 @@ struct kb_ctx_s {
     // communicator (one process per GPU)
     int rank = 0, size = 1;
     void* nccl = nullptr;                // ncclComm_t
+    void* p2p = nullptr;                 // KbP2PHost: IPC-mapped all-reduce mailboxes (NVLink peer path)
     double* comm_buf = nullptr;          // device scratch for all-gathered partial scalars
     double* host_scalar = nullptr;       // pinned
     int refs = 1;                        // the user handle + one per operator created on this context
@@ -175,13 +176,8 @@ __device__ __forceinline__ bool kb_arrive_last(unsigned* ticket, unsigned nblock
 //   Op::NRED                      number of fused reductions
 //   bool Op::skip() const         early-out (e.g. ctl->done)
 //   void Op::pair(i, has1, red)   process elements i (and i+1 if has1); red[r] = e_r(i) + e_r(i+1)
-//   void Op::finish(sums)         scalar epilogue, thread 0 of the last block
+//   void Op::finish_block(ssum)   epilogue, called by ALL threads of the last block (sums in shared memory)
 // ---------------------------------------------------------------------------------------------
-template <class T, class = void>
-struct kb_is_coop { static constexpr bool value = false; };
-template <class T>
-struct kb_is_coop<T, decltype((void)T::COOP)> { static constexpr bool value = T::COOP; };
-
 template <class Op>
 __global__ void __launch_bounds__(KB_THREADS) kb_tile_kernel(Op op) {
     if (op.skip()) return;
@@ -209,17 +205,13 @@ __global__ void __launch_bounds__(KB_THREADS) kb_tile_kernel(Op op) {
             double sums[NR];
 #pragma unroll
             for (int r = 0; r < NR; ++r) sums[r] = kb_level2(op.partials + (size_t)r * op.pstride, (int)gridDim.x, sm);
-            if constexpr (kb_is_coop<Op>::value) {
-                __shared__ double ssum[NR];
-                if (threadIdx.x == 0) {
+            __shared__ double ssum[NR];
+            if (threadIdx.x == 0) {
 #pragma unroll
-                    for (int r = 0; r < NR; ++r) ssum[r] = sums[r];
-                }
-                __syncthreads();
-                op.finish_coop(ssum);      // every thread of the last block (small dense epilogues)
-            } else {
-                if (threadIdx.x == 0) op.finish(sums);
+                for (int r = 0; r < NR; ++r) ssum[r] = sums[r];
             }
+            __syncthreads();
+            op.finish_block(ssum);      // every thread of the last block (scalar epilogue / fused all-reduce)
         }
     }
 }

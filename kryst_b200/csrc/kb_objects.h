@@ -31,6 +31,9 @@ struct kb_csr_s {
     uint64_t n_global = 0, row_lo = 0, row_hi = 0, nghost = 0;
     uint64_t* ghosts = nullptr;  // device: sorted unique global ids of ghost columns
     KbHalo* halo = nullptr;
+    int* tiles_interior = nullptr;   // tiles without ghost columns / with ghost columns (device lists)
+    int* tiles_boundary = nullptr;
+    int n_interior = 0, n_boundary = 0;
     // scratch for host-slice matvec
     double* x_tmp = nullptr;
     double* y_tmp = nullptr;
@@ -85,7 +88,10 @@ void kb_csr_unref(kb_csr_s* A);
 // ---- internal launch API (implemented across the .cu files) ---------------------------------
 int kb_csr_spmv_plain(kb_csr_s* A, const double* d_x, double* d_y);
 int kb_halo_exchange(kb_csr_s* A, double* d_x);   // fills ghost entries of d_x (no-op when !dist)
+int kb_halo_begin(kb_csr_s* A, double* d_x);      // start the exchange ...
+int kb_halo_end(kb_csr_s* A, double* d_x);        // ... ghost tail valid after this
 int kb_allreduce_slots(kb_ctx_s* c, double* d_vals, int count);   // rank-ordered sum, in place
+int kb_p2p_error(kb_ctx_s* c);                                    // 1 if a peer-memory spin timed out
 // z = M^-1 r on the device; kernels are no-ops when skip_ctl->done (or, per skip_mask, early / cycle_break) is set
 int kb_pc_apply_dev(kb_pc_s* pc, const double* d_r, double* d_z, const KbCtl* skip_ctl = nullptr, int skip_mask = 0);
 void kb_pcg_ws_free(KbPcgWs* w);

@@ -83,7 +83,7 @@ struct PcgInitOp : KbRedBase {        // z = D^-1 r (or r) ; p = z ; r.z ; norm
             red[1] = nt == KB_NORM_PRECONDITIONED ? (zz * zz + 0.0) : nt == KB_NORM_UNPRECONDITIONED ? (rr * rr + 0.0) : 0.0;
         }
     }
-    __device__ void finish(const double* s) const { fin(s); }
+    __device__ void finish_block(double* s) const { fin.template coop<0>(s); }
 };
 
 template <class Fin>
@@ -111,7 +111,7 @@ struct PcgUpdateOp : KbRedBase {      // K3
             red[1] = nt == KB_NORM_PRECONDITIONED ? (zz * zz + 0.0) : nt == KB_NORM_UNPRECONDITIONED ? (rr * rr + 0.0) : 0.0;
         }
     }
-    __device__ void finish(const double* s) const { fin(s); }
+    __device__ void finish_block(double* s) const { fin.template coop<0>(s); }
 };
 
 struct PcgXpayOp : KbRedBase {        // K4: p = z + beta p  (pcg.rs:215-217)
@@ -123,7 +123,7 @@ struct PcgXpayOp : KbRedBase {        // K4: p = z + beta p  (pcg.rs:215-217)
         if (has1) { double2 zz = kb_ld2(z + i), pp = kb_ld2(p + i); kb_st2(p + i, make_double2(zz.x + beta * pp.x, zz.y + beta * pp.y)); }
         else p[i] = z[i] + beta * p[i];
     }
-    __device__ void finish(const double*) const {}
+    __device__ void finish_block(double*) const {}
 };
 
 // ---- workspace ----------------------------------------------------------------------------------
@@ -173,16 +173,15 @@ template <bool DIST>
 static int pcg_launch_iteration(kb_csr_s* A, const kb_pc_s* pc, KbPcgWs* w) {
     kb_ctx_s* c = A->ctx;
     const double* inv = pc ? pc->inv_diag : nullptr;
-    if (DIST) KB_TRY(kb_halo_exchange(A, w->p));
     {   // K2
-        KbSpmvEpi<PcgApFin, true, false> epi; epi.ctl = w->ctl; epi.fin.fin = PcgApFin{w->ctl}; epi.fin.slots = DIST ? w->slots : nullptr; epi.fin.nred = 1;
-        KB_TRY((kb_launch_spmv<KbSpmvEpi<PcgApFin, true, false>, false>(A, w->p, w->ap, nullptr, w->p, w->partials, w->pstride, epi)));
+        KbSpmvEpi<PcgApFin, true, false> epi; epi.ctl = w->ctl; epi.fin = kb_make_fin(c, PcgApFin{w->ctl}, DIST, w->slots, 1);
+        KB_TRY((kb_launch_spmv<KbSpmvEpi<PcgApFin, true, false>, false>(A, w->p, w->ap, nullptr, w->p, w->partials, w->pstride, epi, DIST ? w->p : nullptr)));
         if (DIST) KB_TRY((kb_finish_dist<PcgApFin>(c, PcgApFin{w->ctl}, w->ctl, w->slots, 1)));
     }
     {   // K3
         PcgUpdateOp<PcgUpdateFin> op; op.n = (long long)w->n; op.partials = w->partials; op.pstride = w->pstride; op.ticket = c->ticket;
         op.x = w->x; op.p = w->p; op.r = w->r; op.ap = w->ap; op.inv = inv; op.z = w->z; op.ctl = w->ctl;
-        op.fin.fin = PcgUpdateFin{w->ctl}; op.fin.slots = DIST ? w->slots : nullptr; op.fin.nred = 2;
+        op.fin = kb_make_fin(c, PcgUpdateFin{w->ctl}, DIST, w->slots, 2);
         { KbLaunch L(c, KB_K_PCG_UPDATE); kb_tile_kernel<<<A->ntiles, KB_THREADS, 0, c->stream>>>(op); }
         KB_CUDA(cudaGetLastError());
         if (DIST) KB_TRY((kb_finish_dist<PcgUpdateFin>(c, PcgUpdateFin{w->ctl}, w->ctl, w->slots, 2)));
@@ -234,15 +233,14 @@ extern "C" int kb_pcg_solve(kb_csr A, kb_pc pc, const double* b, double* x, doub
     int st = KB_OK;
     do {
         // r = b - A x  (pcg.rs:119-124)
-        if (dist && (st = kb_halo_exchange(A, w->x)) != KB_OK) break;
         {
-            KbSpmvEpi<PcgApFin, false, false> epi; epi.ctl = nullptr; epi.fin.fin = PcgApFin{w->ctl}; epi.fin.slots = nullptr; epi.fin.nred = 0;
-            if ((st = kb_launch_spmv<KbSpmvEpi<PcgApFin, false, false>, true>(A, w->x, w->r, w->b, nullptr, w->partials, w->pstride, epi)) != KB_OK) break;
+            KbSpmvEpi<PcgApFin, false, false> epi; epi.ctl = nullptr; epi.fin = kb_make_fin(c, PcgApFin{w->ctl}, false, nullptr, 0);
+            if ((st = kb_launch_spmv<KbSpmvEpi<PcgApFin, false, false>, true>(A, w->x, w->r, w->b, nullptr, w->partials, w->pstride, epi, dist ? w->x : nullptr)) != KB_OK) break;
         }
         {   // z, p, rz, res0, first history entry (pcg.rs:126-146)
             PcgInitOp<PcgInitFin> op; op.n = (long long)w->n; op.partials = w->partials; op.pstride = w->pstride; op.ticket = c->ticket;
             op.r = w->r; op.inv = pc ? pc->inv_diag : nullptr; op.z = w->z; op.p = w->p; op.ctl = w->ctl;
-            op.fin.fin = PcgInitFin{w->ctl}; op.fin.slots = dist ? w->slots : nullptr; op.fin.nred = 2;
+            op.fin = kb_make_fin(c, PcgInitFin{w->ctl}, dist, w->slots, 2);
             { KbLaunch L(c, KB_K_INIT); kb_tile_kernel<<<A->ntiles, KB_THREADS, 0, c->stream>>>(op); }
             if (cudaGetLastError() != cudaSuccess) { kb_set_error("pcg init launch failed"); st = KB_SOLVE_ERROR; break; }
             if (dist && (st = kb_finish_dist<PcgInitFin>(c, PcgInitFin{w->ctl}, w->ctl, w->slots, 2)) != KB_OK) break;
@@ -256,6 +254,7 @@ extern "C" int kb_pcg_solve(kb_csr A, kb_pc pc, const double* b, double* x, doub
             cudaStreamSynchronize(c->stream) != cudaSuccess) { kb_set_error("pcg: readback failed"); st = KB_SOLVE_ERROR; break; }
         stats->iterations = h->iter; stats->final_residual = h->res; stats->converged = h->converged; stats->breakdown = 0;
         st = h->status;
+        if (dist && kb_p2p_error(c)) { kb_set_error("%s: peer-memory collective timed out", "pcg"); st = KB_SOLVE_ERROR; break; }
         uint64_t hl = std::min<uint64_t>(h->hist_len, hist_cap);
         if (hist_len) *hist_len = h->hist_len;
         if (hl && cudaMemcpyAsync(history, w->hist, hl * sizeof(double), cudaMemcpyDeviceToHost, c->stream) != cudaSuccess) { st = KB_SOLVE_ERROR; break; }

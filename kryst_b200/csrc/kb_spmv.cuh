@@ -38,7 +38,7 @@ struct KbSpmvArgs {
     unsigned* ticket;
 };
 
-// Epi: struct with static constexpr bool WDOT, YDOT (slot order: <w,y> then <y,y>); __device__ bool skip() const; __device__ void finish(const double* sums) const
+// Epi: struct with static constexpr bool WDOT, YDOT (slot order: <w,y> then <y,y>); __device__ bool skip() const; template <int BAR> __device__ void finish_block(double* ssum) const  (all threads of the last CTA)
 template <class Epi, bool RESID>
 __global__ void __launch_bounds__(KB_THREADS) kb_spmv_stream(KbSpmvArgs a, Epi epi) {
     if (epi.skip()) return;
@@ -135,10 +135,11 @@ __global__ void __launch_bounds__(KB_THREADS) kb_spmv_stream(KbSpmvArgs a, Epi e
             for (int d = 0; d < ND; ++d) a.partials[(size_t)d * a.pstride + tile] = out[d];
         }
         if (a.finalize && kb_arrive_last(a.ticket, gridDim.x, &sflag)) {
-            double sums[ND];
+            __shared__ double ssum[ND];
 #pragma unroll
-            for (int d = 0; d < ND; ++d) sums[d] = kb_level2(a.partials + (size_t)d * a.pstride, a.ntiles_total, s_red);
-            if (tid == 0) epi.finish(sums);
+            for (int d = 0; d < ND; ++d) { double v = kb_level2(a.partials + (size_t)d * a.pstride, a.ntiles_total, s_red); if (tid == 0) ssum[d] = v; }
+            __syncthreads();
+            epi.template finish_block<0>(ssum);
         }
     }
 }
@@ -197,10 +198,11 @@ __global__ void __launch_bounds__(KB_THREADS) kb_spmv_vector(KbSpmvArgs a, Epi e
             for (int d = 0; d < ND; ++d) a.partials[(size_t)d * a.pstride + tile] = out[d];
         }
         if (a.finalize && kb_arrive_last(a.ticket, gridDim.x, &sflag)) {
-            double sums[ND];
+            __shared__ double ssum[ND];
 #pragma unroll
-            for (int d = 0; d < ND; ++d) sums[d] = kb_level2(a.partials + (size_t)d * a.pstride, a.ntiles_total, s_red);
-            if (tid == 0) epi.finish(sums);
+            for (int d = 0; d < ND; ++d) { double v = kb_level2(a.partials + (size_t)d * a.pstride, a.ntiles_total, s_red); if (tid == 0) ssum[d] = v; }
+            __syncthreads();
+            epi.template finish_block<0>(ssum);
         }
     }
 }
@@ -209,5 +211,6 @@ __global__ void __launch_bounds__(KB_THREADS) kb_spmv_vector(KbSpmvArgs a, Epi e
 struct KbEpiNone {
     static constexpr bool WDOT = false, YDOT = false;
     __device__ bool skip() const { return false; }
-    __device__ void finish(const double*) const {}
+    template <int BAR>
+    __device__ void finish_block(double*) const {}
 };

@@ -237,10 +237,11 @@ __global__ void __launch_bounds__(KB_BULK_THREADS, 2) kb_spmv_bulk(KbSpmvArgs a,
             }
             kb_bar_consumers();
             if (S.sflag) {
-                double sums[ND];
+                double* ssum = &S.d[0][0];     // tile buffer is free now
 #pragma unroll
-                for (int d = 0; d < ND; ++d) sums[d] = kb_level2_c(a.partials + (size_t)d * a.pstride, a.ntiles_total, S.red);
-                if (tid == 0) epi.finish(sums);
+                for (int d = 0; d < ND; ++d) { double v = kb_level2_c(a.partials + (size_t)d * a.pstride, a.ntiles_total, S.red); if (tid == 0) ssum[d] = v; }
+                kb_bar_consumers();
+                epi.template finish_block<1>(ssum);
             }
         }
     }
