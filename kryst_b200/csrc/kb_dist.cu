@@ -19,6 +19,7 @@
 #include <cub/cub.cuh>
 #include "kb_objects.h"
 #include "kb_p2p.cuh"
+#include "kb_spmv.cuh"
 
 // ---- NCCL through dlopen ----------------------------------------------------------------------------------
 struct NcclApi {
@@ -264,13 +265,14 @@ struct KbHalo {
     int* send_q = nullptr; int* send_pos = nullptr;
     unsigned long long* seqs = nullptr; unsigned* tickets = nullptr;
     KbHaloDev dev{};
+    KbHaloDev* dev_copy = nullptr;
     int push_grid = 1, recv_grid = 1;
     kb_ctx_s* ctx = nullptr;
 };
 void kb_halo_free(KbHalo* h) {
     if (!h) return;
     if (h->p2p && h->ctx) kb_ipc_release(h->ctx, h->ptrs);
-    KB_FREE(h->send_idx); KB_FREE(h->send_buf); KB_FREE(h->send_q); KB_FREE(h->send_pos); KB_FREE(h->seqs); KB_FREE(h->tickets);
+    KB_FREE(h->send_idx); KB_FREE(h->send_buf); KB_FREE(h->send_q); KB_FREE(h->send_pos); KB_FREE(h->seqs); KB_FREE(h->tickets); KB_FREE(h->dev_copy);
     delete h;
 }
 
@@ -278,11 +280,17 @@ void kb_halo_free(KbHalo* h) {
 // push #seq: every boundary value is stored straight into the destination GPU's ghost_in[parity] over NVLink;
 // the last CTA publishes the sequence number in the destination's flag slot.  Flow control: before reusing
 // a parity buffer the pusher checks that the destination acknowledged push seq-2.
-__global__ void __launch_bounds__(KB_THREADS) kb_halo_push(KbHaloDev h, const double* __restrict__ x) {
+// (the descriptor is read through a pointer: indexing a by-value kernel parameter with a runtime rank would
+//  force every thread to spill the whole struct to local memory)
+__global__ void __launch_bounds__(KB_THREADS) kb_halo_push(const KbHaloDev* __restrict__ hp, const double* __restrict__ x) {
+    const KbHaloDev& h = *hp;
     __shared__ int s_last;
     const int tid = threadIdx.x;
     const unsigned long long seq = h.seqs[0] + 1ull;
     const size_t par = (size_t)(seq & 1ull);
+    // acknowledge exchange seq-1 to its sources: by stream order every kernel that read those ghosts is done
+    if (blockIdx.x == 0 && tid < h.size && h.is_src[tid] && seq > 1ull)
+        *reinterpret_cast<volatile unsigned long long*>(h.acks[tid] + h.rank) = seq - 1ull;
     if (tid < h.size && h.is_dest[tid]) {
         const volatile unsigned long long* a = h.acks[h.rank] + tid;
         unsigned spins = 0;
@@ -309,11 +317,12 @@ __global__ void __launch_bounds__(KB_THREADS) kb_halo_push(KbHaloDev h, const do
         if (tid == 0) { h.seqs[0] = seq; h.tickets[0] = 0u; }
     }
 }
-// receive #seq: wait for every source's flag, copy ghost_in[parity] into the operand's ghost tail, acknowledge.
-__global__ void __launch_bounds__(KB_THREADS) kb_halo_recv(KbHaloDev h, double* __restrict__ x) {
-    __shared__ int s_last;
+// receive (only for callers that need the ghosts in the tail of x, e.g. kb_csr_matvec; the solvers' SpMV reads
+// the mailbox directly): wait for every source's flag of the current exchange, copy ghost_in[parity] over.
+__global__ void __launch_bounds__(KB_THREADS) kb_halo_recv(const KbHaloDev* __restrict__ hp, double* __restrict__ x) {
+    const KbHaloDev& h = *hp;
     const int tid = threadIdx.x;
-    const unsigned long long seq = h.seqs[1] + 1ull;
+    const unsigned long long seq = h.seqs[0];
     const size_t par = (size_t)(seq & 1ull);
     if (tid < h.size && h.is_src[tid]) {
         const volatile unsigned long long* f = h.flags[h.rank] + par * h.size + tid;
@@ -324,20 +333,6 @@ __global__ void __launch_bounds__(KB_THREADS) kb_halo_recv(KbHaloDev h, double* 
     __syncthreads();
     const double* g = h.ghost[h.rank] + par * h.gstride;
     for (int k = blockIdx.x * KB_THREADS + tid; k < h.nghost; k += gridDim.x * KB_THREADS) x[h.n_loc + k] = __ldcv(g + k);
-    __syncthreads();
-    if (tid == 0) {
-        __threadfence();
-        const unsigned t = atomicAdd(&h.tickets[1], 1u);
-        s_last = (t == gridDim.x - 1u);
-    }
-    __syncthreads();
-    if (s_last) {
-        if (tid < h.size && h.is_src[tid]) {
-            __threadfence_system();
-            *reinterpret_cast<volatile unsigned long long*>(h.acks[tid] + h.rank) = seq;
-        }
-        if (tid == 0) { h.seqs[1] = seq; h.tickets[1] = 0u; }
-    }
 }
 __global__ void k_tile_boundary_flags(const int* __restrict__ rp, const int* __restrict__ col, int n, int nloc, int ntiles, int* __restrict__ flag) {
     const int tile = blockIdx.x;
@@ -503,8 +498,10 @@ int kb_csr_build_dist(kb_csr_s* A) {
                 D.send_idx = H->send_idx; D.send_q = H->send_q; D.send_pos = H->send_pos;
                 D.seqs = H->seqs; D.tickets = H->tickets;
                 D.err = reinterpret_cast<KbP2PHost*>(c->p2p)->dev.err;
-                H->push_grid = std::max(1, std::min(32, (H->nsend + 4 * KB_THREADS - 1) / (4 * KB_THREADS)));
-                H->recv_grid = std::max(1, std::min(32, (ng + 4 * KB_THREADS - 1) / (4 * KB_THREADS)));
+                H->push_grid = std::max(1, std::min(2 * c->sm_count, (H->nsend + KB_THREADS - 1) / KB_THREADS));   // one value per thread: latency-bound kernel
+                H->recv_grid = std::max(1, std::min(2 * c->sm_count, (ng + KB_THREADS - 1) / KB_THREADS));
+                KB_TRY(kb_alloc(&H->dev_copy, 1));
+                KB_CUDA(cudaMemcpyAsync(H->dev_copy, &H->dev, sizeof(KbHaloDev), cudaMemcpyHostToDevice, c->stream));
                 KB_CUDA(cudaStreamSynchronize(c->stream));
             }
         }
@@ -537,7 +534,7 @@ int kb_halo_begin(kb_csr_s* A, double* d_x) {
     KbHalo* H = A->halo;
     if (H->p2p) {
         KbLaunch L(c, KB_K_HALO);
-        kb_halo_push<<<H->push_grid, KB_THREADS, 0, c->stream>>>(H->dev, d_x);
+        kb_halo_push<<<H->push_grid, KB_THREADS, 0, c->stream>>>(H->dev_copy, d_x);
         KB_CUDA(cudaGetLastError());
         return KB_OK;
     }
@@ -561,11 +558,22 @@ int kb_halo_end(kb_csr_s* A, double* d_x) {
     if (!H->p2p) return KB_OK;
     kb_ctx_s* c = A->ctx;
     KbLaunch L(c, KB_K_HALO);
-    kb_halo_recv<<<H->recv_grid, KB_THREADS, 0, c->stream>>>(H->dev, d_x);
+    kb_halo_recv<<<H->recv_grid, KB_THREADS, 0, c->stream>>>(H->dev_copy, d_x);
     KB_CUDA(cudaGetLastError());
     return KB_OK;
 }
 int kb_halo_exchange(kb_csr_s* A, double* d_x) {
     KB_TRY(kb_halo_begin(A, d_x));
     return kb_halo_end(A, d_x);
+}
+bool kb_halo_fill_args(kb_csr_s* A, KbSpmvArgs* a) {
+    KbHalo* H = A->halo;
+    if (!H || !H->p2p) return false;
+    const KbHaloDev& D = H->dev;
+    a->xg_base = D.ghost[D.rank]; a->xg_stride = D.gstride; a->n_loc = D.n_loc;
+    a->hseq = D.seqs; a->hflags = D.flags[D.rank]; a->hsize = D.size; a->herr = D.err;
+    unsigned m = 0;
+    for (int q = 0; q < D.size; ++q) if (D.is_src[q]) m |= 1u << q;
+    a->hsrc_mask = m;
+    return true;
 }

@@ -12,6 +12,8 @@
 #include "kb_spmv_bulk.cuh"
 #include "kb_p2p.cuh"
 
+struct KbSpmvArgs;
+bool kb_halo_fill_args(kb_csr_s* A, KbSpmvArgs* a);   // peer path: point the SpMV at the IPC mailbox (false: NCCL path)
 const KbP2PDev* kb_p2p_dev(kb_ctx_s* c);        // host copy
 const KbP2PDev* kb_p2p_dev_ptr(kb_ctx_s* c);    // device-resident copy (kernel argument)
 
@@ -77,13 +79,13 @@ static int kb_finish_dist(kb_ctx_s* c, Fin fin, KbCtl* ctl, double* slots, int n
 }
 
 // one launch over a set of canonical tiles (all tiles when list == nullptr); dispatches on the kernel kind
-template <class Epi, bool RESID>
+template <class Epi, bool RESID, bool GH>
 static int kb_launch_spmv_tiles(kb_csr_s* A, KbSpmvArgs a, Epi epi, const int* list, int count, int finalize) {
     if (count <= 0) return KB_OK;
     kb_ctx_s* c = A->ctx;
     a.tile_list = list; a.tile0 = 0; a.ntiles_launch = count; a.finalize = finalize;
     if (A->kind == 2) {
-        auto kfn = kb_spmv_bulk<Epi, RESID>;
+        auto kfn = kb_spmv_bulk<Epi, RESID, GH>;
         if (!c->configured.count((const void*)kfn)) {
             KB_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(KbBulkSmem)));
             c->configured.insert((const void*)kfn);
@@ -96,10 +98,10 @@ static int kb_launch_spmv_tiles(kb_csr_s* A, KbSpmvArgs a, Epi epi, const int* l
         return KB_OK;
     }
     KbLaunch L(c, KB_K_SPMV);
-    if (A->kind == 0) kb_spmv_stream<Epi, RESID><<<count, KB_THREADS, 0, c->stream>>>(a, epi);
-    else if (A->vec == 8) kb_spmv_vector<Epi, RESID, 8><<<count, KB_THREADS, 0, c->stream>>>(a, epi);
-    else if (A->vec == 16) kb_spmv_vector<Epi, RESID, 16><<<count, KB_THREADS, 0, c->stream>>>(a, epi);
-    else kb_spmv_vector<Epi, RESID, 32><<<count, KB_THREADS, 0, c->stream>>>(a, epi);
+    if (A->kind == 0) kb_spmv_stream<Epi, RESID, GH><<<count, KB_THREADS, 0, c->stream>>>(a, epi);
+    else if (A->vec == 8) kb_spmv_vector<Epi, RESID, 8, GH><<<count, KB_THREADS, 0, c->stream>>>(a, epi);
+    else if (A->vec == 16) kb_spmv_vector<Epi, RESID, 16, GH><<<count, KB_THREADS, 0, c->stream>>>(a, epi);
+    else kb_spmv_vector<Epi, RESID, 32, GH><<<count, KB_THREADS, 0, c->stream>>>(a, epi);
     KB_CUDA(cudaGetLastError());
     return KB_OK;
 }
@@ -120,13 +122,18 @@ static int kb_launch_spmv(kb_csr_s* A, const double* x, double* y, const double*
     a.partials = partials; a.pstride = pstride; a.ticket = c->ticket;
     if (dist) KB_TRY(kb_halo_begin(A, halo_x));
     static const int split_env = getenv("KB_HALO_SPLIT") ? atoi(getenv("KB_HALO_SPLIT")) : -1;
-    // splitting costs one more launch: worth it only while the interior is much larger than the boundary
-    const bool split = split_env >= 0 ? (split_env != 0) : (A->n_interior >= 24 * A->n_boundary);
-    if (dist && split && A->n_interior > 0 && A->n_boundary > 0) {
-        KB_TRY((kb_launch_spmv_tiles<Epi, RESID>(A, a, epi, A->tiles_interior, A->n_interior, 0)));
-        KB_TRY(kb_halo_end(A, halo_x));
-        return kb_launch_spmv_tiles<Epi, RESID>(A, a, epi, A->tiles_boundary, A->n_boundary, 1);
+    // Interior/boundary split hides the NVLink latency behind the interior rows but costs one more launch.
+    // Measured on B200 (256^3, 2 and 8 GPUs) the single launch whose CTAs wait on the flags themselves is
+    // faster (8 GPUs: 8089 vs 7627 it/s), so the split is opt-in (KB_HALO_SPLIT=1).
+    const bool split = dist && A->n_interior > 0 && A->n_boundary > 0 && split_env > 0;
+    // peer path: the kernel that touches ghost columns waits for the neighbours' flags itself and reads the
+    // ghosts from the mailbox; NCCL path: ghosts were received into the tail of x by kb_halo_begin
+    const bool gh = dist && kb_halo_fill_args(A, &a);
+    if (split) {
+        KB_TRY((kb_launch_spmv_tiles<Epi, RESID, false>(A, a, epi, A->tiles_interior, A->n_interior, 0)));
+        if (gh) return kb_launch_spmv_tiles<Epi, RESID, true>(A, a, epi, A->tiles_boundary, A->n_boundary, 1);
+        return kb_launch_spmv_tiles<Epi, RESID, false>(A, a, epi, A->tiles_boundary, A->n_boundary, 1);
     }
-    if (dist) KB_TRY(kb_halo_end(A, halo_x));
-    return kb_launch_spmv_tiles<Epi, RESID>(A, a, epi, nullptr, A->ntiles, 1);
+    if (gh) return kb_launch_spmv_tiles<Epi, RESID, true>(A, a, epi, nullptr, A->ntiles, 1);
+    return kb_launch_spmv_tiles<Epi, RESID, false>(A, a, epi, nullptr, A->ntiles, 1);
 }

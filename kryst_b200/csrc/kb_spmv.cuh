@@ -36,12 +36,43 @@ struct KbSpmvArgs {
     double* partials;
     size_t pstride;
     unsigned* ticket;
+    // shard + peer path (GH kernels): ghost values are read straight from the IPC mailbox the neighbours
+    // pushed into, after waiting for their sequence-numbered flags (no receive kernel, no ghost copy)
+    const double* xg_base;              // ghost_in[2][xg_stride] (nullptr: ghosts live in the tail of x)
+    long long xg_stride;
+    int n_loc;
+    const unsigned long long* hseq;     // pushes done by this rank == number of the exchange being consumed
+    const unsigned long long* hflags;   // flags[2][hsize]
+    int hsize; unsigned hsrc_mask;
+    unsigned* herr;
 };
 
+// Wait until every source rank has published exchange #seq; returns the ghost pointer biased by -n_loc, so
+// that xg[c] is the value of local column c >= n_loc.  All threads call it; the caller synchronises after.
+__device__ __forceinline__ const double* kb_halo_wait(const KbSpmvArgs& a) {
+    const unsigned long long seq = *reinterpret_cast<const volatile unsigned long long*>(a.hseq);
+    const size_t par = (size_t)(seq & 1ull);
+    const int tid = threadIdx.x;
+    if (tid < a.hsize && ((a.hsrc_mask >> tid) & 1u)) {
+        const volatile unsigned long long* f = a.hflags + par * a.hsize + tid;
+        unsigned spins = 0;
+        while (*f < seq) { if (++spins > (1u << 25)) { atomicExch(a.herr, 1u); break; } }
+        __threadfence_system();
+    }
+    return a.xg_base + par * a.xg_stride - a.n_loc;
+}
+template <bool GH>
+__device__ __forceinline__ double kb_xload(const KbSpmvArgs& a, const double* xg, int c) {
+    if (GH) { if (c >= a.n_loc) return __ldcg(xg + c); }
+    return __ldg(a.x + c);
+}
+
 // Epi: struct with static constexpr bool WDOT, YDOT (slot order: <w,y> then <y,y>); __device__ bool skip() const; template <int BAR> __device__ void finish_block(double* ssum) const  (all threads of the last CTA)
-template <class Epi, bool RESID>
+template <class Epi, bool RESID, bool GH = false>
 __global__ void __launch_bounds__(KB_THREADS) kb_spmv_stream(KbSpmvArgs a, Epi epi) {
     if (epi.skip()) return;
+    const double* xg = nullptr;
+    if (GH) xg = kb_halo_wait(a);
     constexpr bool WD = Epi::WDOT, YD = Epi::YDOT;      // fused <w,y> and/or <y,y>
     constexpr int NDOT = (WD ? 1 : 0) + (YD ? 1 : 0);
     constexpr int ND = NDOT > 0 ? NDOT : 1;
@@ -84,7 +115,7 @@ __global__ void __launch_bounds__(KB_THREADS) kb_spmv_stream(KbSpmvArgs a, Epi e
             double s = 0.0;
             for (int cb = base; cb < end; cb += KB_SPMV_CAP) {
                 const int ce = min(end, cb + KB_SPMV_CAP);
-                for (int k = cb + tid; k < ce; k += KB_THREADS) s_prod[k - cb] = __ldcs(a.vals + k) * __ldg(a.x + __ldcs(a.col + k));
+                for (int k = cb + tid; k < ce; k += KB_THREADS) s_prod[k - cb] = __ldcs(a.vals + k) * kb_xload<GH>(a, xg, __ldcs(a.col + k));
                 __syncthreads();
                 if (tid == 0) for (int q = 0; q < ce - cb; ++q) s = s + s_prod[q];
                 __syncthreads();
@@ -104,8 +135,8 @@ __global__ void __launch_bounds__(KB_THREADS) kb_spmv_stream(KbSpmvArgs a, Epi e
         for (int k = k0 + 2 * tid; k < end; k += 2 * KB_THREADS) {
             const double2 v = __ldcs(reinterpret_cast<const double2*>(a.vals + k));
             const int2 c = __ldcs(reinterpret_cast<const int2*>(a.col + k));
-            const double p0 = v.x * __ldg(a.x + c.x);
-            const double p1 = v.y * __ldg(a.x + c.y);
+            const double p0 = v.x * kb_xload<GH>(a, xg, c.x);
+            const double p1 = v.y * kb_xload<GH>(a, xg, c.y);
             if (k >= base) s_prod[k - base] = p0;
             if (k + 1 < end) s_prod[k + 1 - base] = p1;
         }
@@ -150,9 +181,11 @@ __global__ void __launch_bounds__(KB_THREADS) kb_spmv_stream(KbSpmvArgs a, Epi e
 // order differs from the oracle's sequential row sum, so parity for this variant is <= 1e-12
 // relative instead of bit-exact.  The dot epilogue is shared with the stream kernel.
 // ---------------------------------------------------------------------------------------------
-template <class Epi, bool RESID, int VEC>
+template <class Epi, bool RESID, int VEC, bool GH = false>
 __global__ void __launch_bounds__(KB_THREADS) kb_spmv_vector(KbSpmvArgs a, Epi epi) {
     if (epi.skip()) return;
+    const double* xg = nullptr;
+    if (GH) { xg = kb_halo_wait(a); __syncthreads(); }
     constexpr bool WD = Epi::WDOT, YD = Epi::YDOT;      // fused <w,y> and/or <y,y>
     constexpr int NDOT = (WD ? 1 : 0) + (YD ? 1 : 0);
     constexpr int ND = NDOT > 0 ? NDOT : 1;
@@ -177,7 +210,7 @@ __global__ void __launch_bounds__(KB_THREADS) kb_spmv_vector(KbSpmvArgs a, Epi e
         const int r = r0 + t;
         const int pb = a.row_ptr[r], pe = a.row_ptr[r + 1];
         double s = 0.0;
-        for (int k = pb + sl; k < pe; k += VEC) s = s + __ldcs(a.vals + k) * __ldg(a.x + __ldcs(a.col + k));
+        for (int k = pb + sl; k < pe; k += VEC) s = s + __ldcs(a.vals + k) * kb_xload<GH>(a, xg, __ldcs(a.col + k));
 #pragma unroll
         for (int off = VEC / 2; off >= 1; off >>= 1) s = s + __shfl_xor_sync(0xffffffffu, s, off, VEC);
         if (sl == 0) {

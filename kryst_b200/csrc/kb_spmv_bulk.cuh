@@ -107,9 +107,11 @@ struct KbChunkTable {
     const int* __restrict__ chunk_nz;     // [nchunks+1] row_ptr[chunk_row[k]]
 };
 
-template <class Epi, bool RESID>
+template <class Epi, bool RESID, bool GH = false>
 __global__ void __launch_bounds__(KB_BULK_THREADS, 2) kb_spmv_bulk(KbSpmvArgs a, KbChunkTable tb, Epi epi) {
     if (epi.skip()) return;
+    const double* xg = nullptr;
+    if (GH) xg = kb_halo_wait(a);          // ordered before the gathers by the __syncthreads() below
     constexpr bool WD = Epi::WDOT, YD = Epi::YDOT;      // fused <w,y> and/or <y,y>
     constexpr int NDOT = (WD ? 1 : 0) + (YD ? 1 : 0);
     constexpr int ND = NDOT > 0 ? NDOT : 1;
@@ -184,8 +186,8 @@ __global__ void __launch_bounds__(KB_BULK_THREADS, 2) kb_spmv_bulk(KbSpmvArgs a,
 #pragma unroll
                 for (int u = 0; u < 8; ++u) {
                     pa[u] = 0.0; pb[u] = 0.0;
-                    if (qa0 + u < qa1) pa[u] = __ldg(a.x + st.cols[qa0 + u]);
-                    if (qb0 + u < qb1) pb[u] = __ldg(a.x + st.cols[qb0 + u]);
+                    if (qa0 + u < qa1) pa[u] = kb_xload<GH>(a, xg, st.cols[qa0 + u]);
+                    if (qb0 + u < qb1) pb[u] = kb_xload<GH>(a, xg, st.cols[qb0 + u]);
                 }
 #pragma unroll
                 for (int u = 0; u < 8; ++u) {
