@@ -11,6 +11,7 @@
 // branches are mathematically inconsistent, F7): Left = Arnoldi on M^-1 A started from M^-1 r0 with the
 // inner test on ||M^-1 r||; Right = Arnoldi on A M^-1, x += M^-1 (V y).
 #include <cstring>
+#include <cstdlib>
 #include <algorithm>
 #include "kb_objects.h"
 #include "kb_epilogue.cuh"
@@ -45,6 +46,53 @@ __global__ void __launch_bounds__(KB_THREADS) kb_gs_dot(KbGmresDev g, const doub
         double v = kb_warp_butterfly(e0 + e1);
         if (lane == 0) sm[c * 8 + wp] = v;
     }
+    __syncthreads();
+    for (int c = tid; c < ncols; c += KB_THREADS) {
+        double s = sm[c * 8];
+#pragma unroll
+        for (int k = 1; k < 8; ++k) s = s + sm[c * 8 + k];
+        partials[(size_t)c * pstride + blockIdx.x] = s;
+    }
+}
+// Fused CGS sweep: w -= V h1 and, in the same pass over the basis tile (kept in registers), the partial sums
+// of h2 = V^T w_new.  Saves one full read of V per Arnoldi step (3 sweeps instead of 4); the arithmetic and
+// the reduction tree are exactly those of kb_gs_dot / GsUpdateOp, so results are unchanged bit for bit.
+template <int MAXC>
+__global__ void __launch_bounds__(KB_THREADS, 1) kb_gs_update_dot(KbGmresDev g, double* __restrict__ w, const double* __restrict__ hsrc, long long n,
+                                                                  double* partials, size_t pstride, int ncols) {
+    KbCtl* ctl = g.ctl;
+    if (ctl->done || ctl->cycle_break) return;
+    __shared__ double sm[MAXC * 8];
+    const int tid = threadIdx.x, lane = tid & 31, wp = tid >> 5;
+    const long long i = (long long)blockIdx.x * KB_TILE + 2 * tid;
+    const bool h0 = i < n, h1 = i + 1 < n;
+    double t0 = 0.0, t1 = 0.0;
+    if (h1) { double2 t = kb_ld2(w + i); t0 = t.x; t1 = t.y; }
+    else if (h0) t0 = w[i];
+    double2 v[MAXC];
+#pragma unroll
+    for (int c = 0; c < MAXC; ++c) {
+        v[c] = make_double2(0.0, 0.0);
+        if (c < ncols) {
+            const double* vc = g.V + (size_t)c * g.ld;
+            if (h1) v[c] = kb_ld2(vc + i);
+            else if (h0) v[c].x = vc[i];
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < MAXC; ++c)
+        if (c < ncols) { const double h = hsrc[c]; t0 = t0 - v[c].x * h; t1 = t1 - v[c].y * h; }
+    if (h1) kb_st2(w + i, make_double2(t0, t1));
+    else if (h0) w[i] = t0;
+#pragma unroll
+    for (int c = 0; c < MAXC; ++c)
+        if (c < ncols) {
+            double e0 = 0.0, e1 = 0.0;
+            if (h1) { e0 = v[c].x * t0; e1 = v[c].y * t1; }
+            else if (h0) e0 = v[c].x * t0;
+            double r = kb_warp_butterfly(e0 + e1);
+            if (lane == 0) sm[c * 8 + wp] = r;
+        }
     __syncthreads();
     for (int c = tid; c < ncols; c += KB_THREADS) {
         double s = sm[c * 8];
@@ -334,6 +382,10 @@ static int gm_inner_iteration(GmPlan& P, int j) {
     KbCtl* ctl = w->ctl;
     double* vj = w->V + (size_t)j * w->ld;
     const int ncols = j + 1;
+    // 3-sweep variant (update fused with the next dot) is opt-in: with the basis tile in registers it runs at
+    // 1 CTA/SM and measured slower on B200 than the two separate bandwidth-bound sweeps (C4g: 191 vs 207 it/s)
+    static const bool fuse_env = getenv("KB_GS_FUSE") && atoi(getenv("KB_GS_FUSE")) != 0;
+    const bool fuse = fuse_env && ncols <= 32;      // the basis tile must fit in registers
     typedef KbSpmvEpi<GmNoFin, false, false> Epi;
     Epi epi; epi.ctl = ctl; epi.skip_mask = 2; epi.fin = kb_make_fin(c, GmNoFin{}, false, nullptr, 0);
     if (P.side == KB_SIDE_LEFT) {            // w = M^-1 (A v_j)
@@ -350,11 +402,17 @@ static int gm_inner_iteration(GmPlan& P, int j) {
         double* dst = P.dist ? w->slots : &ctl->h1[0];
         { KbLaunch L(c, KB_K_SMALL); kb_gs_level2<<<ncols, KB_THREADS, 0, c->stream>>>(ctl, w->partials, w->pstride, A->ntiles, dst); }
         if (P.dist) KB_TRY(kb_allreduce_slots(c, w->slots, ncols));
-        GsUpdateOp<false> op; op.partials = nullptr; op.pstride = 0; op.g = P.g; op.w = w->w; op.hsrc = P.g.h1src; op.slots = nullptr; op.ncols = ncols; op.p2p = nullptr;
-        KB_TRY(gm_tile(A, op, KB_K_GS_UPDATE));
+        if (fuse) {   // w -= V h1 fused with the partial sums of h2 = V^T w
+            KbLaunch L(c, KB_K_GS_UPDATE);
+            kb_gs_update_dot<32><<<A->ntiles, KB_THREADS, 0, c->stream>>>(P.g, w->w, P.g.h1src, (long long)A->n, w->partials, w->pstride, ncols);
+            KB_CUDA(cudaGetLastError());
+        } else {
+            GsUpdateOp<false> op; op.partials = nullptr; op.pstride = 0; op.g = P.g; op.w = w->w; op.hsrc = P.g.h1src; op.slots = nullptr; op.ncols = ncols; op.p2p = nullptr;
+            KB_TRY(gm_tile(A, op, KB_K_GS_UPDATE));
+        }
     }
     {   // h2 = V^T w ; w -= V h2 fused with ||w||^2 ; Arnoldi epilogue (H column, Givens, stop test)
-        { KbLaunch L(c, KB_K_GS_DOT); kb_gs_dot<<<A->ntiles, KB_THREADS, 0, c->stream>>>(P.g, w->w, (long long)A->n, w->partials, w->pstride, ncols); }
+        if (!fuse) { KbLaunch L(c, KB_K_GS_DOT); kb_gs_dot<<<A->ntiles, KB_THREADS, 0, c->stream>>>(P.g, w->w, (long long)A->n, w->partials, w->pstride, ncols); }
         double* s2 = w->slots + (KB_MAX_RESTART + 8);
         double* dst = P.dist ? s2 : &ctl->h2[0];
         { KbLaunch L(c, KB_K_SMALL); kb_gs_level2<<<ncols, KB_THREADS, 0, c->stream>>>(ctl, w->partials, w->pstride, A->ntiles, dst); }

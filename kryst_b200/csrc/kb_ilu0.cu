@@ -541,7 +541,7 @@ int kb_ilu0_build(kb_pc_s* pc) {
         KB_CUDA(cudaStreamSynchronize(c->stream));
         // window of in-flight chunks ~ a few levels wide, between 1 and 8 CTAs per SM
         if (getenv("KB_TRSV_GATE")) x->gate = atoi(getenv("KB_TRSV_GATE"));
-        int g = 8 * c->sm_count;
+        int g = 3 * c->sm_count;   // measured plateau on B200: 3-5 CTAs/SM; more only adds gate pollers
         // every CTA of the grid must be co-resident (a chunk may wait on a chunk of any other CTA)
         int occ = 1;
         if (u == 0) KB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kb_trsv_persistent<false>, KB_THREADS, 0));
