@@ -211,6 +211,9 @@ static int build_chunk_table(kb_csr_s* A) {
     KB_CUDA(cudaStreamSynchronize(c->stream));
     cudaFree(d_flag);
     A->kind = 2;
+    // rows longer than ~12 leave most consumer threads without a row: gather per nonzero instead (histogram-driven)
+    A->prod = A->n > 0 && (double)A->nnz / (double)A->n > 12.0;
+    if (getenv("KB_SPMV_PROD")) A->prod = atoi(getenv("KB_SPMV_PROD")) != 0;
     return KB_OK;
 }
 

@@ -85,7 +85,7 @@ static int kb_launch_spmv_tiles(kb_csr_s* A, KbSpmvArgs a, Epi epi, const int* l
     kb_ctx_s* c = A->ctx;
     a.tile_list = list; a.tile0 = 0; a.ntiles_launch = count; a.finalize = finalize;
     if (A->kind == 2) {
-        auto kfn = kb_spmv_bulk<Epi, RESID, GH>;
+        auto kfn = A->prod ? kb_spmv_bulk<Epi, RESID, GH, true> : kb_spmv_bulk<Epi, RESID, GH, false>;
         if (!c->configured.count((const void*)kfn)) {
             KB_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(KbBulkSmem)));
             c->configured.insert((const void*)kfn);

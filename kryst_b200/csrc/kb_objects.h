@@ -23,6 +23,7 @@ struct kb_csr_s {
     int* chunk_row = nullptr;
     int* chunk_nz = nullptr;
     int nchunks = 0;
+    bool prod = false;           // kind 2: per-nonzero product phase (long rows) instead of per-row gathers
     int vec = 8;                 // sub-warp width of the vector kernel
     uint64_t max_row_len = 0;
     uint64_t hist[6] = {0, 0, 0, 0, 0, 0};   // row-length histogram: <=8,<=16,<=32,<=64,<=128,>128

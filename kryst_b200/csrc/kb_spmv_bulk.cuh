@@ -107,7 +107,11 @@ struct KbChunkTable {
     const int* __restrict__ chunk_nz;     // [nchunks+1] row_ptr[chunk_row[k]]
 };
 
-template <class Epi, bool RESID, bool GH = false>
+// PROD (long rows, e.g. 27-point): a chunk holds fewer rows than consumer threads, so the gathers are not done
+// per row but per nonzero — all 256 consumers turn the staged values into products in place (16 independent
+// gathers per thread), then a thread per row adds its products in stored order.  Same operation sequence
+// (product rounded, then ascending adds) => same bits as the row-wise path and the oracle.
+template <class Epi, bool RESID, bool GH = false, bool PROD = false>
 __global__ void __launch_bounds__(KB_BULK_THREADS, 2) kb_spmv_bulk(KbSpmvArgs a, KbChunkTable tb, Epi epi) {
     if (epi.skip()) return;
     const double* xg = nullptr;
@@ -147,7 +151,7 @@ __global__ void __launch_bounds__(KB_BULK_THREADS, 2) kb_spmv_bulk(KbSpmvArgs a,
                     const unsigned bytes = (unsigned)(b1 - b0) * 12u + (unsigned)nrp * 4u;
                     kb_mbar_wait(&S.empty[s], ph ^ 1u);
                     KbBulkStage& st = S.st[s];
-                    st.hdr[0] = ra; st.hdr[1] = rb; st.hdr[2] = b0; st.hdr[3] = r_al; st.hdr[4] = tile; st.hdr[5] = (c + 1 == c1);
+                    st.hdr[0] = ra; st.hdr[1] = rb; st.hdr[2] = b0; st.hdr[3] = r_al; st.hdr[4] = tile; st.hdr[5] = (c + 1 == c1); st.hdr[6] = b1 - b0;
                     kb_mbar_expect_tx(&S.full[s], bytes);
                     if (b1 > b0) {
                         kb_bulk_g2s(st.vals, a.vals + b0, (unsigned)(b1 - b0) * 8u, &S.full[s], pol);
@@ -169,7 +173,7 @@ __global__ void __launch_bounds__(KB_BULK_THREADS, 2) kb_spmv_bulk(KbSpmvArgs a,
             const unsigned ph = (unsigned)(it / KB_BULK_STAGES) & 1u;
             ++it;
             kb_mbar_wait(&S.full[s], ph);
-            const KbBulkStage& st = S.st[s];
+            KbBulkStage& st = S.st[s];
             const int ra = st.hdr[0], rb = st.hdr[1], b0 = st.hdr[2], r_al = st.hdr[3];
             tile = st.hdr[4]; last = st.hdr[5];
             const int r0 = tile * KB_TILE;
@@ -180,6 +184,21 @@ __global__ void __launch_bounds__(KB_BULK_THREADS, 2) kb_spmv_bulk(KbSpmvArgs a,
             if (hA) { qa0 = st.rp[rA - r_al] - b0; qa1 = st.rp[rA + 1 - r_al] - b0; }
             if (hB) { qb0 = st.rp[rB - r_al] - b0; qb1 = st.rp[rB + 1 - r_al] - b0; }
             double sA = 0.0, sB = 0.0;
+            if (PROD) {
+                const int nwin = st.hdr[6];
+                for (int q0 = tid; q0 < nwin; q0 += 8 * KB_THREADS) {
+                    double xv[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) { const int q = q0 + u * KB_THREADS; xv[u] = q < nwin ? kb_xload<GH>(a, xg, st.cols[q]) : 0.0; }
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) { const int q = q0 + u * KB_THREADS; if (q < nwin) st.vals[q] = st.vals[q] * xv[u]; }
+                }
+                kb_bar_consumers();
+                for (int q = qa0; q < qa1; ++q) sA = sA + st.vals[q];
+                for (int q = qb0; q < qb1; ++q) sB = sB + st.vals[q];
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes before the next bulk refill
+                qa0 = qa1; qb0 = qb1;
+            }
             // groups of 8 entries per row: gather everything first, then add in stored order
             while (qa0 < qa1 || qb0 < qb1) {
                 double pa[8], pb[8];
