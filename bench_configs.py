@@ -39,18 +39,25 @@ def main():
     import numpy as np
     import torch
     import kryst_b200 as kb
-    from kryst_b200 import stencils
+    from kryst_b200 import stencils, parallel
     from bench import peaks
     peak, src = peaks()
-    ctx = kb.Context(0)
-    stream = torch.cuda.ExternalStream(ctx.stream)
+    rank, world, local = parallel.dist_env()
+    torch.cuda.set_device(local)
+    ctx = kb.Context(local)
+    if world > 1:          # under torchrun: row-block shards, block-Jacobi ILU(0) per GPU
+        import torch.distributed as dist
+        dist.init_process_group("gloo")
+        parallel.init_comm(ctx)
+    stream = torch.cuda.ExternalStream(ctx.stream, device=torch.device("cuda", local))
     for name in args.configs:
         cfg = dict(stencils.CONFIGS[name])
         N = args.scale or cfg["N"]
         t0 = time.perf_counter()
-        n, rp, ci, v = stencils.stencil(cfg["kind"], N)
+        n_glob, lo, hi, rp, ci, v = parallel.shard_stencil(cfg["kind"], N, world, rank)
+        n = hi - lo
         nnz = int(rp[-1])
-        A = kb.DeviceCsr.from_csr(n, n, rp, ci, v, ctx)
+        A = kb.DeviceCsr.from_csr_shard(n_glob, lo, hi, rp, ci, v, ctx) if world > 1 else kb.DeviceCsr.from_csr(n, n, rp, ci, v, ctx)
         del rp, ci, v
         t_up = time.perf_counter() - t0
         t0 = time.perf_counter()
@@ -90,7 +97,14 @@ def main():
         prof = ctx.profile()
         bi = bytes_per_iter(cfg, n, nnz)
         its = st.iterations
-        line = {"config": name, "kind": cfg["kind"], "N": N, "n": n, "nnz": nnz, "solver": cfg["solver"], "pc": cfg["pc"],
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        if rank != 0:
+            del A, pc, b, x, ones
+            torch.cuda.empty_cache()
+            continue
+        line = {"config": name, "gpus": world, "kind": cfg["kind"], "N": N, "n": n, "nnz": nnz, "solver": cfg["solver"], "pc": cfg["pc"],
                 "iterations": its, "converged": st.converged, "final_residual": st.final_residual, "max_abs_err_vs_ones": err,
                 "solve_ms": best, "it_per_s": its / (best * 1e-3), "bytes_per_iter_model": bi,
                 "achieved_gbs": bi * its / (best * 1e-3) / 1e9, "frac_of_peak": bi * its / (best * 1e-3) / 1e9 / peak, "peak_gbs": peak,
