@@ -114,6 +114,43 @@ struct PcgUpdateOp : KbRedBase {      // K3
     __device__ void finish_block(double* s) const { fin.template coop<0>(s); }
 };
 
+// --- generic preconditioner (e.g. ILU(0)): the pc apply cannot be fused, so K3 splits into update / apply / dots
+struct PcgXrOp : KbRedBase {          // x += alpha p ; r -= alpha ap   (pcg.rs:175-181)
+    static constexpr int NRED = 0;
+    double* x; const double* p; double* r; const double* ap; KbCtl* ctl;
+    __device__ bool skip() const { return ctl->done != 0; }
+    __device__ void pair(long long i, bool has1, double*) const {
+        const double alpha = ctl->alpha;
+        if (has1) {
+            double2 xx = kb_ld2(x + i), pp = kb_ld2(p + i), rr = kb_ld2(r + i), aa = kb_ld2(ap + i);
+            kb_st2(x + i, make_double2(xx.x + alpha * pp.x, xx.y + alpha * pp.y));
+            kb_st2(r + i, make_double2(rr.x - alpha * aa.x, rr.y - alpha * aa.y));
+        } else { x[i] = x[i] + alpha * p[i]; r[i] = r[i] - alpha * ap[i]; }
+    }
+    __device__ void finish_block(double*) const {}
+};
+template <class Fin, bool COPY_P>
+struct PcgRzOp : KbRedBase {          // r.z and the norm (pcg.rs:188-195); COPY_P: p = z (pcg.rs:132)
+    static constexpr int NRED = 2;
+    const double* r; const double* z; double* p; KbCtl* ctl; KbFinish<Fin> fin;
+    __device__ bool skip() const { return COPY_P ? false : ctl->done != 0; }
+    __device__ void pair(long long i, bool has1, double* red) const {
+        const int nt = ctl->norm_type;
+        if (has1) {
+            double2 rr = kb_ld2(r + i), zz = kb_ld2(z + i);
+            if (COPY_P) kb_st2(p + i, zz);
+            red[0] = rr.x * zz.x + rr.y * zz.y;
+            red[1] = nt == KB_NORM_PRECONDITIONED ? (zz.x * zz.x + zz.y * zz.y) : nt == KB_NORM_UNPRECONDITIONED ? (rr.x * rr.x + rr.y * rr.y) : 0.0;
+        } else {
+            double rr = r[i], zz = z[i];
+            if (COPY_P) p[i] = zz;
+            red[0] = rr * zz + 0.0;
+            red[1] = nt == KB_NORM_PRECONDITIONED ? (zz * zz + 0.0) : nt == KB_NORM_UNPRECONDITIONED ? (rr * rr + 0.0) : 0.0;
+        }
+    }
+    __device__ void finish_block(double* s) const { fin.template coop<0>(s); }
+};
+
 struct PcgXpayOp : KbRedBase {        // K4: p = z + beta p  (pcg.rs:215-217)
     static constexpr int NRED = 0;
     const double* z; double* p; KbCtl* ctl;
@@ -178,7 +215,18 @@ static int pcg_launch_iteration(kb_csr_s* A, const kb_pc_s* pc, KbPcgWs* w) {
         KB_TRY((kb_launch_spmv<KbSpmvEpi<PcgApFin, true, false>, false>(A, w->p, w->ap, nullptr, w->p, w->partials, w->pstride, epi, DIST ? w->p : nullptr)));
         if (DIST) KB_TRY((kb_finish_dist<PcgApFin>(c, PcgApFin{w->ctl}, w->ctl, w->slots, 1)));
     }
-    {   // K3
+    if (pc && pc->kind != KB_PC_JACOBI) {   // K3 with a generic preconditioner
+        PcgXrOp u; u.n = (long long)w->n; u.partials = nullptr; u.pstride = 0; u.ticket = c->ticket;
+        u.x = w->x; u.p = w->p; u.r = w->r; u.ap = w->ap; u.ctl = w->ctl;
+        { KbLaunch L(c, KB_K_PCG_UPDATE); kb_tile_kernel<<<A->ntiles, KB_THREADS, 0, c->stream>>>(u); }
+        KB_CUDA(cudaGetLastError());
+        KB_TRY(kb_pc_apply_dev(const_cast<kb_pc_s*>(pc), w->r, w->z, w->ctl, 0));
+        PcgRzOp<PcgUpdateFin, false> op; op.n = (long long)w->n; op.partials = w->partials; op.pstride = w->pstride; op.ticket = c->ticket;
+        op.r = w->r; op.z = w->z; op.p = nullptr; op.ctl = w->ctl; op.fin = kb_make_fin(c, PcgUpdateFin{w->ctl}, DIST, w->slots, 2);
+        { KbLaunch L(c, KB_K_PCG_UPDATE); kb_tile_kernel<<<A->ntiles, KB_THREADS, 0, c->stream>>>(op); }
+        KB_CUDA(cudaGetLastError());
+        if (DIST) KB_TRY((kb_finish_dist<PcgUpdateFin>(c, PcgUpdateFin{w->ctl}, w->ctl, w->slots, 2)));
+    } else {   // K3
         PcgUpdateOp<PcgUpdateFin> op; op.n = (long long)w->n; op.partials = w->partials; op.pstride = w->pstride; op.ticket = c->ticket;
         op.x = w->x; op.p = w->p; op.r = w->r; op.ap = w->ap; op.inv = inv; op.z = w->z; op.ctl = w->ctl;
         op.fin = kb_make_fin(c, PcgUpdateFin{w->ctl}, DIST, w->slots, 2);
@@ -216,7 +264,6 @@ extern "C" int kb_pcg_solve(kb_csr A, kb_pc pc, const double* b, double* x, doub
     if (hist_len) *hist_len = 0;
     if (A->n == 0 && !dist) { stats->converged = 0; return KB_OK; }
     const bool jacobi_like = !pc || pc->kind == KB_PC_JACOBI;
-    if (!jacobi_like) { kb_set_error("kb_pcg_solve: only Jacobi (or no) preconditioning is fused on device"); return KB_UNSUPPORTED; }
 
     KB_TRY(kb_upload_or_alias(c, b, w->b, w->n, dev));
     KB_TRY(kb_upload_or_alias(c, x, w->x, w->n, dev));
@@ -237,7 +284,14 @@ extern "C" int kb_pcg_solve(kb_csr A, kb_pc pc, const double* b, double* x, doub
             KbSpmvEpi<PcgApFin, false, false> epi; epi.ctl = nullptr; epi.fin = kb_make_fin(c, PcgApFin{w->ctl}, false, nullptr, 0);
             if ((st = kb_launch_spmv<KbSpmvEpi<PcgApFin, false, false>, true>(A, w->x, w->r, w->b, nullptr, w->partials, w->pstride, epi, dist ? w->x : nullptr)) != KB_OK) break;
         }
-        {   // z, p, rz, res0, first history entry (pcg.rs:126-146)
+        if (!jacobi_like) {   // z = M^-1 r ; p = z ; rz ; norm
+            if ((st = kb_pc_apply_dev(pc, w->r, w->z, nullptr, 0)) != KB_OK) break;
+            PcgRzOp<PcgInitFin, true> op; op.n = (long long)w->n; op.partials = w->partials; op.pstride = w->pstride; op.ticket = c->ticket;
+            op.r = w->r; op.z = w->z; op.p = w->p; op.ctl = w->ctl; op.fin = kb_make_fin(c, PcgInitFin{w->ctl}, dist, w->slots, 2);
+            { KbLaunch L(c, KB_K_INIT); kb_tile_kernel<<<A->ntiles, KB_THREADS, 0, c->stream>>>(op); }
+            if (cudaGetLastError() != cudaSuccess) { kb_set_error("pcg init launch failed"); st = KB_SOLVE_ERROR; break; }
+            if (dist && (st = kb_finish_dist<PcgInitFin>(c, PcgInitFin{w->ctl}, w->ctl, w->slots, 2)) != KB_OK) break;
+        } else {   // z, p, rz, res0, first history entry (pcg.rs:126-146)
             PcgInitOp<PcgInitFin> op; op.n = (long long)w->n; op.partials = w->partials; op.pstride = w->pstride; op.ticket = c->ticket;
             op.r = w->r; op.inv = pc ? pc->inv_diag : nullptr; op.z = w->z; op.p = w->p; op.ctl = w->ctl;
             op.fin = kb_make_fin(c, PcgInitFin{w->ctl}, dist, w->slots, 2);
