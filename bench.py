@@ -126,6 +126,7 @@ def run_reference(args):
     for _ in range(args.steps):
         rc, x, st, _h = o.pcg(A, pc, b, np.zeros(A.n), TOL, S)
         its += int(st.iterations)
+    S = its // max(1, args.steps)
     dt = time.perf_counter() - t0
     val = its / dt
     line = {
