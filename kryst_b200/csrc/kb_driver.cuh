@@ -43,8 +43,17 @@ static int kb_run_iterations(kb_ctx_s* c, KbGraphCache* gc, uint64_t key, int B,
         if (e != cudaSuccess) { gc->exec = nullptr; kb_set_error("CUDA graph instantiate failed: %s", cudaGetErrorString(e)); return KB_SOLVE_ERROR; }
         gc->key = key; gc->iters = B; gc->launches = c->captured_launches;
     }
+    // Software-pipelined polling: replay k+1 is enqueued before the host looks at the `done` flag copied after
+    // replay k, so the device never idles on the host round trip (the speculative replay is a string of no-ops
+    // once `done` is set).
     uint64_t issued = 0;
-    while (true) {
+    cudaEvent_t ev[2] = {nullptr, nullptr};
+    for (int k = 0; k < 2; ++k) if (cudaEventCreateWithFlags(&ev[k], cudaEventDisableTiming) != cudaSuccess) { kb_set_error("event create failed"); return KB_SOLVE_ERROR; }
+    int* flags = reinterpret_cast<int*>(reinterpret_cast<char*>(h_ctl) + sizeof(KbCtl) - 2 * sizeof(int));   // tail of the pinned mirror: unused by copies
+    int st = KB_OK;
+    int slot = 0;
+    bool pending[2] = {false, false};
+    auto enqueue = [&](int sl) -> int {
         if (use_graph) {
             cudaError_t e = cudaGraphLaunch(gc->exec, c->stream);
             if (e != cudaSuccess) { kb_set_error("CUDA graph launch failed: %s", cudaGetErrorString(e)); return KB_SOLVE_ERROR; }
@@ -53,19 +62,28 @@ static int kb_run_iterations(kb_ctx_s* c, KbGraphCache* gc, uint64_t key, int B,
             for (int k = 0; k < B; ++k) KB_TRY(launch_iter());
         }
         issued += (uint64_t)B;
-        if (cudaMemcpyAsync(h_ctl, d_ctl, offsetof(KbCtl, rz), cudaMemcpyDeviceToHost, c->stream) != cudaSuccess ||
-            cudaStreamSynchronize(c->stream) != cudaSuccess) {
-            kb_set_error("device error during Krylov iterations: %s", cudaGetErrorString(cudaGetLastError()));
-            return KB_SOLVE_ERROR;
-        }
-        if (h_ctl->done || issued >= units_cap + (uint64_t)B) break;
+        if (cudaMemcpyAsync(&flags[sl], &d_ctl->done, sizeof(int), cudaMemcpyDeviceToHost, c->stream) != cudaSuccess ||
+            cudaEventRecord(ev[sl], c->stream) != cudaSuccess) { kb_set_error("poll enqueue failed"); return KB_SOLVE_ERROR; }
+        pending[sl] = true;
+        return KB_OK;
+    };
+    st = enqueue(slot);
+    while (st == KB_OK) {
+        const bool more = issued < units_cap + (uint64_t)B;
+        if (more) { st = enqueue(slot ^ 1); if (st != KB_OK) break; }
+        if (cudaEventSynchronize(ev[slot]) != cudaSuccess) { kb_set_error("device error during Krylov iterations: %s", cudaGetErrorString(cudaGetLastError())); st = KB_SOLVE_ERROR; break; }
+        pending[slot] = false;
+        if (flags[slot] || !more) break;
+        slot ^= 1;
     }
-    return KB_OK;
+    if (cudaStreamSynchronize(c->stream) != cudaSuccess && st == KB_OK) { kb_set_error("device error during Krylov iterations: %s", cudaGetErrorString(cudaGetLastError())); st = KB_SOLVE_ERROR; }
+    for (int k = 0; k < 2; ++k) cudaEventDestroy(ev[k]);
+    return st;
 }
 
-// iterations per replay so that one replay is ~2 ms of work (the host poll is then <1 %)
+// iterations per replay so that one replay is ~4 ms of work
 static inline int kb_batch_size(double bytes_per_iter, int kernels_per_iter) {
     double t = bytes_per_iter / 6.0e12 + 3.0e-6 * kernels_per_iter;
-    double b = 2.0e-3 / t;
+    double b = 4.0e-3 / t;
     return (int)(b < 4.0 ? 4.0 : (b > 64.0 ? 64.0 : b));
 }

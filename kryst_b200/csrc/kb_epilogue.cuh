@@ -91,7 +91,8 @@ static int kb_launch_spmv_tiles(kb_csr_s* A, KbSpmvArgs a, Epi epi, const int* l
             c->configured.insert((const void*)kfn);
         }
         KbChunkTable tb{A->tile_chunk, A->chunk_row, A->chunk_nz};
-        const int grid = std::min(2 * c->sm_count, count);
+        static const int per_sm = getenv("KB_BULK_CTAS_PER_SM") ? atoi(getenv("KB_BULK_CTAS_PER_SM")) : 2;
+        const int grid = std::min(per_sm * c->sm_count, count);
         KbLaunch L(c, KB_K_SPMV);
         kfn<<<grid, KB_BULK_THREADS, sizeof(KbBulkSmem), c->stream>>>(a, tb, epi);
         KB_CUDA(cudaGetLastError());

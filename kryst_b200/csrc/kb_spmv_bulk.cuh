@@ -194,7 +194,9 @@ __global__ void __launch_bounds__(KB_BULK_THREADS, 2) kb_spmv_bulk(KbSpmvArgs a,
                     for (int u = 0; u < 8; ++u) { const int q = q0 + u * KB_THREADS; if (q < nwin) st.vals[q] = st.vals[q] * xv[u]; }
                 }
                 kb_bar_consumers();
+#pragma unroll 4
                 for (int q = qa0; q < qa1; ++q) sA = sA + st.vals[q];
+#pragma unroll 4
                 for (int q = qb0; q < qb1; ++q) sB = sB + st.vals[q];
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes before the next bulk refill
                 qa0 = qa1; qb0 = qb1;
