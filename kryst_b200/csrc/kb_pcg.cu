@@ -11,11 +11,13 @@
 // exit immediately, so the reported iteration count is exactly the reference's.
 #include <cstring>
 #include <cstddef>
+#include <cstdlib>
 #include <algorithm>
 #include "kb_objects.h"
 #include "kb_spmv.cuh"
 #include "kb_epilogue.cuh"
 #include "kb_driver.cuh"
+#include "kb_pcg_mega.cuh"
 
 // ---- scalar epilogues (device, single thread) ------------------------------------------------
 struct PcgInitFin {   // pcg.rs:132-146
@@ -172,12 +174,13 @@ struct KbPcgWs {
     KbCtl* ctl = nullptr; KbCtl* h_ctl = nullptr;
     double* hist = nullptr; uint64_t hist_cap = 0;
     KbGraphCache gc;
+    unsigned* mega_bar = nullptr;     // grid-barrier words of the persistent kernel
 };
 void kb_pcg_ws_free(KbPcgWs* w) {
     if (!w) return;
     w->gc.reset();
     KB_FREE(w->x); KB_FREE(w->r); KB_FREE(w->z); KB_FREE(w->p); KB_FREE(w->ap); KB_FREE(w->b);
-    KB_FREE(w->partials); KB_FREE(w->slots); KB_FREE(w->ctl); KB_FREE(w->hist);
+    KB_FREE(w->partials); KB_FREE(w->slots); KB_FREE(w->ctl); KB_FREE(w->hist); KB_FREE(w->mega_bar);
     if (w->h_ctl) cudaFreeHost(w->h_ctl);
     delete w;
 }
@@ -243,6 +246,34 @@ static int pcg_launch_iteration(kb_csr_s* A, const kb_pc_s* pc, KbPcgWs* w) {
     return KB_OK;
 }
 
+// whole solve in one cooperative launch (single GPU, bulk SpMV, Jacobi or no preconditioner)
+static int pcg_persistent(kb_csr_s* A, const kb_pc_s* pc, KbPcgWs* w) {
+    kb_ctx_s* c = A->ctx;
+    auto kfn = kb_pcg_persistent<PcgApFin, PcgUpdateFin, PcgUpdateOp<PcgUpdateFin>, PcgXpayOp>;
+    if (!c->configured.count((const void*)kfn)) {
+        KB_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(KbBulkSmem)));
+        c->configured.insert((const void*)kfn);
+    }
+    int occ = 0;
+    KB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kfn, KB_BULK_THREADS, sizeof(KbBulkSmem)));
+    if (occ < 1) { kb_set_error("persistent PCG kernel does not fit on this device"); return KB_UNSUPPORTED; }
+    const int grid = std::min(std::min(occ, 2) * c->sm_count, A->ntiles);
+    if (!w->mega_bar) { KB_TRY(kb_alloc(&w->mega_bar, 4)); }
+    KB_CUDA(cudaMemsetAsync(w->mega_bar, 0, 4 * sizeof(unsigned), c->stream));
+    KbSpmvArgs a{};
+    a.row_ptr = A->row_ptr; a.col = A->col; a.vals = A->vals; a.x = w->p; a.y = w->ap; a.b = nullptr; a.w = w->p;
+    a.n = (int)A->n; a.tile0 = 0; a.ntiles_launch = A->ntiles; a.ntiles_total = A->ntiles; a.tile_list = nullptr; a.finalize = 0;
+    a.partials = w->partials; a.pstride = w->pstride; a.ticket = c->ticket;
+    KbChunkTable tb{A->tile_chunk, A->chunk_row, A->chunk_nz};
+    KbPcgMegaArgs m{};
+    m.ctl = w->ctl; m.x = w->x; m.r = w->r; m.z = w->z; m.p = w->p; m.ap = w->ap; m.inv = pc ? pc->inv_diag : nullptr;
+    m.partials = w->partials; m.pstride = w->pstride; m.n = (int)A->n; m.ntiles = A->ntiles; m.bar = w->mega_bar;
+    void* args[] = {&a, &tb, &m};
+    KbLaunch L(c, KB_K_SPMV);
+    KB_CUDA(cudaLaunchCooperativeKernel((const void*)kfn, dim3(grid), dim3(KB_BULK_THREADS), args, sizeof(KbBulkSmem), c->stream));
+    return KB_OK;
+}
+
 static int pcg_iteration(kb_csr_s* A, const kb_pc_s* pc, KbPcgWs* w) {
     return A->dist && A->ctx->size > 1 ? pcg_launch_iteration<true>(A, pc, w) : pcg_launch_iteration<false>(A, pc, w);
 }
@@ -299,10 +330,24 @@ extern "C" int kb_pcg_solve(kb_csr A, kb_pc pc, const double* b, double* x, doub
             if (cudaGetLastError() != cudaSuccess) { kb_set_error("pcg init launch failed"); st = KB_SOLVE_ERROR; break; }
             if (dist && (st = kb_finish_dist<PcgInitFin>(c, PcgInitFin{w->ctl}, w->ctl, w->slots, 2)) != KB_OK) break;
         }
+        // Optional: the whole loop in one persistent cooperative kernel (KB_PCG_PERSISTENT=1).  Measured on B200 the
+        // software grid barriers (3 per iteration over 296 CTAs, ~3 us each) cost more than the three kernel
+        // boundaries of the graph path (C1: 22.3 vs 18.5 us per iteration), so it is opt-in.
+        const int mega_env = getenv("KB_PCG_PERSISTENT") ? atoi(getenv("KB_PCG_PERSISTENT")) : 0;
+        const bool mega_ok = !dist && jacobi_like && A->kind == 2 && !A->prod && !profile && max_iters > 0;
+        const bool mega = mega_ok && mega_env != 0;
+        if (mega) {
+            if ((st = pcg_persistent(A, pc, w)) != KB_OK) break;
+            unsigned berr = 0;
+            if (cudaMemcpyAsync(&berr, w->mega_bar + 2, sizeof(unsigned), cudaMemcpyDeviceToHost, c->stream) != cudaSuccess ||
+                cudaStreamSynchronize(c->stream) != cudaSuccess) { kb_set_error("pcg: persistent kernel failed: %s", cudaGetErrorString(cudaGetLastError())); st = KB_SOLVE_ERROR; break; }
+            if (berr) { kb_set_error("pcg: grid barrier timed out"); st = KB_SOLVE_ERROR; break; }
+        } else {
         // iterations per graph replay: ~2 ms of work, so the per-replay host poll is amortised
         const int B = kb_batch_size(12.0 * (double)A->nnz + 108.0 * (double)A->n, 3);
         st = kb_run_iterations(c, &w->gc, (uint64_t)(uintptr_t)pc + 1, B, max_iters, use_graph, w->ctl, h,
                                [&]() { return pcg_iteration(A, pc, w); });
+        }
         if (st != KB_OK) break;
         if (cudaMemcpyAsync(h, w->ctl, offsetof(KbCtl, h), cudaMemcpyDeviceToHost, c->stream) != cudaSuccess ||
             cudaStreamSynchronize(c->stream) != cudaSuccess) { kb_set_error("pcg: readback failed"); st = KB_SOLVE_ERROR; break; }

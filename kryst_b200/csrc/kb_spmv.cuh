@@ -61,10 +61,12 @@ __device__ __forceinline__ const double* kb_halo_wait(const KbSpmvArgs& a) {
     }
     return a.xg_base + par * a.xg_stride - a.n_loc;
 }
-template <bool GH>
+// NC: the operand is read-only for the kernel's lifetime -> non-coherent (texture path) loads.  The persistent
+// PCG kernel rewrites p between phases, so there the gather must be an ordinary coherent load.
+template <bool GH, bool NC = true>
 __device__ __forceinline__ double kb_xload(const KbSpmvArgs& a, const double* xg, int c) {
     if (GH) { if (c >= a.n_loc) return __ldcg(xg + c); }
-    return __ldg(a.x + c);
+    return NC ? __ldg(a.x + c) : __ldca(a.x + c);
 }
 
 // Epi: struct with static constexpr bool WDOT, YDOT (slot order: <w,y> then <y,y>); __device__ bool skip() const; template <int BAR> __device__ void finish_block(double* ssum) const  (all threads of the last CTA)

@@ -107,65 +107,46 @@ struct KbChunkTable {
     const int* __restrict__ chunk_nz;     // [nchunks+1] row_ptr[chunk_row[k]]
 };
 
+// ---- producer / consumer halves of the bulk SpMV (shared by kb_spmv_bulk and the persistent PCG kernel) ------
+// `it` counts stages used so far by this CTA; it persists across calls so the mbarrier phases keep alternating.
+__device__ __forceinline__ void kb_bulk_produce(const KbSpmvArgs& a, const KbChunkTable& tb, KbBulkSmem& S, int& it, unsigned long long pol) {
+    const int ntl = a.ntiles_launch;
+    for (int ti = blockIdx.x; ti < ntl; ti += gridDim.x) {
+        const int tile = a.tile_list ? a.tile_list[ti] : (a.tile0 + ti);
+        const int c0 = tb.tile_chunk[tile], c1 = tb.tile_chunk[tile + 1];
+        for (int c = c0; c < c1; ++c, ++it) {
+            const int s = it % KB_BULK_STAGES;
+            const unsigned ph = (unsigned)(it / KB_BULK_STAGES) & 1u;
+            const int ra = tb.chunk_row[c], rb = tb.chunk_row[c + 1];
+            const int nz0 = tb.chunk_nz[c], nz1 = tb.chunk_nz[c + 1];
+            const int b0 = nz0 & ~3, b1 = (nz1 + 3) & ~3;        // 16-B aligned window for both arrays
+            const int r_al = ra & ~3;                            // row_ptr slice [r_al, rb] padded to 16 B
+            const int nrp = ((rb + 1 - r_al) + 3) & ~3;
+            const unsigned bytes = (unsigned)(b1 - b0) * 12u + (unsigned)nrp * 4u;
+            kb_mbar_wait(&S.empty[s], ph ^ 1u);
+            KbBulkStage& st = S.st[s];
+            st.hdr[0] = ra; st.hdr[1] = rb; st.hdr[2] = b0; st.hdr[3] = r_al; st.hdr[4] = tile; st.hdr[5] = (c + 1 == c1); st.hdr[6] = b1 - b0;
+            kb_mbar_expect_tx(&S.full[s], bytes);
+            if (b1 > b0) {
+                kb_bulk_g2s(st.vals, a.vals + b0, (unsigned)(b1 - b0) * 8u, &S.full[s], pol);
+                kb_bulk_g2s(st.cols, a.col + b0, (unsigned)(b1 - b0) * 4u, &S.full[s], pol);
+            }
+            kb_bulk_g2s(st.rp, a.row_ptr + r_al, (unsigned)nrp * 4u, &S.full[s], pol);
+        }
+    }
+}
+
 // PROD (long rows, e.g. 27-point): a chunk holds fewer rows than consumer threads, so the gathers are not done
-// per row but per nonzero — all 256 consumers turn the staged values into products in place (16 independent
-// gathers per thread), then a thread per row adds its products in stored order.  Same operation sequence
-// (product rounded, then ascending adds) => same bits as the row-wise path and the oracle.
-template <class Epi, bool RESID, bool GH = false, bool PROD = false>
-__global__ void __launch_bounds__(KB_BULK_THREADS, 2) kb_spmv_bulk(KbSpmvArgs a, KbChunkTable tb, Epi epi) {
-    if (epi.skip()) return;
-    const double* xg = nullptr;
-    if (GH) xg = kb_halo_wait(a);          // ordered before the gathers by the __syncthreads() below
-    constexpr bool WD = Epi::WDOT, YD = Epi::YDOT;      // fused <w,y> and/or <y,y>
+// per row but per nonzero — all 256 consumers turn the staged values into products in place, then a thread per
+// row adds its products in stored order.  Same operation sequence (product rounded, then ascending adds) =>
+// same bits as the row-wise path and the oracle.
+template <bool WD, bool YD, bool RESID, bool GH, bool PROD, bool NC = true>
+__device__ __forceinline__ void kb_bulk_consume(const KbSpmvArgs& a, KbBulkSmem& S, int& it, const double* xg) {
     constexpr int NDOT = (WD ? 1 : 0) + (YD ? 1 : 0);
     constexpr int ND = NDOT > 0 ? NDOT : 1;
     constexpr int YS = WD ? 1 : 0;                      // slot of <y,y>
-    extern __shared__ __align__(128) unsigned char kb_smem_raw[];
-    KbBulkSmem& S = *reinterpret_cast<KbBulkSmem*>(kb_smem_raw);
     const int tid = threadIdx.x;
-    const int ntl = a.ntiles_launch;   // tiles handled by this launch
-
-    if (tid == 0) {
-#pragma unroll
-        for (int s = 0; s < KB_BULK_STAGES; ++s) { kb_mbar_init(&S.full[s], 1); kb_mbar_init(&S.empty[s], KB_THREADS); }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-
-    if (tid >= KB_THREADS) {
-        // ------------------------------ producer warp ------------------------------
-        if (tid == KB_THREADS) {
-            const unsigned long long pol = kb_policy_evict_first();
-            int it = 0;
-            for (int ti = blockIdx.x; ti < ntl; ti += gridDim.x) {
-                const int tile = a.tile_list ? a.tile_list[ti] : (a.tile0 + ti);
-                const int c0 = tb.tile_chunk[tile], c1 = tb.tile_chunk[tile + 1];
-                for (int c = c0; c < c1; ++c, ++it) {
-                    const int s = it % KB_BULK_STAGES;
-                    const unsigned ph = (unsigned)(it / KB_BULK_STAGES) & 1u;
-                    const int ra = tb.chunk_row[c], rb = tb.chunk_row[c + 1];
-                    const int nz0 = tb.chunk_nz[c], nz1 = tb.chunk_nz[c + 1];
-                    const int b0 = nz0 & ~3, b1 = (nz1 + 3) & ~3;        // 16-B aligned window for both arrays
-                    const int r_al = ra & ~3;                            // row_ptr slice [r_al, rb] padded to 16 B
-                    const int nrp = ((rb + 1 - r_al) + 3) & ~3;
-                    const unsigned bytes = (unsigned)(b1 - b0) * 12u + (unsigned)nrp * 4u;
-                    kb_mbar_wait(&S.empty[s], ph ^ 1u);
-                    KbBulkStage& st = S.st[s];
-                    st.hdr[0] = ra; st.hdr[1] = rb; st.hdr[2] = b0; st.hdr[3] = r_al; st.hdr[4] = tile; st.hdr[5] = (c + 1 == c1); st.hdr[6] = b1 - b0;
-                    kb_mbar_expect_tx(&S.full[s], bytes);
-                    if (b1 > b0) {
-                        kb_bulk_g2s(st.vals, a.vals + b0, (unsigned)(b1 - b0) * 8u, &S.full[s], pol);
-                        kb_bulk_g2s(st.cols, a.col + b0, (unsigned)(b1 - b0) * 4u, &S.full[s], pol);
-                    }
-                    kb_bulk_g2s(st.rp, a.row_ptr + r_al, (unsigned)nrp * 4u, &S.full[s], pol);
-                }
-            }
-        }
-        return;
-    }
-
-    // ------------------------------ consumers (256 threads) ------------------------------
-    int it = 0;
+    const int ntl = a.ntiles_launch;
     for (int ti = blockIdx.x; ti < ntl; ti += gridDim.x) {
         int tile = 0, last = 0;
         do {
@@ -189,7 +170,7 @@ __global__ void __launch_bounds__(KB_BULK_THREADS, 2) kb_spmv_bulk(KbSpmvArgs a,
                 for (int q0 = tid; q0 < nwin; q0 += 8 * KB_THREADS) {
                     double xv[8];
 #pragma unroll
-                    for (int u = 0; u < 8; ++u) { const int q = q0 + u * KB_THREADS; xv[u] = q < nwin ? kb_xload<GH>(a, xg, st.cols[q]) : 0.0; }
+                    for (int u = 0; u < 8; ++u) { const int q = q0 + u * KB_THREADS; xv[u] = q < nwin ? kb_xload<GH, NC>(a, xg, st.cols[q]) : 0.0; }
 #pragma unroll
                     for (int u = 0; u < 8; ++u) { const int q = q0 + u * KB_THREADS; if (q < nwin) st.vals[q] = st.vals[q] * xv[u]; }
                 }
@@ -207,8 +188,8 @@ __global__ void __launch_bounds__(KB_BULK_THREADS, 2) kb_spmv_bulk(KbSpmvArgs a,
 #pragma unroll
                 for (int u = 0; u < 8; ++u) {
                     pa[u] = 0.0; pb[u] = 0.0;
-                    if (qa0 + u < qa1) pa[u] = kb_xload<GH>(a, xg, st.cols[qa0 + u]);
-                    if (qb0 + u < qb1) pb[u] = kb_xload<GH>(a, xg, st.cols[qb0 + u]);
+                    if (qa0 + u < qa1) pa[u] = kb_xload<GH, NC>(a, xg, st.cols[qa0 + u]);
+                    if (qb0 + u < qb1) pb[u] = kb_xload<GH, NC>(a, xg, st.cols[qb0 + u]);
                 }
 #pragma unroll
                 for (int u = 0; u < 8; ++u) {
@@ -250,6 +231,35 @@ __global__ void __launch_bounds__(KB_BULK_THREADS, 2) kb_spmv_bulk(KbSpmvArgs a,
             }
         }
     }
+}
+__device__ __forceinline__ void kb_bulk_init_barriers(KbBulkSmem& S) {
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int s = 0; s < KB_BULK_STAGES; ++s) { kb_mbar_init(&S.full[s], 1); kb_mbar_init(&S.empty[s], KB_THREADS); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+}
+
+template <class Epi, bool RESID, bool GH = false, bool PROD = false>
+__global__ void __launch_bounds__(KB_BULK_THREADS, 2) kb_spmv_bulk(KbSpmvArgs a, KbChunkTable tb, Epi epi) {
+    if (epi.skip()) return;
+    const double* xg = nullptr;
+    if (GH) xg = kb_halo_wait(a);          // ordered before the gathers by the __syncthreads() below
+    constexpr bool WD = Epi::WDOT, YD = Epi::YDOT;      // fused <w,y> and/or <y,y>
+    constexpr int NDOT = (WD ? 1 : 0) + (YD ? 1 : 0);
+    constexpr int ND = NDOT > 0 ? NDOT : 1;
+    extern __shared__ __align__(128) unsigned char kb_smem_raw[];
+    KbBulkSmem& S = *reinterpret_cast<KbBulkSmem*>(kb_smem_raw);
+    const int tid = threadIdx.x;
+    kb_bulk_init_barriers(S);
+    __syncthreads();
+    int it = 0;
+    if (tid >= KB_THREADS) {
+        // producer warp: one elected lane feeds the shared-memory ring
+        if (tid == KB_THREADS) kb_bulk_produce(a, tb, S, it, kb_policy_evict_first());
+        return;
+    }
+    kb_bulk_consume<WD, YD, RESID, GH, PROD>(a, S, it, xg);
     if constexpr (NDOT > 0) {
         if (a.finalize) {
             if (tid == 0) {

@@ -50,8 +50,11 @@ def test_jacobi_bit_exact(ctx, kind, N):
 
 @pytest.mark.parametrize("kind,N", [("poisson2d", 16), ("poisson2d", 100), ("poisson3d", 24), ("varcoef27", 12)])
 @pytest.mark.parametrize("use_pc", [True, False])
-def test_pcg_bit_exact(ctx, kind, N, use_pc):
+@pytest.mark.parametrize("persistent", ["0", "1"])
+def test_pcg_bit_exact(ctx, kind, N, use_pc, persistent, monkeypatch):
+    """Both drivers: CUDA-graph replay of 3 kernels/iteration, and the single persistent cooperative kernel."""
     import kryst_b200 as kb
+    monkeypatch.setenv("KB_PCG_PERSISTENT", persistent)
     A, Ao = _mk(kind, N, ctx)
     b = o.spmv(Ao, np.ones(Ao.n))
     pc = kb.Jacobi().setup(A) if use_pc else None
