@@ -234,6 +234,15 @@ __device__ __forceinline__ double kb_wait_value_bo(const double* p, unsigned* er
     return __longlong_as_double((long long)v);
 }
 
+__device__ __forceinline__ unsigned long long kb_ld_relaxed_gpu(const double* p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void kb_st_relaxed_gpu(double* p, unsigned long long v) {
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
 // Persistent grid: CTA b handles chunks b, b+G, b+2G, ... in order.  All G CTAs are co-resident (G <= resident
 // capacity), and a chunk only waits on rows of earlier chunks, so progress is guaranteed without tickets; G also
 // bounds the window of in-flight rows to a few levels, so few threads spin at any time.
@@ -285,14 +294,14 @@ __global__ void __launch_bounds__(KB_THREADS) kb_trsv_persistent(KbTrsvEll a) {
                 // poll the (up to 4) dependencies of this group in parallel
                 unsigned long long dv[4];
 #pragma unroll
-                for (int u = 0; u < 4; ++u) dv[u] = cc[u] >= 0 ? *reinterpret_cast<const volatile unsigned long long*>(a.out + cc[u]) : 0ull;
+                for (int u = 0; u < 4; ++u) dv[u] = cc[u] >= 0 ? kb_ld_relaxed_gpu(a.out + cc[u]) : 0ull;
                 unsigned spins = 0;
                 while (true) {
                     bool pending = false;
 #pragma unroll
                     for (int u = 0; u < 4; ++u)
                         if (cc[u] >= 0 && dv[u] == KB_SENTINEL) {
-                            dv[u] = *reinterpret_cast<const volatile unsigned long long*>(a.out + cc[u]);
+                            dv[u] = kb_ld_relaxed_gpu(a.out + cc[u]);
                             pending = pending || (dv[u] == KB_SENTINEL);
                         }
                     if (!pending) break;
@@ -304,7 +313,7 @@ __global__ void __launch_bounds__(KB_THREADS) kb_trsv_persistent(KbTrsvEll a) {
                     if (cc[u] >= 0) s = s - vv[u] * __longlong_as_double((long long)dv[u]);
             }
             if (UPPER) s = s * dg;
-            *reinterpret_cast<volatile unsigned long long*>(a.out + row) = (unsigned long long)__double_as_longlong(s);
+            kb_st_relaxed_gpu(a.out + row, (unsigned long long)__double_as_longlong(s));
         }
         // ---- publish per-level completion (slots of every level present in this chunk)
         __syncthreads();
