@@ -9,9 +9,10 @@ from .api import (BiCgStabSolver, BlockJacobiIlu0, CgNormType, Context, DeviceCs
                   IndefiniteMatrix, IndefinitePreconditioner, Jacobi, KError, PcgSolver, Preconditioning, SolveError,
                   SolveStats, Unsupported, ZeroPivot, default_context, partition_range)
 from . import stencils
+from .context import KspContext, SolverKind
 
 _ffi.lib()   # fail loudly at import time if the CUDA library is missing
 
 __all__ = ["BiCgStabSolver", "BlockJacobiIlu0", "CgNormType", "Context", "DeviceCsr", "FactorError", "GmresSolver", "Ilu0",
            "IndefiniteMatrix", "IndefinitePreconditioner", "Jacobi", "KError", "PcgSolver", "Preconditioning", "SolveError",
-           "SolveStats", "Unsupported", "ZeroPivot", "default_context", "partition_range", "stencils"]
+           "SolveStats", "Unsupported", "ZeroPivot", "default_context", "partition_range", "stencils", "KspContext", "SolverKind"]

@@ -238,3 +238,37 @@ def test_graph_and_plain_launch_paths_agree(ctx):
     for r in res[1:]:
         assert r[0] == res[0][0] and r[1] == res[0][1] and np.array_equal(r[2], res[0][2])
     assert ctx.launch_count() > 0
+
+
+def test_ksp_context_dispatch(ctx):
+    """KspContext::solve_context (src/context/ksp_context.rs:88-148) routes to the same device solvers."""
+    import kryst_b200 as kb
+    from kryst_b200 import stencils
+    n, rp, ci, v = stencils.stencil("convdiff2d", 20)
+    A = kb.DeviceCsr.from_csr(n, n, rp, ci, v, ctx)
+    Ao = o.OCsr(n, n, rp, ci, v)
+    b = o.spmv(Ao, np.ones(n))
+    x = np.zeros(n)
+    st = kb.KspContext(kb.SolverKind.GmresLeft, A, kb.Ilu0().setup(A), tol=1e-9, max_it=500, restart=12).solve_context(b, x)
+    rc, xo, so = o.gmres(Ao, o.OPc.ilu0(Ao), b, np.zeros(n), 12, 1e-9, 500, mode=1, variant=o.GMRES_CGS2)
+    assert st.iterations == so.iterations and np.array_equal(x, xo)
+    x = np.zeros(n)
+    st = kb.KspContext(kb.SolverKind.GmresRight, A, kb.Jacobi().setup(A), tol=1e-9, max_it=500, restart=12).solve_context(b, x)
+    rc, xo, so = o.gmres(Ao, o.OPc.jacobi(Ao), b, np.zeros(n), 12, 1e-9, 500, mode=2, variant=o.GMRES_CGS2)
+    assert st.iterations == so.iterations and np.array_equal(x, xo)
+    x = np.zeros(n)
+    tol_abs = 1e-8 * float(np.linalg.norm(b))
+    st = kb.KspContext(kb.SolverKind.Bicgstab, A, kb.Jacobi().setup(A), tol=tol_abs, max_it=500).solve_context(b, x)
+    rc, xo, so = o.bicgstab(Ao, None, b, np.zeros(n), tol_abs, 500)
+    assert st.iterations == so.iterations and np.array_equal(x, xo)
+    ns, rps, cis, vs = stencils.stencil("poisson2d", 20)
+    S = kb.DeviceCsr.from_csr(ns, ns, rps, cis, vs, ctx)
+    So = o.OCsr(ns, ns, rps, cis, vs)
+    bs = o.spmv(So, np.ones(ns))
+    for kind, pco in ((kb.SolverKind.Pcg, o.OPc.jacobi(So)), (kb.SolverKind.Cg, None)):
+        x = np.zeros(ns)
+        st = kb.KspContext(kind, S, kb.Jacobi().setup(S), tol=1e-9, max_it=500).solve_context(bs, x)
+        rc, xo, so, _ = o.pcg(So, pco, bs, np.zeros(ns), 1e-9, 500)
+        assert st.iterations == so.iterations and np.array_equal(x, xo)
+    with pytest.raises(kb.Unsupported):
+        kb.KspContext(kb.SolverKind.Minres, S).solve_context(bs, np.zeros(ns))
