@@ -136,6 +136,11 @@ int kb_pcg_solve(kb_csr a, kb_pc pc, const double* b, double* x, double tol, uin
  * orthogonalisation is CGS2 as a block GEMV (Tier T formulation for Left/Right).     */
 int kb_gmres_solve(kb_csr a, kb_pc pc, const double* b, double* x, uint64_t restart, double tol,
                    uint64_t max_iters, int side, uint32_t flags, kb_stats* stats);
+/* FgmresSolver::new(tol,max_iters,restart).solve_flex(&a, pc, &b, &mut x) (src/solver/fgmres.rs:52-340):
+ * flexible right-preconditioned GMRES, one classical Gram-Schmidt pass, z_j = M^-1 v_j kept; the reference's quirks
+ * are reproduced (inner test relative to the current cycle's residual, absolute cycle test, final_residual = ||r0||). */
+int kb_fgmres_solve(kb_csr a, kb_pc pc, const double* b, double* x, uint64_t restart, double tol,
+                    uint64_t max_iters, uint32_t flags, kb_stats* stats);
 /* BiCgStabSolver::new(tol,max_iters).solve (bicgstab.rs:45-47,69-293).  Default = literal
  * (pc ignored, absolute tol); KB_FLAG_TEXTBOOK = right-preconditioned, relative tol.             */
 int kb_bicgstab_solve(kb_csr a, kb_pc pc, const double* b, double* x, double tol, uint64_t max_iters,

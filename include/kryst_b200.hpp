@@ -149,6 +149,17 @@ public:
 private:
     size_t restart_; double tol_; size_t max_iters_; Preconditioning mode_ = Preconditioning::Left;   // gmres.rs:53
 };
+class FgmresSolver {         // src/solver/fgmres.rs:30-340: FgmresSolver::new(tol, max_iters, restart).solve_flex(..)
+public:
+    FgmresSolver(double tol, size_t max_iters, size_t restart) : tol_(tol), max_iters_(max_iters), restart_(restart) {}
+    SolveStats solve_flex(const DeviceCsr& a, const Preconditioner* pc, const std::vector<double>& b, std::vector<double>& x) {
+        kb_stats st{};
+        check(kb_fgmres_solve(a.handle(), pc ? pc->handle() : nullptr, b.data(), x.data(), restart_, tol_, max_iters_, 0, &st));
+        return to_stats(st);
+    }
+private:
+    double tol_; size_t max_iters_; size_t restart_;
+};
 class BiCgStabSolver {       // src/solver/bicgstab.rs:36-293 (textbook=true: right-preconditioned, relative tol)
 public:
     BiCgStabSolver(double tol, size_t max_iters, bool textbook = false) : tol_(tol), max_iters_(max_iters), textbook_(textbook) {}

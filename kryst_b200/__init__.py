@@ -5,7 +5,7 @@ package is the host-side mirror of the reference's operator / preconditioner / s
 There is no CPU fallback: importing fails when libkryst_b200.so has not been built.
 """
 from . import _ffi
-from .api import (BiCgStabSolver, BlockJacobiIlu0, CgNormType, Context, DeviceCsr, FactorError, GmresSolver, Ilu0,
+from .api import (BiCgStabSolver, BlockJacobiIlu0, CgNormType, Context, DeviceCsr, FactorError, FgmresSolver, GmresSolver, Ilu0,
                   IndefiniteMatrix, IndefinitePreconditioner, Jacobi, KError, PcgSolver, Preconditioning, SolveError,
                   SolveStats, Unsupported, ZeroPivot, default_context, partition_range)
 from . import stencils
@@ -13,6 +13,6 @@ from .context import KspContext, SolverKind
 
 _ffi.lib()   # fail loudly at import time if the CUDA library is missing
 
-__all__ = ["BiCgStabSolver", "BlockJacobiIlu0", "CgNormType", "Context", "DeviceCsr", "FactorError", "GmresSolver", "Ilu0",
+__all__ = ["BiCgStabSolver", "BlockJacobiIlu0", "CgNormType", "Context", "DeviceCsr", "FactorError", "FgmresSolver", "GmresSolver", "Ilu0",
            "IndefiniteMatrix", "IndefinitePreconditioner", "Jacobi", "KError", "PcgSolver", "Preconditioning", "SolveError",
            "SolveStats", "Unsupported", "ZeroPivot", "default_context", "partition_range", "stencils", "KspContext", "SolverKind"]

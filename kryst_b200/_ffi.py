@@ -66,6 +66,8 @@ SIGNATURES = {
                                C.c_uint32, f64p, C.c_uint64, u64p, C.POINTER(KbStats)]),
     "kb_gmres_solve": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_double, C.c_uint64,
                                  C.c_int, C.c_uint32, C.POINTER(KbStats)]),
+    "kb_fgmres_solve": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_double, C.c_uint64,
+                                  C.c_uint32, C.POINTER(KbStats)]),
     "kb_bicgstab_solve": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_uint64,
                                     C.c_uint32, C.POINTER(KbStats)]),
     "kb_profile_reset": (C.c_int, [C.c_void_p]),

@@ -507,6 +507,25 @@ class GmresSolver(_SolverBase):
         return self.last_stats
 
 
+class FgmresSolver(_SolverBase):
+    """FgmresSolver::new(tol, max_iters, restart) (src/solver/fgmres.rs:52-66); solve_flex at fgmres.rs:114-340."""
+
+    def __init__(self, tol, max_iters, restart):
+        self.tol, self.max_iters, self.restart = float(tol), int(max_iters), int(restart)
+
+    def solve_flex(self, a, pc, b, x):
+        pb, px, flags, keep = self._solve_args(a, b, x)
+        st = KbStats()
+        rc = _ffi.lib().kb_fgmres_solve(a.handle, _pc_handle(pc), pb, px, self.restart, self.tol, self.max_iters, flags, C.byref(st))
+        self.last_stats = SolveStats(st.iterations, st.final_residual, st.converged, st.breakdown)
+        _check(rc)
+        if keep[2] is not None:
+            keep[2][...] = keep[1]
+        return self.last_stats
+
+    solve = solve_flex
+
+
 class BiCgStabSolver(_SolverBase):
     """BiCgStabSolver::new(tol, max_iters) (src/solver/bicgstab.rs:45-47); solve at bicgstab.rs:69-293.
 

@@ -2,13 +2,13 @@
 
 Mirror of src/context/ksp_context.rs:25-148: public fields `kind, a, pc, tol, max_it, restart` and
 `solve_context(b, x, comm)`, which builds the solver with (tol, max_it[, restart]) and forwards to `solve`.
-The kinds on the north-star path run on the device; the others (CGS, QMR, TFQMR, MINRES, CGNR, FGMRES) are out of
+The kinds on the north-star path (and FGMRES) run on the device; the others (CGS, QMR, TFQMR, MINRES, CGNR) are out of
 scope of this build and raise `Unsupported`.  Unlike the reference (ksp_context.rs:88 accepts `comm` and never uses
 it), a row-partitioned operator already carries its communicator, so `comm` is only checked for consistency.
 """
 import enum
 
-from .api import BiCgStabSolver, GmresSolver, PcgSolver, Preconditioning, Unsupported
+from .api import BiCgStabSolver, FgmresSolver, GmresSolver, PcgSolver, Preconditioning, Unsupported
 
 
 class SolverKind(enum.Enum):           # ksp_context.rs:25-48
@@ -48,4 +48,6 @@ class KspContext:
             return PcgSolver(self.tol, self.max_it).solve(self.a, None, b, x)
         if k is SolverKind.Bicgstab:
             return BiCgStabSolver(self.tol, self.max_it).solve(self.a, self.pc, b, x)
+        if k is SolverKind.Fgmres:
+            return FgmresSolver(self.tol, self.max_it, self.restart).solve_flex(self.a, self.flex_pc, b, x)
         raise Unsupported("SolverKind::%s is not on the device hot path" % k.value)

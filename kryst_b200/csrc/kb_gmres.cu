@@ -23,7 +23,10 @@ struct KbGmresDev {       // device pointers shared by the kernels
     KbCtl* ctl;
     double* V; size_t ld;
     const double* h1src; const double* h2src;   // where the (all-reduced) CGS coefficients live
+    int flex;                                   // FGMRES (fgmres.rs): single-pass CGS, z_j = M^-1 v_j kept, literal quirks
+    double* Z;                                  // flexible basis (== V when there is no preconditioner)
 };
+#define KB_SIDE_FLEX 3
 
 // ---- multi-column dot: partial[c][tile] = canonical tile sum of V_c . w, c = 0..j ----------------------
 __global__ void __launch_bounds__(KB_THREADS) kb_gs_dot(KbGmresDev g, const double* __restrict__ w, long long n, double* partials, size_t pstride,
@@ -113,7 +116,8 @@ __global__ void __launch_bounds__(KB_THREADS) kb_gs_level2(KbCtl* ctl, const dou
 __device__ void kb_arnoldi_fin(const KbGmresDev& g, double ww, int j) {
     KbCtl* c = g.ctl;
     __shared__ double hcol[KB_MAX_RESTART + 2], scs[KB_MAX_RESTART], ssn[KB_MAX_RESTART];
-    for (int k = threadIdx.x; k <= j; k += blockDim.x) hcol[k] = g.h1src[k] + g.h2src[k];
+    if (g.flex) { for (int k = threadIdx.x; k <= j; k += blockDim.x) hcol[k] = g.h1src[k]; }      // one classical GS pass (fgmres.rs:219-228)
+    else { for (int k = threadIdx.x; k <= j; k += blockDim.x) hcol[k] = g.h1src[k] + g.h2src[k]; }
     for (int k = threadIdx.x; k < j; k += blockDim.x) { scs[k] = c->cs[k]; ssn[k] = c->sn[k]; }
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -121,7 +125,8 @@ __device__ void kb_arnoldi_fin(const KbGmresDev& g, double ww, int j) {
         const double hn = sqrt(ww);
         hcol[j + 1] = hn;
         c->hnorm = hn;
-        const int happy = fabs(hn) < KB_GM_EPS;
+        // happy breakdown: gmres.rs:97-101 (|h| < 1e-14) ; fgmres.rs:253-262 (|h| < haptol*|s_j|, v_{j+1} := 0, no break)
+        const int happy = g.flex ? (fabs(hn) < 1e-12 * fabs(c->g[j])) : (fabs(hn) < KB_GM_EPS);
         for (int i = 0; i < j; ++i) {                       // gmres.rs:155-159
             const double temp = scs[i] * hcol[i] + ssn[i] * hcol[i + 1];
             hcol[i + 1] = -ssn[i] * hcol[i] + scs[i] * hcol[i + 1];
@@ -130,7 +135,7 @@ __device__ void kb_arnoldi_fin(const KbGmresDev& g, double ww, int j) {
         const double hkk = hcol[j], hk1k = hcol[j + 1];
         const double r = sqrt(hkk * hkk + hk1k * hk1k);
         double cj, sj;
-        if (fabs(r) < KB_GM_EPS) { cj = 1.0; sj = 0.0; } else { cj = hkk / r; sj = hk1k / r; }
+        if (g.flex ? (r == 0.0) : (fabs(r) < KB_GM_EPS)) { cj = 1.0; sj = 0.0; } else { cj = hkk / r; sj = hk1k / r; }
         hcol[j] = cj * hkk + sj * hk1k;
         hcol[j + 1] = 0.0;
         c->cs[j] = cj; c->sn[j] = sj;
@@ -142,11 +147,12 @@ __device__ void kb_arnoldi_fin(const KbGmresDev& g, double ww, int j) {
         const double res_norm = fabs(c->g[j + 1]);
         const unsigned long long it = c->iter + 1;
         c->iter = it;
-        const double rel = res_norm / c->res0;              // Convergence::check (convergence.rs:18-34)
+        const double rel = res_norm / (g.flex ? c->beta_g : c->res0);   // Convergence::check; FGMRES divides by this cycle's s[0] (fgmres.rs:292)
         const int stop = (rel <= c->tol) || (it >= c->max_iters);
         c->res = res_norm; c->converged = stop;
-        c->m = j + 1; c->happy = happy;
-        if (stop || happy) c->cycle_break = 1;
+        c->m = j + 1; c->happy = g.flex ? (c->happy | happy) : happy;
+        if (g.flex) { c->hflag = happy; if (stop) { c->cycle_break = 1; c->early = 1; } }   // early: "converged" of fgmres.rs:299
+        else if (stop || happy) c->cycle_break = 1;
         c->j = j + 1;
     }
 }
@@ -193,10 +199,15 @@ struct ScaleOp : KbRedBase {
     __device__ bool skip() const {
         const KbCtl* c = g.ctl;
         if (c->done) return true;
+        if (g.flex) return start_vec ? false : (c->cycle_break != 0);
         return start_vec ? false : (c->happy != 0 || c->cycle_break != 0);
     }
     __device__ void pair(long long i, bool has1, double*) const {
         const KbCtl* c = g.ctl;
+        if (g.flex && !start_vec && c->hflag) {           // fgmres.rs:261: v_{j+1} := 0
+            if (has1) kb_st2(dst + i, make_double2(0.0, 0.0)); else dst[i] = 0.0;
+            return;
+        }
         const double d = start_vec ? c->beta_g : c->hnorm;
         if (has1) { double2 t = kb_ld2(src + i); kb_st2(dst + i, make_double2(t.x / d, t.y / d)); }
         else dst[i] = src[i] / d;
@@ -217,7 +228,8 @@ __global__ void kb_gmres_backsubst(KbCtl* c) {
         for (int i = m - 1; i >= 0; --i) {
             double yi = G[i];
             for (int j = i + 1; j < m; ++j) yi = yi - H[i * m + j] * Y[j];
-            if (fabs(H[i * m + i]) > KB_GM_EPS) yi = yi / H[i * m + i]; else yi = 0.0;
+            if (c->side == KB_SIDE_FLEX) yi = yi / H[i * m + i];                      // fgmres.rs:309-315
+            else if (fabs(H[i * m + i]) > KB_GM_EPS) yi = yi / H[i * m + i]; else yi = 0.0;
             Y[i] = yi; c->y[i] = yi;
         }
     }
@@ -227,7 +239,7 @@ __global__ void kb_gmres_backsubst(KbCtl* c) {
 template <bool RIGHT>
 struct UpdateXOp : KbRedBase {
     static constexpr int NRED = 0;
-    KbGmresDev g; double* x; double* out;
+    KbGmresDev g; double* x; double* out; const double* basis;
     __device__ bool skip() const { return g.ctl->done != 0; }
     __device__ void pair(long long i, bool has1, double*) const {
         const KbCtl* c = g.ctl;
@@ -236,14 +248,14 @@ struct UpdateXOp : KbRedBase {
             double2 t = RIGHT ? make_double2(0.0, 0.0) : kb_ld2(x + i);
 #pragma unroll 4
             for (int j = 0; j < m; ++j) {
-                const double2 v = kb_ld2(g.V + (size_t)j * g.ld + i);
+                const double2 v = kb_ld2(basis + (size_t)j * g.ld + i);
                 const double y = c->y[j];
                 t.x = t.x + y * v.x; t.y = t.y + y * v.y;
             }
             kb_st2((RIGHT ? out : x) + i, t);
         } else {
             double t = RIGHT ? 0.0 : x[i];
-            for (int j = 0; j < m; ++j) t = t + c->y[j] * g.V[(size_t)j * g.ld + i];
+            for (int j = 0; j < m; ++j) t = t + c->y[j] * basis[(size_t)j * g.ld + i];
             (RIGHT ? out : x)[i] = t;
         }
     }
@@ -289,6 +301,27 @@ struct GmCycleFin {    // gmres.rs:388-398
         gm_reset_cycle(c, beta);
     }
 };
+struct FgInitFin {     // fgmres.rs:146-158
+    KbCtl* ctl;
+    __device__ void operator()(const double* s) const {
+        KbCtl* c = ctl;
+        const double beta = sqrt(s[0]);
+        c->res0_true = beta; c->res0 = beta; c->res = beta; c->converged = 0; c->iter = 0; c->outer = 0; c->early = 0; c->hflag = 0;
+        if (beta == 0.0) { c->res0_true = 0.0; c->converged = 1; c->done = 1; return; }
+        if (c->max_iters == 0) { c->done = 1; return; }
+        gm_reset_cycle(c, beta);
+    }
+};
+struct FgCycleFin {    // fgmres.rs:317-334
+    KbCtl* ctl;
+    __device__ void operator()(const double* s) const {
+        KbCtl* c = ctl;
+        const double rn = sqrt(s[0]);
+        if (rn < c->tol || c->early) { c->converged = 1; c->done = 1; return; }   // ABSOLUTE test, or the inner stop fired
+        if (c->iter >= c->max_iters) { c->done = 1; return; }
+        gm_reset_cycle(c, rn);
+    }
+};
 struct GmLeftNormFin { // textbook left: r0_norm = ||M^-1 r||, inner denominator from the first cycle
     KbCtl* ctl;
     __device__ void operator()(const double* s) const {
@@ -313,7 +346,7 @@ struct NormOp : KbRedBase {
 // ---- workspace --------------------------------------------------------------------------------------------
 struct KbGmresWs {
     uint64_t n = 0, nx = 0; int restart = 0; size_t ld = 0;
-    double *V = nullptr, *x = nullptr, *b = nullptr, *r = nullptr, *w = nullptr, *t = nullptr, *z = nullptr;
+    double *V = nullptr, *Z = nullptr, *x = nullptr, *b = nullptr, *r = nullptr, *w = nullptr, *t = nullptr, *z = nullptr;
     double* partials = nullptr; size_t pstride = 0;
     double* slots = nullptr;
     KbCtl* ctl = nullptr; KbCtl* h_ctl = nullptr;
@@ -322,7 +355,7 @@ struct KbGmresWs {
 void kb_gmres_ws_free(KbGmresWs* w) {
     if (!w) return;
     w->gc.reset();
-    KB_FREE(w->V); KB_FREE(w->x); KB_FREE(w->b); KB_FREE(w->r); KB_FREE(w->w); KB_FREE(w->t); KB_FREE(w->z);
+    KB_FREE(w->V); KB_FREE(w->Z); KB_FREE(w->x); KB_FREE(w->b); KB_FREE(w->r); KB_FREE(w->w); KB_FREE(w->t); KB_FREE(w->z);
     KB_FREE(w->partials); KB_FREE(w->slots); KB_FREE(w->ctl);
     if (w->h_ctl) cudaFreeHost(w->h_ctl);
     delete w;
@@ -388,6 +421,28 @@ static int gm_inner_iteration(GmPlan& P, int j) {
     const bool fuse = fuse_env && ncols <= 32;      // the basis tile must fit in registers
     typedef KbSpmvEpi<GmNoFin, false, false> Epi;
     Epi epi; epi.ctl = ctl; epi.skip_mask = 2; epi.fin = kb_make_fin(c, GmNoFin{}, false, nullptr, 0);
+    if (P.g.flex) {                          // z_j = M^-1 v_j kept ; w = A z_j ; one classical GS pass (fgmres.rs:205-251)
+        double* zj = P.pc ? P.g.Z + (size_t)j * w->ld : vj;
+        if (P.pc) KB_TRY(kb_pc_apply_dev(P.pc, vj, zj, ctl, 2));
+        KB_TRY((kb_launch_spmv<Epi, false>(A, zj, w->w, nullptr, nullptr, nullptr, 0, epi, P.dist ? zj : nullptr)));
+        { KbLaunch L(c, KB_K_GS_DOT); kb_gs_dot<<<A->ntiles, KB_THREADS, 0, c->stream>>>(P.g, w->w, (long long)A->n, w->partials, w->pstride, ncols); }
+        double* dst = P.dist ? w->slots : &ctl->h1[0];
+        { KbLaunch L(c, KB_K_SMALL); kb_gs_level2<<<ncols, KB_THREADS, 0, c->stream>>>(ctl, w->partials, w->pstride, A->ntiles, dst); }
+        if (P.dist) KB_TRY(kb_allreduce_slots(c, w->slots, ncols));
+        double* s3 = w->slots + 2 * (KB_MAX_RESTART + 8);
+        GsUpdateOp<true> op; op.partials = w->partials; op.pstride = w->pstride; op.g = P.g; op.w = w->w; op.hsrc = P.g.h1src;
+        op.p2p = P.dist ? kb_p2p_dev_ptr(c) : nullptr;
+        op.slots = (P.dist && !op.p2p) ? s3 : nullptr; op.ncols = ncols;
+        KB_TRY(gm_tile(A, op, KB_K_GS_UPDATE));
+        if (P.dist && !op.p2p) {
+            KB_TRY(kb_allreduce_slots(c, s3, 1));
+            KbLaunch L(c, KB_K_SMALL);
+            kb_arnoldi_fin_kernel<<<1, KB_THREADS, 0, c->stream>>>(P.g, s3, j);
+            KB_CUDA(cudaGetLastError());
+        }
+        ScaleOp sc; sc.partials = nullptr; sc.pstride = 0; sc.g = P.g; sc.src = w->w; sc.dst = w->V + (size_t)(j + 1) * w->ld; sc.start_vec = 0;
+        return gm_tile(A, sc, KB_K_SMALL);
+    }
     if (P.side == KB_SIDE_LEFT) {            // w = M^-1 (A v_j)
         KB_TRY((kb_launch_spmv<Epi, false>(A, vj, w->z, nullptr, nullptr, nullptr, 0, epi, P.dist ? vj : nullptr)));
         KB_TRY(kb_pc_apply_dev(P.pc, w->z, w->w, ctl, 2));
@@ -452,31 +507,50 @@ static int gm_cycle(GmPlan& P) {
         KB_CUDA(cudaGetLastError());
     }
     if (P.side == KB_SIDE_RIGHT) {           // x += M^-1 (V y)
-        UpdateXOp<true> op; op.partials = nullptr; op.pstride = 0; op.g = P.g; op.x = w->x; op.out = w->w;
+        UpdateXOp<true> op; op.partials = nullptr; op.pstride = 0; op.g = P.g; op.x = w->x; op.out = w->w; op.basis = w->V;
         KB_TRY(gm_tile(A, op, KB_K_GS_UPDATE));
         KB_TRY(kb_pc_apply_dev(P.pc, w->w, w->z, w->ctl, 0));
         AddOp add; add.partials = nullptr; add.pstride = 0; add.ctl = w->ctl; add.x = w->x; add.z = w->z;
         KB_TRY(gm_tile(A, add, KB_K_SMALL));
     } else {
-        UpdateXOp<false> op; op.partials = nullptr; op.pstride = 0; op.g = P.g; op.x = w->x; op.out = nullptr;
+        UpdateXOp<false> op; op.partials = nullptr; op.pstride = 0; op.g = P.g; op.x = w->x; op.out = nullptr; op.basis = P.g.flex ? P.g.Z : w->V;
         KB_TRY(gm_tile(A, op, KB_K_GS_UPDATE));
     }
     {   // r = b - A x ; beta = ||r|| ; converged = beta < tol * res0 (gmres.rs:388-398)
+        if (P.g.flex) {
+            typedef KbSpmvEpi<FgCycleFin, false, true> Epi;
+            Epi epi; epi.ctl = w->ctl; epi.fin = kb_make_fin(c, FgCycleFin{w->ctl}, P.dist, w->slots, 1);
+            KB_TRY((kb_launch_spmv<Epi, true>(A, w->x, w->r, w->b, nullptr, w->partials, w->pstride, epi, P.dist ? w->x : nullptr)));
+            if (P.dist) KB_TRY((kb_finish_dist<FgCycleFin>(c, FgCycleFin{w->ctl}, w->ctl, w->slots, 1)));
+        } else {
         typedef KbSpmvEpi<GmCycleFin, false, true> Epi;
         Epi epi; epi.ctl = w->ctl; epi.fin = kb_make_fin(c, GmCycleFin{w->ctl}, P.dist, w->slots, 1);
         KB_TRY((kb_launch_spmv<Epi, true>(A, w->x, w->r, w->b, nullptr, w->partials, w->pstride, epi, P.dist ? w->x : nullptr)));
         if (P.dist) KB_TRY((kb_finish_dist<GmCycleFin>(c, GmCycleFin{w->ctl}, w->ctl, w->slots, 1)));
+        }
     }
     return gm_start_vector(P);
 }
 
+static int gmres_solve_impl(kb_csr A, kb_pc pc, const double* b, double* x, uint64_t restart, double tol, uint64_t max_iters, int side,
+                            uint32_t flags, kb_stats* stats);
 extern "C" int kb_gmres_solve(kb_csr A, kb_pc pc, const double* b, double* x, uint64_t restart, double tol, uint64_t max_iters, int side,
                               uint32_t flags, kb_stats* stats) {
+    if (side < 0 || side > 2) { kb_set_error("bad preconditioning side"); return KB_SOLVE_ERROR; }
+    return gmres_solve_impl(A, pc, b, x, restart, tol, max_iters, side, flags, stats);
+}
+// FgmresSolver::new(tol, max_iters, restart).solve_flex(&a, pc, &b, &mut x)  (src/solver/fgmres.rs:52-340)
+extern "C" int kb_fgmres_solve(kb_csr A, kb_pc pc, const double* b, double* x, uint64_t restart, double tol, uint64_t max_iters,
+                               uint32_t flags, kb_stats* stats) {
+    return gmres_solve_impl(A, pc, b, x, restart, tol, max_iters, KB_SIDE_FLEX, flags, stats);
+}
+static int gmres_solve_impl(kb_csr A, kb_pc pc, const double* b, double* x, uint64_t restart, double tol, uint64_t max_iters, int side,
+                            uint32_t flags, kb_stats* stats) {
     if (!A || !b || !x || !stats) { kb_set_error("kb_gmres_solve: null argument"); return KB_SOLVE_ERROR; }
     if (pc && pc->a != A) { kb_set_error("preconditioner was set up for a different operator"); return KB_SOLVE_ERROR; }
     if (restart < 1 || restart > KB_MAX_RESTART) { kb_set_error("restart must be in [1,%d]", KB_MAX_RESTART); return KB_UNSUPPORTED; }
-    if (side < 0 || side > 2) { kb_set_error("bad preconditioning side"); return KB_SOLVE_ERROR; }
-    if (!pc) side = KB_SIDE_NONE;               // gmres.rs:262: `_ =>` branch when pc is None
+    const bool flex = side == KB_SIDE_FLEX;
+    if (!pc && !flex) side = KB_SIDE_NONE;      // gmres.rs:262: `_ =>` branch when pc is None
     kb_ctx_s* c = A->ctx;
     KB_CUDA(cudaSetDevice(c->device));
     const bool dev = (flags & KB_FLAG_DEVICE_PTRS) != 0;
@@ -491,11 +565,14 @@ extern "C" int kb_gmres_solve(kb_csr A, kb_pc pc, const double* b, double* x, ui
     memset(h, 0, offsetof(KbCtl, h));
     h->max_iters = max_iters; h->tol = tol; h->restart = (int)restart; h->side = side;
     h->n_outer = (int)std::min<uint64_t>((max_iters + restart - 1) / restart, 0x7fffffffull);
+    if (flex) h->n_outer = (int)std::min<uint64_t>(max_iters, 0x7fffffffull);   // `while total_iters < max_iters` (fgmres.rs:162): every cycle makes >= 1 step
+    if (flex && pc && !w->Z) KB_TRY(kb_alloc(&w->Z, w->ld * (size_t)w->restart));
     KB_CUDA(cudaMemcpyAsync(w->ctl, h, offsetof(KbCtl, h), cudaMemcpyHostToDevice, c->stream));
     GmPlan P{A, pc, w, side, dist, (int)restart, {}};
     P.g.ctl = w->ctl; P.g.V = w->V; P.g.ld = w->ld;
     P.g.h1src = dist ? w->slots : &w->ctl->h1[0];
     P.g.h2src = dist ? w->slots + (KB_MAX_RESTART + 8) : &w->ctl->h2[0];
+    P.g.flex = flex ? 1 : 0; P.g.Z = (flex && pc) ? w->Z : w->V;
     const bool profile = (flags & KB_FLAG_PROFILE) != 0;
     const bool use_graph = !(flags & (KB_FLAG_NO_GRAPH | KB_FLAG_PROFILE));
     const bool was_prof = c->profiling;
@@ -503,10 +580,17 @@ extern "C" int kb_gmres_solve(kb_csr A, kb_pc pc, const double* b, double* x, ui
     int st = KB_OK;
     do {
         {   // r0 = b - A x ; beta = ||r0|| (gmres.rs:221-229)
+            if (flex) {
+                typedef KbSpmvEpi<FgInitFin, false, true> Epi;
+                Epi epi; epi.ctl = nullptr; epi.fin = kb_make_fin(c, FgInitFin{w->ctl}, dist, w->slots, 1);
+                if ((st = kb_launch_spmv<Epi, true>(A, w->x, w->r, w->b, nullptr, w->partials, w->pstride, epi, dist ? w->x : nullptr)) != KB_OK) break;
+                if (dist && (st = kb_finish_dist<FgInitFin>(c, FgInitFin{w->ctl}, w->ctl, w->slots, 1)) != KB_OK) break;
+            } else {
             typedef KbSpmvEpi<GmInitFin, false, true> Epi;
             Epi epi; epi.ctl = nullptr; epi.fin = kb_make_fin(c, GmInitFin{w->ctl}, dist, w->slots, 1);
             if ((st = kb_launch_spmv<Epi, true>(A, w->x, w->r, w->b, nullptr, w->partials, w->pstride, epi, dist ? w->x : nullptr)) != KB_OK) break;
             if (dist && (st = kb_finish_dist<GmInitFin>(c, GmInitFin{w->ctl}, w->ctl, w->slots, 1)) != KB_OK) break;
+            }
         }
         if ((st = gm_start_vector(P)) != KB_OK) break;
         const uint64_t key = (((uint64_t)(uintptr_t)pc + 1) * 4 + (uint64_t)side) * 256 + restart;
@@ -514,7 +598,7 @@ extern "C" int kb_gmres_solve(kb_csr A, kb_pc pc, const double* b, double* x, ui
         if (st != KB_OK) break;
         if (cudaMemcpyAsync(h, w->ctl, offsetof(KbCtl, h), cudaMemcpyDeviceToHost, c->stream) != cudaSuccess ||
             cudaStreamSynchronize(c->stream) != cudaSuccess) { kb_set_error("gmres: readback failed"); st = KB_SOLVE_ERROR; break; }
-        stats->iterations = h->iter; stats->final_residual = h->res; stats->converged = h->converged; stats->breakdown = h->happy;
+        stats->iterations = h->iter; stats->final_residual = flex ? h->res0_true : h->res; stats->converged = h->converged; stats->breakdown = h->happy;
         st = h->status;
         if (dist && kb_p2p_error(c)) { kb_set_error("%s: peer-memory collective timed out", "gmres"); st = KB_SOLVE_ERROR; break; }
         if (st == KB_OK) {

@@ -69,6 +69,7 @@ struct KbCtl {
     int restart;
     int cycle_break;           // inner loop of this cycle has exited
     int happy;
+    int hflag;                 // FGMRES: happy breakdown of the current step only
     int side;
     int outer, n_outer;
     double res0_true, beta_g, hnorm;

@@ -652,6 +652,91 @@ int ko_gmres(const ko_csr* A, const ko_pc* pc, const double* b, double* x, u64 r
 }
 
 // ----------------------------------------------------------------------------
+// FGMRES literal — src/solver/fgmres.rs:114-340 (Saad §9.4), Orthog::Classical default (:219-228: all dots on the
+// unmodified w, then the subtractions), haptol 1e-12 (:59), quirks kept as they are:
+//   * the stop test divides by s[0] of the CURRENT cycle (:292), and hitting max_iters reports converged (F8);
+//   * a happy breakdown zeroes v_{j+1} and carries on (:255-262);
+//   * the cycle test is ABSOLUTE: ||b - A x|| < tol (:323);
+//   * the returned final_residual is the INITIAL ||r0|| (the outer `res_norm` binding, :158 and :337).
+// ----------------------------------------------------------------------------
+int ko_fgmres(const ko_csr* A, const ko_pc* pc, const double* b, double* x, u64 restart, double tol, u64 max_iters,
+              u64 nshards, ko_stats* stats) {
+    const u64 n = A->n;
+    auto DOT = [&](const double* a, const double* c) { return ko_dot_sharded(n, a, c, nshards); };
+    auto NRM = [&](const double* a) { return std::sqrt(ko_dot_sharded(n, a, a, nshards)); };
+    std::vector<double> xk(x, x + n), r(n), tmp(n), w(n);
+    ko_spmv(A, xk.data(), tmp.data());
+    for (u64 i = 0; i < n; ++i) r[i] = b[i] - tmp[i];
+    double beta = NRM(r.data());
+    stats->iterations = 0; stats->final_residual = beta; stats->converged = 0; stats->breakdown = 0;
+    if (beta == 0.0) { stats->final_residual = 0.0; stats->converged = 1; return KO_OK; }
+    const double res_norm_outer = beta;
+    std::vector<std::vector<double>> V(restart + 1, std::vector<double>(n, 0.0)), Z(restart, std::vector<double>(n, 0.0));
+    std::vector<std::vector<double>> h(restart + 1, std::vector<double>(restart, 0.0));
+    std::vector<double> cs(restart, 0.0), sn(restart, 0.0), s(restart + 1, 0.0);
+    s[0] = beta;
+    for (u64 i = 0; i < n; ++i) V[0][i] = r[i] / beta;
+    u64 total = 0;
+    while (total < max_iters) {
+        const u64 m = std::min<u64>(restart, max_iters - total);
+        bool converged = false;
+        u64 steps = m;
+        for (u64 j = 0; j < m; ++j) {
+            if (pc && pc->kind != KO_PC_NONE) pc_apply(pc, V[j].data(), Z[j].data(), n); else Z[j] = V[j];
+            ko_spmv(A, Z[j].data(), w.data());
+            std::vector<double> hc(j + 2, 0.0);
+            for (u64 i = 0; i <= j; ++i) hc[i] = DOT(w.data(), V[i].data());
+#pragma omp parallel for schedule(static)
+            for (i64 k = 0; k < (i64)n; ++k) { double t = w[k]; for (u64 i = 0; i <= j; ++i) t = t - hc[i] * V[i][k]; w[k] = t; }
+            h[j + 1][j] = NRM(w.data());
+            for (u64 i = 0; i <= j; ++i) h[i][j] = hc[i];
+            const double hapbnd = 1e-12 * std::fabs(s[j]);
+            if (!(std::fabs(h[j + 1][j]) < hapbnd)) { const double wn = h[j + 1][j]; for (u64 k = 0; k < n; ++k) V[j + 1][k] = w[k] / wn; }
+            else { stats->breakdown = 1; std::fill(V[j + 1].begin(), V[j + 1].end(), 0.0); }
+            for (u64 i = 0; i < j; ++i) {
+                double temp = cs[i] * h[i][j] + sn[i] * h[i + 1][j];
+                h[i + 1][j] = -sn[i] * h[i][j] + cs[i] * h[i + 1][j];
+                h[i][j] = temp;
+            }
+            const double h1 = h[j][j], h2 = h[j + 1][j];
+            const double denom = std::sqrt(h1 * h1 + h2 * h2);
+            double c, s_;
+            if (denom == 0.0) { c = 1.0; s_ = 0.0; } else { c = h1 / denom; s_ = h2 / denom; }
+            cs[j] = c; sn[j] = s_;
+            const double temp = c * s[j] + s_ * s[j + 1];
+            s[j + 1] = -s_ * s[j] + c * s[j + 1];
+            s[j] = temp;
+            h[j][j] = c * h[j][j] + s_ * h[j + 1][j];
+            h[j + 1][j] = 0.0;
+            const double rn = std::fabs(s[j + 1]);
+            total += 1;
+            if (conv_check(rn, s[0], total, tol, max_iters, stats)) { steps = j + 1; converged = true; break; }
+        }
+        const u64 k = steps;
+        std::vector<double> y(k, 0.0);
+        for (u64 i = k; i-- > 0;) {
+            double sum = s[i];
+            for (u64 l = i + 1; l < k; ++l) sum = sum - h[i][l] * y[l];
+            y[i] = sum / h[i][i];
+        }
+#pragma omp parallel for schedule(static)
+        for (i64 q = 0; q < (i64)n; ++q) { double t = xk[q]; for (u64 i = 0; i < k; ++i) t = t + y[i] * Z[i][q]; xk[q] = t; }
+        ko_spmv(A, xk.data(), tmp.data());
+        for (u64 i = 0; i < n; ++i) r[i] = b[i] - tmp[i];
+        const double rn_new = NRM(r.data());
+        if (rn_new < tol || converged) { stats->converged = 1; break; }
+        beta = rn_new;
+        for (u64 i = 0; i < n; ++i) V[0][i] = r[i] / beta;
+        std::fill(s.begin(), s.end(), 0.0);
+        s[0] = beta;
+    }
+    stats->final_residual = res_norm_outer;
+    stats->iterations = total;
+    std::memcpy(x, xk.data(), sizeof(double) * n);
+    return KO_OK;
+}
+
+// ----------------------------------------------------------------------------
 // BiCGStab
 //   variant 0 (LITERAL): src/solver/bicgstab.rs:69-293 — pc ignored (:70), absolute
 //       tolerance (:98,:189,:281), |.| < f64::EPSILON breakdown `break`s (:117,:161,:235,:285)

@@ -54,6 +54,17 @@ int main() {
         st = s2.solve(a, &ilu, b, x);
         REQUIRE(st.converged); REQUIRE(rel_error(x, 1.0) < 1e-10);
     }
+    {   // fgmres_equiv_to_gmres_on_fixed_pc (src/solver/fgmres.rs:531-551)
+        Csr m; m.n = 2; m.rp = {0, 2, 4}; m.ci = {0, 1, 0, 1}; m.v = {2.0, 1.0, 1.0, 3.0};
+        DeviceCsr a = DeviceCsr::from_csr(ctx, 2, 2, m.rp, m.ci, m.v);
+        std::vector<double> xt = {1.0, 2.0}, b(2), x(2, 0.0);
+        a.matvec(xt, b);
+        Jacobi pc; pc.setup(a);
+        FgmresSolver solver(1e-10, 100, 25);
+        SolveStats st = solver.solve_flex(a, &pc, b, x);
+        REQUIRE(st.converged);
+        for (int i = 0; i < 2; ++i) REQUIRE(std::fabs(x[i] - xt[i]) < 1e-6);
+    }
     {   // bicgstab_solves_well_conditioned_nonsym (src/solver/bicgstab.rs:303-328)
         Csr m; m.n = 3; m.rp = {0, 3, 6, 9}; m.ci = {0, 1, 2, 0, 1, 2, 0, 1, 2};
         for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) m.v.push_back(i == j ? 4.0 : double(i + 2 * j + 1));

@@ -62,6 +62,12 @@ def main():
                                  mode=mode, variant=o.GMRES_CGS2, nshards=world)
             assert (st.iterations, st.converged) == (so.iterations, bool(so.converged)), ("dist gmres", kind, mode, st.iterations, so.iterations)
             assert st.final_residual == so.final_residual and np.array_equal(x, xo[lo:hi]), "dist gmres"
+        # FGMRES (flexible, block-Jacobi ILU(0) as the fixed preconditioner)
+        x = np.zeros(hi - lo)
+        st = kb.FgmresSolver(1e-8, 3000, 10).solve_flex(A, kb.Ilu0().setup(A), b, x)
+        rc, xo, so = o.fgmres(Ao, o.OPc.ilu0(Ao, nblocks=world), bg, np.zeros(n), 10, 1e-8, 3000, nshards=world)
+        assert (st.iterations, st.converged) == (so.iterations, bool(so.converged)), ("dist fgmres", kind, st.iterations, so.iterations)
+        assert st.final_residual == so.final_residual and np.array_equal(x, xo[lo:hi]), "dist fgmres"
         pc = None
         A.close()
     dist.barrier()

@@ -80,6 +80,9 @@ def lib():
         L.ko_gmres.restype = C.c_int
         L.ko_gmres.argtypes = [C.POINTER(KoCsr), C.c_void_p, f64p, f64p, C.c_uint64, C.c_double, C.c_uint64,
                                C.c_int, C.c_int, C.c_uint64, C.POINTER(KoStats)]
+        L.ko_fgmres.restype = C.c_int
+        L.ko_fgmres.argtypes = [C.POINTER(KoCsr), C.c_void_p, f64p, f64p, C.c_uint64, C.c_double, C.c_uint64, C.c_uint64,
+                                C.POINTER(KoStats)]
         L.ko_bicgstab.restype = C.c_int
         L.ko_bicgstab.argtypes = [C.POINTER(KoCsr), C.c_void_p, f64p, f64p, C.c_double, C.c_uint64,
                                   C.c_int, C.c_uint64, C.POINTER(KoStats)]
@@ -307,6 +310,14 @@ def gmres(A, pc, b, x0, restart, tol, max_iters, mode=MODE_LEFT, variant=GMRES_L
     x = _vec(x0).copy()
     st = KoStats()
     rc = lib().ko_gmres(A.ptr(), _h(pc), _f(b), _f(x), restart, tol, max_iters, mode, variant, nshards, C.byref(st))
+    return rc, x, st
+
+
+def fgmres(A, pc, b, x0, restart, tol, max_iters, nshards=1):
+    b = _vec(b)
+    x = _vec(x0).copy()
+    st = KoStats()
+    rc = lib().ko_fgmres(A.ptr(), _h(pc), _f(b), _f(x), restart, tol, max_iters, nshards, C.byref(st))
     return rc, x, st
 
 

@@ -129,3 +129,39 @@ def test_gmres_limits(ctx):
         rc, xo, so = o.gmres(Ao, None, b, np.zeros(Ao.n), restart, tol, mi, mode=0, variant=o.GMRES_CGS2)
         assert (st.iterations, st.converged) == (so.iterations, bool(so.converged)), (restart, tol, mi)
         assert st.final_residual == so.final_residual and np.array_equal(x, xo)
+
+
+@pytest.mark.parametrize("kind,N,restart", [("convdiff2d", 24, 20), ("convdiff3d", 10, 8), ("poisson3d", 12, 30)])
+@pytest.mark.parametrize("pcname", [None, "jacobi", "ilu0"])
+def test_fgmres_bit_exact(ctx, kind, N, restart, pcname):
+    """FgmresSolver::solve_flex (src/solver/fgmres.rs:114-340, SURVEY 8f-2) incl. its literal quirks."""
+    import kryst_b200 as kb
+    A, Ao = _mk(kind, N, ctx)
+    b = o.spmv(Ao, np.ones(Ao.n))
+    pc = {None: None, "jacobi": kb.Jacobi, "ilu0": kb.Ilu0}[pcname]
+    pc = pc().setup(A) if pc else None
+    pco = {None: None, "jacobi": o.OPc.jacobi, "ilu0": o.OPc.ilu0}[pcname]
+    pco = pco(Ao) if pco else None
+    for tol, mi in ((1e-8, 3000), (1e-8, 7), (1e-3, 3000)):
+        x = np.zeros(Ao.n)
+        st = kb.FgmresSolver(tol, mi, restart).solve_flex(A, pc, b, x)
+        rc, xo, so = o.fgmres(Ao, pco, b, np.zeros(Ao.n), restart, tol, mi)
+        assert (st.iterations, st.converged) == (so.iterations, bool(so.converged)), (tol, mi, st.iterations, so.iterations)
+        assert st.final_residual == so.final_residual
+        assert np.array_equal(x, xo)
+
+
+def test_fgmres_reference_fixture_and_zero_rhs(ctx):
+    import kryst_b200 as kb
+    a = np.array([[2.0, 1.0], [1.0, 3.0]])                                   # fgmres.rs:492-551
+    Ao = o.OCsr.from_dense(a)
+    A = kb.DeviceCsr.from_csr(2, 2, Ao.row_ptr, Ao.col_idx, Ao.vals, ctx)
+    xt = np.array([1.0, 2.0])
+    x = np.zeros(2)
+    st = kb.FgmresSolver(1e-10, 100, 25).solve_flex(A, kb.Jacobi().setup(A), a @ xt, x)
+    assert st.converged and np.abs(x - xt).max() < 1e-6
+    x = np.zeros(2)
+    st = kb.FgmresSolver(1e-10, 100, 25).solve_flex(A, None, np.zeros(2), x)
+    assert st.converged and st.iterations == 0 and st.final_residual == 0.0
+    st = kb.KspContext(kb.SolverKind.Fgmres, A, tol=1e-10, max_it=100, restart=25, flex_pc=kb.Jacobi().setup(A)).solve_context(a @ xt, x)
+    assert st.converged and np.abs(x - xt).max() < 1e-6

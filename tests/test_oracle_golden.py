@@ -365,3 +365,16 @@ def test_block_jacobi_ilu0_blocks_match_separate_factorisations():
 def test_jacobi_zero_diagonal_rule():
     A = o.OCsr(3, 3, [0, 1, 2, 3], [0, 2, 2], [2.0, 1.0, 4.0])     # row 1 has no diagonal entry
     assert o.jacobi_inv_diag(A).tolist() == [0.5, 0.0, 0.25]          # jacobi.rs:69-71: zero -> 0
+
+
+def test_ref_fgmres_2x2_fixture():
+    """src/solver/fgmres.rs:531-551: [2 1; 1 3] x = b, x_true = [1, 2], Jacobi as (fixed) flexible preconditioner."""
+    a = np.array([[2.0, 1.0], [1.0, 3.0]])
+    A = o.OCsr.from_dense(a)
+    xt = np.array([1.0, 2.0])
+    rc, x, st = o.fgmres(A, o.OPc.jacobi(A), a @ xt, np.zeros(2), 25, 1e-10, 100)
+    assert rc == 0 and st.converged and np.abs(x - xt).max() < 1e-6
+    # literal quirk: the reported final_residual is the INITIAL residual norm (fgmres.rs:158,337)
+    assert st.final_residual == o.norm(a @ xt)
+    rc, x, st = o.fgmres(A, None, np.zeros(2), np.zeros(2), 25, 1e-10, 100)      # beta == 0 early return (fgmres.rs:152-154)
+    assert st.converged and st.iterations == 0 and st.final_residual == 0.0
