@@ -169,6 +169,8 @@ def main():
     ap.add_argument("--impl", default="kryst_b200")
     ap.add_argument("--workload", default="C4", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--pcg-variant", default="literal", choices=["literal", "fused"],
+                    help="literal = pcg.rs recurrences (the headline); fused = single-reduction extension (SURVEY 8(f3))")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -220,6 +222,9 @@ def main():
 
     solver_obj = kb.PcgSolver(TOL, MAX_ITERS)
     solver_obj.record_history = False
+    fused = args.pcg_variant == "fused"
+    if fused:
+        solver_obj.with_fused_reduction(True)
 
     def barrier():
         if world > 1:
@@ -294,7 +299,7 @@ def main():
         except Exception:
             traffic = None
     total_ms = sum(v["ms"] for v in prof.values())
-    iter_bytes = b_spmv + 88 * nloc          # PCG+Jacobi per iteration
+    iter_bytes = b_spmv + (96 if fused else 88) * nloc   # PCG+Jacobi per iteration (fused variant: DESIGN §4)
     roofline = {"bound": "hbm", "kernel": "kb_spmv_bulk<PcgAp> (bulk-async staged CSR SpMV fused with p.Ap)", "achieved": achieved, "peak": peak,
                 "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": b_spmv, "avg_launch_ms": spmv_ms,
@@ -312,7 +317,7 @@ def main():
             "warmup": W, "ms_per_step": 1e3 * sec / args.steps, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": args.workload + ": " + desc, "n": n, "nnz_rank0": nnz_local, "rtol": TOL,
-                       "iterations_per_solve": its // args.steps, "parallelism": "row-block x%d" % world,
+                       "iterations_per_solve": its // args.steps, "pcg_variant": args.pcg_variant, "parallelism": "row-block x%d" % world,
                        "l2": "inputs larger than L2 (per-iteration working set %.2f GB)" % (iter_bytes / 1e9)},
             "clocks": clocks,
             "e2e": {"value": its_e2e / sec_e2e, "unit": "it/s", "h2d_bytes_per_step": 16 * nloc, "d2h_bytes_per_step": 8 * nloc,

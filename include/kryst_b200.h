@@ -121,6 +121,8 @@ int kb_pc_ilu0_get_levels(kb_pc pc, int upper, uint64_t* nlevels, uint64_t* leve
 #define KB_FLAG_TEXTBOOK    2u    /* BiCGStab: Tier-T relative-tolerance, preconditioned variant  */
 #define KB_FLAG_PROFILE     4u    /* time every kernel class with CUDA events (no graph replay)   */
 #define KB_FLAG_NO_GRAPH    8u    /* plain launches instead of CUDA-graph replay                   */
+#define KB_FLAG_SINGLE_REDUCTION 16u /* PCG: Chronopoulos-Gear recurrences, ONE fused reduction (one all-reduce on
+                                        shards) per iteration - what pcg.rs:36-37's flag is named after; SURVEY 8(f3) */
 
 /* CgNormType (pcg.rs:25) */
 enum { KB_NORM_PRECONDITIONED = 0, KB_NORM_UNPRECONDITIONED = 1, KB_NORM_NATURAL = 2, KB_NORM_NONE = 3 };
@@ -128,7 +130,9 @@ enum { KB_NORM_PRECONDITIONED = 0, KB_NORM_UNPRECONDITIONED = 1, KB_NORM_NATURAL
 enum { KB_SIDE_NONE = 0, KB_SIDE_LEFT = 1, KB_SIDE_RIGHT = 2 };
 
 /* PcgSolver::new(tol,max_iters).with_norm(..).solve (pcg.rs:50-90,114-222).  history receives the
- * residual_history pushes (pcg.rs:146,199); x is written iff the call returns KB_OK.            */
+ * residual_history pushes (pcg.rs:146,199); x is written iff the call returns KB_OK.
+ * KB_FLAG_SINGLE_REDUCTION (Jacobi / no preconditioner): same conventions, r.u, (Au).u and the norm reduced together;
+ * not the reference's arithmetic (its flag is a no-op there) - checked against the oracle's restatement of the variant. */
 int kb_pcg_solve(kb_csr a, kb_pc pc, const double* b, double* x, double tol, uint64_t max_iters,
                  int norm_type, uint32_t flags, double* history, uint64_t hist_cap, uint64_t* hist_len,
                  kb_stats* stats);

@@ -123,12 +123,19 @@ class PcgSolver {            // src/solver/pcg.rs:31-222
 public:
     PcgSolver(double tol, size_t max_iters) : tol_(tol), max_iters_(max_iters) {}
     PcgSolver& with_norm(CgNormType t) { norm_ = t; return *this; }
+    // pcg.rs:66-80: the reference stores these three and its solve never changes arithmetic on them
+    // (single_reduction only swaps the Rayon dot for a serial loop, pcg.rs:151-160); same here.
+    PcgSolver& with_single_reduction(bool f) { single_reduction_ = f; return *this; }
+    // extension: true single-reduction (Chronopoulos-Gear) recurrences, KB_FLAG_SINGLE_REDUCTION
+    PcgSolver& with_fused_reduction(bool f = true) { fused_ = f; return *this; }
+    PcgSolver& with_radius(double r) { radius_ = r; has_radius_ = true; return *this; }
+    PcgSolver& with_obj_target(double t) { obj_target_ = t; has_obj_target_ = true; return *this; }
     std::vector<double> residual_history;
     SolveStats solve(const DeviceCsr& a, const Preconditioner* pc, const std::vector<double>& b, std::vector<double>& x) {
         std::vector<double> hist(max_iters_ + 1 < (1u << 20) ? max_iters_ + 1 : (1u << 20));
         uint64_t hl = 0;
         kb_stats st{};
-        int rc = kb_pcg_solve(a.handle(), pc ? pc->handle() : nullptr, b.data(), x.data(), tol_, max_iters_, static_cast<int>(norm_), 0,
+        int rc = kb_pcg_solve(a.handle(), pc ? pc->handle() : nullptr, b.data(), x.data(), tol_, max_iters_, static_cast<int>(norm_), fused_ ? KB_FLAG_SINGLE_REDUCTION : 0u,
                               hist.data(), hist.size(), &hl, &st);
         residual_history.insert(residual_history.end(), hist.begin(), hist.begin() + (hl < hist.size() ? hl : hist.size()));
         check(rc);
@@ -136,6 +143,8 @@ public:
     }
 private:
     double tol_; size_t max_iters_; CgNormType norm_ = CgNormType::Unpreconditioned;
+    bool single_reduction_ = false, fused_ = false, has_radius_ = false, has_obj_target_ = false;
+    double radius_ = 0.0, obj_target_ = 0.0;
 };
 class GmresSolver {          // src/solver/gmres.rs:38-402
 public:

@@ -20,7 +20,7 @@ import numpy as np
 from . import _ffi
 from ._ffi import KbStats, KbProfile, f64p, u64p
 
-KB_FLAG_DEVICE_PTRS, KB_FLAG_TEXTBOOK, KB_FLAG_PROFILE, KB_FLAG_NO_GRAPH = 1, 2, 4, 8
+KB_FLAG_DEVICE_PTRS, KB_FLAG_TEXTBOOK, KB_FLAG_PROFILE, KB_FLAG_NO_GRAPH, KB_FLAG_SINGLE_REDUCTION = 1, 2, 4, 8, 16
 
 
 # ---- KError (src/error.rs:6-19) ----------------------------------------------------------------
@@ -438,6 +438,10 @@ class PcgSolver(_SolverBase):
     def __init__(self, tol, max_iters):
         self.tol, self.max_iters = float(tol), int(max_iters)
         self.norm_type = CgNormType.Unpreconditioned
+        self.single_reduction = False
+        self.fused_reduction = False
+        self.radius = None
+        self.obj_target = None
         self.residual_history = []
         self.monitor = None
         self.record_history = True
@@ -453,6 +457,23 @@ class PcgSolver(_SolverBase):
         self.single_reduction = bool(flag)
         return self
 
+    def with_fused_reduction(self, flag=True):
+        """Extension: Chronopoulos-Gear recurrences, ONE reduction (one all-reduce on shards) per
+        iteration - what the reference's flag name promises but its code does not do.  Not the reference's
+        arithmetic: parity is checked against the oracle's restatement of this variant (Jacobi / no pc only)."""
+        self.fused_reduction = bool(flag)
+        return self
+
+    def with_radius(self, radius):
+        # pcg.rs:72-75 stores the value; solve (pcg.rs:114-222) never reads it - same here
+        self.radius = float(radius)
+        return self
+
+    def with_obj_target(self, obj):
+        # pcg.rs:77-80: stored, never read by solve
+        self.obj_target = float(obj)
+        return self
+
     def with_monitor(self, f):
         self.monitor = f
         return self
@@ -462,6 +483,8 @@ class PcgSolver(_SolverBase):
 
     def solve(self, a, pc, b, x):
         pb, px, flags, keep = self._solve_args(a, b, x)
+        if self.fused_reduction:
+            flags |= KB_FLAG_SINGLE_REDUCTION
         cap = 0
         hist = None
         if self.record_history or self.monitor:

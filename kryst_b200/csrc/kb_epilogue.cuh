@@ -7,6 +7,7 @@
 #pragma once
 #include <algorithm>
 #include <cstdlib>
+#include <type_traits>
 #include "kb_objects.h"
 #include "kb_spmv.cuh"
 #include "kb_spmv_bulk.cuh"
@@ -21,6 +22,11 @@ const KbP2PDev* kb_p2p_dev_ptr(kb_ctx_s* c);    // device-resident copy (kernel 
 //   single GPU            : thread 0 runs the scalar epilogue `fin`
 //   shard, peer path (p2p): NVLink all-reduce INSIDE this kernel, then `fin` — compute + collective in one launch
 //   shard, NCCL path      : store the local sums to `slots`; all-gather + epilogue follow as separate launches
+// Fin may define `__device__ void pre(double* ssum) const`: thread 0 of the last CTA calls it before the
+// all-reduce to append sums produced by an earlier kernel (single-reduction PCG), so they ride the same collective.
+template <class F, class = void> struct kb_has_pre : std::false_type {};
+template <class F> struct kb_has_pre<F, std::void_t<decltype(&F::pre)>> : std::true_type {};
+
 template <class Fin>
 struct KbFinish {
     Fin fin;
@@ -29,6 +35,10 @@ struct KbFinish {
     const KbP2PDev* p2p = nullptr;
     template <int BAR>
     __device__ void coop(double* ssum) const {
+        if constexpr (kb_has_pre<Fin>::value) {
+            if (threadIdx.x == 0) fin.pre(ssum);
+            kb_sync<BAR>();
+        }
         if (p2p) {
             kb_p2p_allreduce_block<BAR>(*p2p, ssum, nred);
             if (threadIdx.x == 0) fin(ssum);

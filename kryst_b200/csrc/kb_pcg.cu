@@ -165,6 +165,87 @@ struct PcgXpayOp : KbRedBase {        // K4: p = z + beta p  (pcg.rs:215-217)
     __device__ void finish_block(double*) const {}
 };
 
+// ---- single-reduction variant (Chronopoulos-Gear) ---------------------------------------
+// One iteration = two kernels and ONE reduction (one all-reduce on shards) instead of three kernels and two:
+//   S1  p = u + beta p ; s = w + beta s ; x += alpha p ; r -= alpha s ; u = D^-1 r ; local sums of r.u and the norm
+//   S2  w = A u  fused with  u.w ; its last CTA appends S1's local sums, all-reduces the three together and runs
+//       history push, Convergence::check, beta = g'/g, p.Ap = delta - beta g'/alpha (IndefiniteMatrix test), alpha
+// Bytes per iteration: B_spmv + 96 n (literal path: B_spmv + 88 n).
+struct PcgSrLocalFin {   // S1: keep this rank's sums for S2's collective
+    KbCtl* ctl;
+    __device__ void operator()(const double* s) const { ctl->sr_loc[0] = s[0]; ctl->sr_loc[1] = s[1]; }
+};
+struct PcgSrFin {        // S2 epilogue; s = {u.w, r.u, norm sum} (global)
+    KbCtl* ctl; int init;
+    __device__ void pre(double* s) const { s[1] = ctl->sr_loc[0]; s[2] = ctl->sr_loc[1]; }
+    __device__ void operator()(const double* s) const {
+        KbCtl* c = ctl;
+        const double delta = s[0], g_new = s[1];
+        const double res = (c->norm_type == KB_NORM_PRECONDITIONED || c->norm_type == KB_NORM_UNPRECONDITIONED) ? sqrt(s[2])
+                           : (c->norm_type == KB_NORM_NATURAL ? sqrt(fabs(g_new)) : 0.0);
+        if (c->hist_len < c->hist_cap) c->hist[c->hist_len] = res;
+        c->hist_len += 1;
+        c->res = res;
+        if (init) {
+            c->rz = g_new;
+            c->res0 = sqrt(fabs(g_new));
+            if (c->max_iters == 0) { c->res = c->res0; c->done = 1; return; }
+            if (delta <= 0.0) { c->status = KB_INDEFINITE_MATRIX; c->iter = 1; c->converged = 0; c->done = 1; return; }
+            c->pAp = delta; c->alpha = g_new / delta; c->beta = 0.0;
+            return;
+        }
+        const unsigned long long it = c->iter + 1;
+        c->iter = it;
+        const double rel = res / c->res0;                       // Convergence::check (convergence.rs:18-34)
+        if (rel <= c->tol || it >= c->max_iters) { c->converged = 1; c->done = 1; return; }
+        const double beta = g_new / c->rz;
+        if (beta < 0.0) { c->status = KB_INDEFINITE_PC; c->converged = 0; c->done = 1; return; }
+        const double pAp = delta - beta * g_new / c->alpha;
+        if (pAp <= 0.0) { c->status = KB_INDEFINITE_MATRIX; c->iter = it + 1; c->converged = 0; c->done = 1; return; }
+        c->pAp = pAp; c->beta = beta; c->alpha = g_new / pAp; c->rz = g_new;
+    }
+};
+template <class Fin, bool INIT>
+struct PcgSrOp : KbRedBase {          // S1 (INIT: u = D^-1 r ; p = s = 0 and the sums only)
+    static constexpr int NRED = 2;
+    double* x; double* p; double* r; double* s; const double* w; const double* inv; double* u; KbCtl* ctl; KbFinish<Fin> fin;
+    __device__ bool skip() const { return INIT ? false : ctl->done != 0; }
+    __device__ void pair(long long i, bool has1, double* red) const {
+        const int nt = ctl->norm_type;
+        if (has1) {
+            double2 rr = kb_ld2(r + i), uu;
+            if (!INIT) {
+                const double alpha = ctl->alpha, beta = ctl->beta;
+                double2 pp = kb_ld2(p + i), ss = kb_ld2(s + i), ww = kb_ld2(w + i), xx = kb_ld2(x + i), u0 = kb_ld2(u + i);
+                pp.x = u0.x + beta * pp.x; pp.y = u0.y + beta * pp.y;
+                ss.x = ww.x + beta * ss.x; ss.y = ww.y + beta * ss.y;
+                xx.x = xx.x + alpha * pp.x; xx.y = xx.y + alpha * pp.y;
+                rr.x = rr.x - alpha * ss.x; rr.y = rr.y - alpha * ss.y;
+                kb_st2(p + i, pp); kb_st2(s + i, ss); kb_st2(x + i, xx); kb_st2(r + i, rr);
+            } else { kb_st2(p + i, make_double2(0.0, 0.0)); kb_st2(s + i, make_double2(0.0, 0.0)); }
+            if (inv) { double2 d = kb_ld2(inv + i); uu = make_double2(d.x * rr.x, d.y * rr.y); } else uu = rr;
+            kb_st2(u + i, uu);
+            red[0] = rr.x * uu.x + rr.y * uu.y;
+            red[1] = nt == KB_NORM_PRECONDITIONED ? (uu.x * uu.x + uu.y * uu.y) : nt == KB_NORM_UNPRECONDITIONED ? (rr.x * rr.x + rr.y * rr.y) : 0.0;
+        } else {
+            double rr = r[i];
+            if (!INIT) {
+                const double alpha = ctl->alpha, beta = ctl->beta;
+                const double pp = u[i] + beta * p[i];
+                const double ss = w[i] + beta * s[i];
+                x[i] = x[i] + alpha * pp;
+                rr = rr - alpha * ss;
+                p[i] = pp; s[i] = ss; r[i] = rr;
+            } else { p[i] = 0.0; s[i] = 0.0; }
+            const double uu = inv ? inv[i] * rr : rr;
+            u[i] = uu;
+            red[0] = rr * uu + 0.0;
+            red[1] = nt == KB_NORM_PRECONDITIONED ? (uu * uu + 0.0) : nt == KB_NORM_UNPRECONDITIONED ? (rr * rr + 0.0) : 0.0;
+        }
+    }
+    __device__ void finish_block(double* sm) const { fin.template coop<0>(sm); }
+};
+
 // ---- workspace ----------------------------------------------------------------------------------
 struct KbPcgWs {
     uint64_t n = 0, nx = 0;
@@ -175,12 +256,13 @@ struct KbPcgWs {
     double* hist = nullptr; uint64_t hist_cap = 0;
     KbGraphCache gc;
     unsigned* mega_bar = nullptr;     // grid-barrier words of the persistent kernel
+    double *u_sr = nullptr, *s_sr = nullptr;   // single-reduction variant: u (SpMV operand, with ghost tail) and s = A p
 };
 void kb_pcg_ws_free(KbPcgWs* w) {
     if (!w) return;
     w->gc.reset();
     KB_FREE(w->x); KB_FREE(w->r); KB_FREE(w->z); KB_FREE(w->p); KB_FREE(w->ap); KB_FREE(w->b);
-    KB_FREE(w->partials); KB_FREE(w->slots); KB_FREE(w->ctl); KB_FREE(w->hist); KB_FREE(w->mega_bar);
+    KB_FREE(w->partials); KB_FREE(w->slots); KB_FREE(w->ctl); KB_FREE(w->hist); KB_FREE(w->mega_bar); KB_FREE(w->u_sr); KB_FREE(w->s_sr);
     if (w->h_ctl) cudaFreeHost(w->h_ctl);
     delete w;
 }
@@ -246,6 +328,29 @@ static int pcg_launch_iteration(kb_csr_s* A, const kb_pc_s* pc, KbPcgWs* w) {
     return KB_OK;
 }
 
+// single-reduction variant: S1 (INIT: setup form) then S2
+template <bool DIST, bool INIT>
+static int pcg_sr_launch(kb_csr_s* A, const kb_pc_s* pc, KbPcgWs* w) {
+    kb_ctx_s* c = A->ctx;
+    {
+        PcgSrOp<PcgSrLocalFin, INIT> op; op.n = (long long)w->n; op.partials = w->partials; op.pstride = w->pstride; op.ticket = c->ticket;
+        op.x = w->x; op.p = w->p; op.r = w->r; op.s = w->s_sr; op.w = w->ap; op.inv = pc ? pc->inv_diag : nullptr; op.u = w->u_sr; op.ctl = w->ctl;
+        op.fin = kb_make_fin(c, PcgSrLocalFin{w->ctl}, false, nullptr, 2);       // local sums only: no collective here
+        { KbLaunch L(c, INIT ? KB_K_INIT : KB_K_PCG_UPDATE); kb_tile_kernel<<<A->ntiles, KB_THREADS, 0, c->stream>>>(op); }
+        KB_CUDA(cudaGetLastError());
+    }
+    {
+        typedef KbSpmvEpi<PcgSrFin, true, false> Epi;
+        Epi epi; epi.ctl = INIT ? nullptr : w->ctl; epi.fin = kb_make_fin(c, PcgSrFin{w->ctl, INIT ? 1 : 0}, DIST, w->slots, 3);
+        KB_TRY((kb_launch_spmv<Epi, false>(A, w->u_sr, w->ap, nullptr, w->u_sr, w->partials, w->pstride, epi, DIST ? w->u_sr : nullptr)));
+        if (DIST) KB_TRY((kb_finish_dist<PcgSrFin>(c, PcgSrFin{w->ctl, INIT ? 1 : 0}, w->ctl, w->slots, 3)));
+    }
+    return KB_OK;
+}
+static int pcg_sr_iteration(kb_csr_s* A, const kb_pc_s* pc, KbPcgWs* w) {
+    return A->dist && A->ctx->size > 1 ? pcg_sr_launch<true, false>(A, pc, w) : pcg_sr_launch<false, false>(A, pc, w);
+}
+
 // whole solve in one cooperative launch (single GPU, bulk SpMV, Jacobi or no preconditioner)
 static int pcg_persistent(kb_csr_s* A, const kb_pc_s* pc, KbPcgWs* w) {
     kb_ctx_s* c = A->ctx;
@@ -295,6 +400,9 @@ extern "C" int kb_pcg_solve(kb_csr A, kb_pc pc, const double* b, double* x, doub
     if (hist_len) *hist_len = 0;
     if (A->n == 0 && !dist) { stats->converged = 0; return KB_OK; }
     const bool jacobi_like = !pc || pc->kind == KB_PC_JACOBI;
+    const bool single_red = (flags & KB_FLAG_SINGLE_REDUCTION) != 0;
+    if (single_red && !jacobi_like) { kb_set_error("single-reduction PCG supports Jacobi or no preconditioner"); return KB_UNSUPPORTED; }
+    if (single_red && !w->u_sr) { KB_TRY(kb_alloc(&w->u_sr, w->nx + 2)); KB_TRY(kb_alloc(&w->s_sr, w->n + 2)); }
 
     KB_TRY(kb_upload_or_alias(c, b, w->b, w->n, dev));
     KB_TRY(kb_upload_or_alias(c, x, w->x, w->n, dev));
@@ -315,7 +423,10 @@ extern "C" int kb_pcg_solve(kb_csr A, kb_pc pc, const double* b, double* x, doub
             KbSpmvEpi<PcgApFin, false, false> epi; epi.ctl = nullptr; epi.fin = kb_make_fin(c, PcgApFin{w->ctl}, false, nullptr, 0);
             if ((st = kb_launch_spmv<KbSpmvEpi<PcgApFin, false, false>, true>(A, w->x, w->r, w->b, nullptr, w->partials, w->pstride, epi, dist ? w->x : nullptr)) != KB_OK) break;
         }
-        if (!jacobi_like) {   // z = M^-1 r ; p = z ; rz ; norm
+        if (single_red) {     // u = D^-1 r ; w = A u ; gamma, delta, res0, first history entry
+            st = dist ? pcg_sr_launch<true, true>(A, pc, w) : pcg_sr_launch<false, true>(A, pc, w);
+            if (st != KB_OK) break;
+        } else if (!jacobi_like) {   // z = M^-1 r ; p = z ; rz ; norm
             if ((st = kb_pc_apply_dev(pc, w->r, w->z, nullptr, 0)) != KB_OK) break;
             PcgRzOp<PcgInitFin, true> op; op.n = (long long)w->n; op.partials = w->partials; op.pstride = w->pstride; op.ticket = c->ticket;
             op.r = w->r; op.z = w->z; op.p = w->p; op.ctl = w->ctl; op.fin = kb_make_fin(c, PcgInitFin{w->ctl}, dist, w->slots, 2);
@@ -334,7 +445,7 @@ extern "C" int kb_pcg_solve(kb_csr A, kb_pc pc, const double* b, double* x, doub
         // software grid barriers (3 per iteration over 296 CTAs, ~3 us each) cost more than the three kernel
         // boundaries of the graph path (C1: 22.3 vs 18.5 us per iteration), so it is opt-in.
         const int mega_env = getenv("KB_PCG_PERSISTENT") ? atoi(getenv("KB_PCG_PERSISTENT")) : 0;
-        const bool mega_ok = !dist && jacobi_like && A->kind == 2 && !A->prod && !profile && max_iters > 0;
+        const bool mega_ok = !single_red && !dist && jacobi_like && A->kind == 2 && !A->prod && !profile && max_iters > 0;
         const bool mega = mega_ok && mega_env != 0;
         if (mega) {
             if ((st = pcg_persistent(A, pc, w)) != KB_OK) break;
@@ -345,8 +456,9 @@ extern "C" int kb_pcg_solve(kb_csr A, kb_pc pc, const double* b, double* x, doub
         } else {
         // iterations per graph replay: ~2 ms of work, so the per-replay host poll is amortised
         const int B = kb_batch_size(12.0 * (double)A->nnz + 108.0 * (double)A->n, 3);
-        st = kb_run_iterations(c, &w->gc, (uint64_t)(uintptr_t)pc + 1, B, max_iters, use_graph, w->ctl, h,
-                               [&]() { return pcg_iteration(A, pc, w); });
+        // graph key: the captured launches differ between the two variants
+        st = kb_run_iterations(c, &w->gc, ((uint64_t)(uintptr_t)pc + 1) ^ (single_red ? 0x5352ull << 48 : 0ull), B, max_iters, use_graph, w->ctl, h,
+                               [&]() { return single_red ? pcg_sr_iteration(A, pc, w) : pcg_iteration(A, pc, w); });
         }
         if (st != KB_OK) break;
         if (cudaMemcpyAsync(h, w->ctl, offsetof(KbCtl, h), cudaMemcpyDeviceToHost, c->stream) != cudaSuccess ||

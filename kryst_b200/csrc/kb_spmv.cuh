@@ -168,7 +168,7 @@ __global__ void __launch_bounds__(KB_THREADS) kb_spmv_stream(KbSpmvArgs a, Epi e
             for (int d = 0; d < ND; ++d) a.partials[(size_t)d * a.pstride + tile] = out[d];
         }
         if (a.finalize && kb_arrive_last(a.ticket, gridDim.x, &sflag)) {
-            __shared__ double ssum[ND];
+            __shared__ double ssum[ND + 4];      // + room for sums appended by Fin::pre
 #pragma unroll
             for (int d = 0; d < ND; ++d) { double v = kb_level2(a.partials + (size_t)d * a.pstride, a.ntiles_total, s_red); if (tid == 0) ssum[d] = v; }
             __syncthreads();
@@ -233,7 +233,7 @@ __global__ void __launch_bounds__(KB_THREADS) kb_spmv_vector(KbSpmvArgs a, Epi e
             for (int d = 0; d < ND; ++d) a.partials[(size_t)d * a.pstride + tile] = out[d];
         }
         if (a.finalize && kb_arrive_last(a.ticket, gridDim.x, &sflag)) {
-            __shared__ double ssum[ND];
+            __shared__ double ssum[ND + 4];      // + room for sums appended by Fin::pre
 #pragma unroll
             for (int d = 0; d < ND; ++d) { double v = kb_level2(a.partials + (size_t)d * a.pstride, a.ntiles_total, s_red); if (tid == 0) ssum[d] = v; }
             __syncthreads();

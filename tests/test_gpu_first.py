@@ -69,6 +69,58 @@ def test_pcg_bit_exact(ctx, kind, N, use_pc, persistent, monkeypatch):
     assert np.array_equal(np.array(s.residual_history), ho)
 
 
+@pytest.mark.parametrize("kind,N", [("poisson2d", 16), ("poisson2d", 100), ("poisson3d", 24), ("varcoef27", 12)])
+@pytest.mark.parametrize("use_pc", [True, False])
+@pytest.mark.parametrize("norm", [0, 1, 2, 3])
+def test_pcg_fused_single_reduction_bit_exact(ctx, kind, N, use_pc, norm):
+    """Chronopoulos-Gear PCG (one fused reduction per iteration) vs the oracle's restatement."""
+    import kryst_b200 as kb
+    A, Ao = _mk(kind, N, ctx)
+    b = o.spmv(Ao, np.ones(Ao.n))
+    pc = kb.Jacobi().setup(A) if use_pc else None
+    x = np.zeros(Ao.n)
+    s = kb.PcgSolver(1e-8, 300).with_norm(norm).with_fused_reduction(True)
+    st = s.solve(A, pc, b, x)
+    rc, xo, so, ho = o.pcg_sr(Ao, o.OPc.jacobi(Ao) if use_pc else None, b, np.zeros(Ao.n), 1e-8, 300, norm_type=norm, hist_cap=301)
+    assert rc == 0
+    assert st.iterations == so.iterations and st.converged == bool(so.converged)
+    assert st.final_residual == so.final_residual
+    assert np.array_equal(x, xo)
+    assert np.array_equal(np.array(s.residual_history), ho)
+    if norm == 1 and so.iterations < 300:
+        # same Krylov method as the literal recurrences: iteration count within 2 % (here: identical or +-1)
+        rc, _, sl, _ = o.pcg(Ao, o.OPc.jacobi(Ao) if use_pc else None, b, np.zeros(Ao.n), 1e-8, 300)
+        assert abs(int(sl.iterations) - int(st.iterations)) <= max(1, int(0.02 * sl.iterations))
+
+
+def test_pcg_fused_single_reduction_edges(ctx):
+    import kryst_b200 as kb
+    A, Ao = _mk("poisson2d", 20, ctx)
+    b = o.spmv(Ao, np.ones(Ao.n))
+    # max_iters = 0: stats {0, res0, false}, x untouched but written back
+    x = np.full(Ao.n, 0.25)
+    st = kb.PcgSolver(1e-8, 0).with_fused_reduction().solve(A, None, b, x)
+    rc, xo, so, _ = o.pcg_sr(Ao, None, b, np.full(Ao.n, 0.25), 1e-8, 0)
+    assert (st.iterations, st.converged, st.final_residual) == (0, False, so.final_residual) and np.array_equal(x, xo)
+    # iteration cap hit: Convergence::check reports converged (F8), like the literal path
+    x = np.zeros(Ao.n)
+    st = kb.PcgSolver(1e-30, 7).with_fused_reduction().solve(A, None, b, x)
+    rc, xo, so, _ = o.pcg_sr(Ao, None, b, np.zeros(Ao.n), 1e-30, 7)
+    assert (st.iterations, st.converged) == (7, True) == (so.iterations, bool(so.converged)) and np.array_equal(x, xo)
+    # negative definite operator: IndefiniteMatrix, x not written
+    n, rp, ci, v = Ao.n, Ao.row_ptr, Ao.col_idx, -Ao.vals
+    An = kb.DeviceCsr.from_csr(n, n, rp, ci, v, ctx)
+    x = np.full(n, 3.0)
+    with pytest.raises(kb.IndefiniteMatrix):
+        kb.PcgSolver(1e-8, 50).with_fused_reduction().solve(An, None, b, x)
+    assert np.all(x == 3.0)
+    rc, _, so, _ = o.pcg_sr(o.OCsr(n, n, rp, ci, v), None, b, np.full(n, 3.0), 1e-8, 50)
+    assert rc == 3
+    # ILU(0) cannot be fused into the update sweep
+    with pytest.raises(kb.Unsupported):
+        kb.PcgSolver(1e-8, 50).with_fused_reduction().solve(A, kb.Ilu0().setup(A), b, np.zeros(n))
+
+
 def test_handle_lifetimes_any_destroy_order(built):
     """pc -> operator -> context references: destroying parents first must be safe."""
     import kryst_b200 as kb

@@ -258,6 +258,22 @@ def test_anchor_c1_909_iterations():
     assert st.iterations == c["c1_pcg_jacobi_b_1"]
 
 
+def test_single_reduction_pcg_matches_literal_iteration_counts():
+    """the Chronopoulos-Gear recurrences are the same Krylov method - iteration counts within 2 %
+    of the literal PCG (north_star's bar) and the same solution to solver tolerance; sharded sums stay reproducible."""
+    for kind, N in (("poisson2d", 128), ("poisson3d", 24), ("varcoef27", 12)):
+        A = o.stencil(kind, N)
+        b = o.spmv(A, np.ones(A.n))
+        for pc in (None, o.OPc.jacobi(A)):
+            rc1, x1, s1, _ = o.pcg(A, pc, b, np.zeros(A.n), 1e-8, 5000)
+            rc2, x2, s2, h2 = o.pcg_sr(A, pc, b, np.zeros(A.n), 1e-8, 5000, hist_cap=5001)
+            assert rc1 == 0 and rc2 == 0 and s2.converged
+            assert abs(int(s1.iterations) - int(s2.iterations)) <= max(1, int(0.02 * s1.iterations))
+            assert np.abs(x2 - x1).max() < 1e-6 and len(h2) == s2.iterations + 1
+            rc3, x3, s3, _ = o.pcg_sr(A, pc, b, np.zeros(A.n), 1e-8, 5000, nshards=3)
+            assert rc3 == 0 and abs(int(s3.iterations) - int(s2.iterations)) <= 1
+
+
 def test_anchor_c2_small():
     c = KA["survey_anchors"]
     A = o.stencil("convdiff2d", 48)
