@@ -116,6 +116,15 @@ def test_pcg_fused_single_reduction_edges(ctx):
     assert np.all(x == 3.0)
     rc, _, so, _ = o.pcg_sr(o.OCsr(n, n, rp, ci, v), None, b, np.full(n, 3.0), 1e-8, 50)
     assert rc == 3
+    # nonsymmetric operator: the recurrence p.Ap = delta - beta*gamma/alpha goes non-positive mid-solve; same
+    # iteration, residual and error as the oracle
+    Ac, Aco = _mk("convdiff2d", 20, ctx)
+    bc = o.spmv(Aco, np.ones(Aco.n))
+    sv = kb.PcgSolver(1e-8, 3000).with_fused_reduction()
+    with pytest.raises(kb.IndefiniteMatrix):
+        sv.solve(Ac, kb.Jacobi().setup(Ac), bc, np.zeros(Aco.n))
+    rc, _, so, _ = o.pcg_sr(Aco, o.OPc.jacobi(Aco), bc, np.zeros(Aco.n), 1e-8, 3000)
+    assert rc == 3 and (sv.last_stats.iterations, sv.last_stats.final_residual) == (so.iterations, so.final_residual)
     # ILU(0) cannot be fused into the update sweep
     with pytest.raises(kb.Unsupported):
         kb.PcgSolver(1e-8, 50).with_fused_reduction().solve(A, kb.Ilu0().setup(A), b, np.zeros(n))
