@@ -98,7 +98,13 @@ int kb_csr_matvec_device(kb_csr a, const double* d_x, double* d_y); /* device po
 /* partition maps for parity tests (integers, bit-exact vs the oracle) */
 uint64_t kb_csr_num_ghosts(kb_csr a);
 int kb_csr_get_ghosts(kb_csr a, uint64_t* ghosts_global);
-int kb_csr_spmv_kernel_kind(kb_csr a);                 /* 0 = CSR-stream (thread/row from smem), 1 = vector-per-row */
+int kb_csr_spmv_kernel_kind(kb_csr a);                 /* 0 = CSR-stream (thread/row from smem), 1 = vector-per-row, 2 = bulk-async staged */
+/* SubmatrixExtract::submatrix(&self, indices) (src/core/traits.rs; impl src/matrix/sparse.rs:72-93), the call
+ * AdditiveSchwarz::setup makes per subdomain (src/preconditioner/asm.rs:58-65): out[i][j] = a[indices[i]][indices[j]]
+ * for any index order (repeats allowed), stored zeros dropped, built on the device.  Single-GPU operators only.   */
+int kb_csr_submatrix(kb_csr a, const uint64_t* indices, uint64_t k, kb_csr* out);
+/* read the operator back as the arrays CsrMatrix::from_csr takes (sparse.rs:26-34): row_ptr[nrows+1], col_idx[nnz], vals[nnz] */
+int kb_csr_download(kb_csr a, uint64_t* row_ptr, uint64_t* col_idx, double* vals);
 
 /* ---- InnerProduct (wrappers.rs:90-128): canonical-tree dot / norm on device ------------ */
 int kb_dot(kb_ctx ctx, uint64_t n, const double* x, const double* y, double* out);   /* host slices */

@@ -79,6 +79,17 @@ public:
     DeviceCsr& operator=(DeviceCsr&& o) noexcept { if (this != &o) { kb_csr_destroy(h_); h_ = o.h_; o.h_ = nullptr; } return *this; }
     ~DeviceCsr() { kb_csr_destroy(h_); }
     void matvec(const std::vector<double>& x, std::vector<double>& y) const { check(kb_csr_matvec(h_, x.data(), y.data())); }   // MatVec::matvec
+    // SubmatrixExtract::submatrix (sparse.rs:72-93; used by AdditiveSchwarz::setup, asm.rs:58-65)
+    DeviceCsr submatrix(const std::vector<uint64_t>& indices) const {
+        DeviceCsr s;
+        check(kb_csr_submatrix(h_, indices.data(), indices.size(), &s.h_));
+        return s;
+    }
+    // the arrays CsrMatrix::from_csr takes, read back from the device
+    void to_csr(std::vector<uint64_t>& row_ptr, std::vector<uint64_t>& col_idx, std::vector<double>& values) const {
+        row_ptr.assign(nrows() + 1, 0); col_idx.assign(kb_csr_nnz(h_), 0); values.assign(kb_csr_nnz(h_), 0.0);
+        check(kb_csr_download(h_, row_ptr.data(), col_idx.data(), values.data()));
+    }
     size_t nrows() const { return kb_csr_nrows(h_); }     // Indexing::nrows / MatShape::nrows
     size_t ncols() const { return kb_csr_ncols(h_); }     // MatShape::ncols
     kb_csr handle() const { return h_; }

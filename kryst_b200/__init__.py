@@ -9,10 +9,11 @@ from .api import (BiCgStabSolver, BlockJacobiIlu0, CgNormType, Context, DeviceCs
                   IndefiniteMatrix, IndefinitePreconditioner, Jacobi, KError, PcgSolver, Preconditioning, SolveError,
                   SolveStats, Unsupported, ZeroPivot, default_context, partition_range)
 from . import stencils
+from . import mmio
 from .context import KspContext, SolverKind
 
 _ffi.lib()   # fail loudly at import time if the CUDA library is missing
 
 __all__ = ["BiCgStabSolver", "BlockJacobiIlu0", "CgNormType", "Context", "DeviceCsr", "FactorError", "FgmresSolver", "GmresSolver", "Ilu0",
            "IndefiniteMatrix", "IndefinitePreconditioner", "Jacobi", "KError", "PcgSolver", "Preconditioning", "SolveError",
-           "SolveStats", "Unsupported", "ZeroPivot", "default_context", "partition_range", "stencils", "KspContext", "SolverKind"]
+           "SolveStats", "Unsupported", "ZeroPivot", "default_context", "partition_range", "stencils", "mmio", "KspContext", "SolverKind"]

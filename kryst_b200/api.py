@@ -285,6 +285,22 @@ class DeviceCsr:
         _check(_ffi.lib().kb_csr_get_ghosts(self._h, _u(g)))
         return g
 
+    def submatrix(self, indices):
+        """SubmatrixExtract::submatrix(&self, indices) (sparse.rs:72-93): out[i][j] = a[indices[i]][indices[j]],
+        stored zeros dropped, built on the device - what AdditiveSchwarz::setup calls per subdomain (asm.rs:58-65)."""
+        idx = np.ascontiguousarray(indices, dtype=np.uint64)
+        h = C.c_void_p()
+        _check(_ffi.lib().kb_csr_submatrix(self._h, _u(idx), int(idx.size), C.byref(h)))
+        return DeviceCsr(h, self.ctx)
+
+    def to_csr(self):
+        """(row_ptr, col_idx, values) as CsrMatrix::from_csr takes them (sparse.rs:26-34), read back from the device."""
+        rp = np.zeros(self.nrows() + 1, dtype=np.uint64)
+        ci = np.zeros(self.nnz(), dtype=np.uint64)
+        v = np.zeros(self.nnz(), dtype=np.float64)
+        _check(_ffi.lib().kb_csr_download(self._h, _u(rp), _u(ci), _f(v)))
+        return rp, ci, v
+
     def matvec(self, x, y):
         """y <- A x  (MatVec::matvec)."""
         nx = self.nrows() if self.ctx.size() > 1 else self.ncols()

@@ -217,13 +217,9 @@ static int build_chunk_table(kb_csr_s* A) {
     return KB_OK;
 }
 
-static int csr_create_common(kb_ctx c, uint64_t nrows, uint64_t ncols_global, bool dist, uint64_t n_global, uint64_t lo,
-                             uint64_t hi, const uint64_t* row_ptr, const uint64_t* col_idx, const double* vals, kb_csr* out) {
+// allocate the device arrays of an operator (padded tails zeroed); the caller fills row_ptr / col / vals
+int kb_csr_alloc(kb_ctx c, uint64_t nrows, uint64_t ncols_global, uint64_t nnz, kb_csr_s** out) {
     *out = nullptr;
-    if (!c) { kb_set_error("null context"); return KB_SOLVE_ERROR; }
-    KB_CUDA(cudaSetDevice(c->device));
-    if (!row_ptr || (nrows > 0 && row_ptr[nrows] > 0 && (!col_idx || !vals))) { kb_set_error("null CSR array"); return KB_SOLVE_ERROR; }
-    const uint64_t nnz = nrows ? row_ptr[nrows] : 0;
     if (nrows >= (1ull << 31) - 2 * KB_TILE || nnz >= (1ull << 31) - 16 || ncols_global >= (1ull << 31) - 2 * KB_TILE) {
         kb_set_error("matrix shard too large for i32 device indices (rows %llu, nnz %llu): partition it across more GPUs",
                      (unsigned long long)nrows, (unsigned long long)nnz);
@@ -232,28 +228,33 @@ static int csr_create_common(kb_ctx c, uint64_t nrows, uint64_t ncols_global, bo
     kb_csr_s* A = new kb_csr_s;
     A->ctx = c; A->n = nrows; A->ncols_global = ncols_global; A->ncols_local = ncols_global; A->nnz = nnz;
     A->ntiles = kb_num_tiles(nrows);
-    A->dist = dist; A->n_global = n_global; A->row_lo = lo; A->row_hi = hi;
+    A->dist = false; A->n_global = nrows; A->row_lo = 0; A->row_hi = nrows;
+    c->refs++;
     int st = KB_OK;
-    int* d_err = nullptr;
-    unsigned long long* d_stats = nullptr;   // [0] first_bad, [1..6] hist, [7] maxlen
     do {
         if ((st = kb_alloc(&A->row_ptr, nrows + 1 + 8)) != KB_OK) break;
         cudaMemsetAsync(A->row_ptr, 0, (nrows + 9) * sizeof(int), c->stream);
         if ((st = kb_alloc(&A->col, nnz + 8)) != KB_OK) break;
         if ((st = kb_alloc(&A->vals, nnz + 8)) != KB_OK) break;
-        if ((st = kb_alloc(&d_err, 1)) != KB_OK) break;
-        if ((st = kb_alloc(&d_stats, 8)) != KB_OK) break;
         cudaMemsetAsync(A->col + nnz, 0, 8 * sizeof(int), c->stream);
         cudaMemsetAsync(A->vals + nnz, 0, 8 * sizeof(double), c->stream);
-        cudaMemsetAsync(d_err, 0, sizeof(int), c->stream);
+    } while (0);
+    if (st != KB_OK) { kb_csr_destroy(A); return st; }
+    *out = A;
+    return KB_OK;
+}
+
+// validate the device arrays (new_checked rules), row-length histogram -> kernel choice, shard maps, chunk table.
+// d_err (optional): device flag raised by the index-narrowing upload.
+int kb_csr_finalize(kb_csr_s* A, const int* d_err) {
+    kb_ctx_s* c = A->ctx;
+    const uint64_t nrows = A->n, nnz = A->nnz;
+    unsigned long long* d_stats = nullptr;   // [0] first_bad, [1..6] hist, [7] maxlen
+    int st = KB_OK;
+    do {
+        if ((st = kb_alloc(&d_stats, 8)) != KB_OK) break;
         cudaMemsetAsync(d_stats, 0, 8 * sizeof(unsigned long long), c->stream);
         cudaMemsetAsync(d_stats, 0xFF, sizeof(unsigned long long), c->stream);
-        if (nrows == 0) { cudaMemsetAsync(A->row_ptr, 0, sizeof(int), c->stream); }
-        if ((st = upload_narrow(c, row_ptr, A->row_ptr, nrows + 1, nnz + 1, d_err)) != KB_OK) break;
-        if ((st = upload_narrow(c, col_idx, A->col, nnz, ncols_global, d_err)) != KB_OK) break;
-        if (nnz && cudaMemcpyAsync(A->vals, vals, nnz * sizeof(double), cudaMemcpyHostToDevice, c->stream) != cudaSuccess) {
-            kb_set_error("H2D copy of values failed"); st = KB_SOLVE_ERROR; break;
-        }
         if (nrows) {
             KbLaunch L(c, KB_K_OTHER);
             k_validate_hist<<<(unsigned)((nrows + 255) / 256), 256, 0, c->stream>>>(A->row_ptr, A->col, (int)nrows, (long long)nnz,
@@ -261,7 +262,7 @@ static int csr_create_common(kb_ctx c, uint64_t nrows, uint64_t ncols_global, bo
         }
         int h_err = 0;
         unsigned long long h_stats[8];
-        if (cudaMemcpyAsync(&h_err, d_err, sizeof(int), cudaMemcpyDeviceToHost, c->stream) != cudaSuccess ||
+        if ((d_err && cudaMemcpyAsync(&h_err, d_err, sizeof(int), cudaMemcpyDeviceToHost, c->stream) != cudaSuccess) ||
             cudaMemcpyAsync(h_stats, d_stats, sizeof(h_stats), cudaMemcpyDeviceToHost, c->stream) != cudaSuccess ||
             cudaStreamSynchronize(c->stream) != cudaSuccess) {
             kb_set_error("CSR validation failed to run: %s", cudaGetErrorString(cudaGetLastError())); st = KB_SOLVE_ERROR; break;
@@ -281,12 +282,36 @@ static int csr_create_common(kb_ctx c, uint64_t nrows, uint64_t ncols_global, bo
             double mean = (double)nnz / (double)nrows;
             A->vec = mean > 256 ? 32 : mean > 128 ? 16 : 8;
         }
-        if (dist && (st = kb_csr_build_dist(A)) != KB_OK) break;
+        if (A->dist && (st = kb_csr_build_dist(A)) != KB_OK) break;
         if (A->kind == 0 && nrows && (st = build_chunk_table(A)) != KB_OK) break;
     } while (0);
-    if (d_err) cudaFree(d_err);
     if (d_stats) cudaFree(d_stats);
-    c->refs++;
+    return st;
+}
+
+static int csr_create_common(kb_ctx c, uint64_t nrows, uint64_t ncols_global, bool dist, uint64_t n_global, uint64_t lo,
+                             uint64_t hi, const uint64_t* row_ptr, const uint64_t* col_idx, const double* vals, kb_csr* out) {
+    *out = nullptr;
+    if (!c) { kb_set_error("null context"); return KB_SOLVE_ERROR; }
+    KB_CUDA(cudaSetDevice(c->device));
+    if (!row_ptr || (nrows > 0 && row_ptr[nrows] > 0 && (!col_idx || !vals))) { kb_set_error("null CSR array"); return KB_SOLVE_ERROR; }
+    const uint64_t nnz = nrows ? row_ptr[nrows] : 0;
+    kb_csr_s* A = nullptr;
+    KB_TRY(kb_csr_alloc(c, nrows, ncols_global, nnz, &A));
+    A->dist = dist; A->n_global = n_global; A->row_lo = lo; A->row_hi = hi;
+    int st = KB_OK;
+    int* d_err = nullptr;
+    do {
+        if ((st = kb_alloc(&d_err, 1)) != KB_OK) break;
+        cudaMemsetAsync(d_err, 0, sizeof(int), c->stream);
+        if ((st = upload_narrow(c, row_ptr, A->row_ptr, nrows + 1, nnz + 1, d_err)) != KB_OK) break;
+        if ((st = upload_narrow(c, col_idx, A->col, nnz, ncols_global, d_err)) != KB_OK) break;
+        if (nnz && cudaMemcpyAsync(A->vals, vals, nnz * sizeof(double), cudaMemcpyHostToDevice, c->stream) != cudaSuccess) {
+            kb_set_error("H2D copy of values failed"); st = KB_SOLVE_ERROR; break;
+        }
+        st = kb_csr_finalize(A, d_err);
+    } while (0);
+    if (d_err) cudaFree(d_err);
     if (st != KB_OK) { kb_csr_destroy(A); return st; }
     *out = A;
     return KB_OK;

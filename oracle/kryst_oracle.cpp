@@ -485,6 +485,40 @@ int ko_pcg(const ko_csr* A, const ko_pc* pc, const double* b, double* x, double 
 }
 
 // ----------------------------------------------------------------------------
+// SubmatrixExtract::submatrix (src/matrix/sparse.rs:72-93): sub[i][j] = A[indices[i]][indices[j]] for i, j in
+// index-list order, entries equal to zero dropped (:84), columns ascending per row (:82 `for j in 0..n`).
+// Restated without the dense detour: per output row, every stored non-zero (g, v) of row indices[i] lands in each
+// local column j with indices[j] == g.  Two-call protocol: col_idx == NULL returns the count only.
+// Returns nnz of the sub-matrix, or (u64)-1 when an index is out of range (the reference would panic).
+// ----------------------------------------------------------------------------
+u64 ko_submatrix(const ko_csr* A, const u64* indices, u64 k, u64* row_ptr, u64* col_idx, double* vals) {
+    const u64 limit = A->n < A->ncols ? A->n : A->ncols;
+    for (u64 j = 0; j < k; ++j) if (indices[j] >= limit) return ~(u64)0;
+    std::vector<std::pair<u64, u64>> pairs(k);
+    for (u64 j = 0; j < k; ++j) pairs[j] = {indices[j], j};
+    std::sort(pairs.begin(), pairs.end());
+    u64 nnz = 0;
+    std::vector<std::pair<u64, double>> rowbuf;
+    row_ptr[0] = 0;
+    for (u64 i = 0; i < k; ++i) {
+        rowbuf.clear();
+        const u64 row = indices[i];
+        for (u64 p = A->row_ptr[row]; p < A->row_ptr[row + 1]; ++p) {
+            const double v = A->vals[p];
+            if (!(v != 0.0)) continue;
+            const u64 g = A->col_idx[p];
+            auto it = std::lower_bound(pairs.begin(), pairs.end(), std::make_pair(g, (u64)0));
+            for (; it != pairs.end() && it->first == g; ++it) rowbuf.push_back({it->second, v});
+        }
+        std::sort(rowbuf.begin(), rowbuf.end(), [](const std::pair<u64, double>& a, const std::pair<u64, double>& b) { return a.first < b.first; });
+        if (col_idx) for (u64 t = 0; t < rowbuf.size(); ++t) { col_idx[nnz + t] = rowbuf[t].first; vals[nnz + t] = rowbuf[t].second; }
+        nnz += rowbuf.size();
+        row_ptr[i + 1] = nnz;
+    }
+    return nnz;
+}
+
+// ----------------------------------------------------------------------------
 // PCG with ONE fused reduction per iteration (Chronopoulos-Gear recurrences) — SURVEY 8(f3), Tier T.
 // The reference's `single_reduction` flag (pcg.rs:36-37,66-69) only swaps the Rayon dot for a serial loop
 // (pcg.rs:151-160); this is what the flag's name promises: gamma = r.u, delta = (A u).u and the norm are reduced

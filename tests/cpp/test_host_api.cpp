@@ -65,6 +65,24 @@ int main() {
         REQUIRE(st.converged);
         for (int i = 0; i < 2; ++i) REQUIRE(std::fabs(x[i] - xt[i]) < 1e-6);
     }
+    {   // SubmatrixExtract::submatrix (src/matrix/sparse.rs:72-93) + read-back; fused single-reduction PCG
+        Csr m; m.n = 4; m.rp = {0, 2, 5, 8, 10}; m.ci = {0, 1, 0, 1, 2, 1, 2, 3, 2, 3};
+        m.v = {4, -1, -1, 4, -1, -1, 4, -1, -1, 4};
+        DeviceCsr a = DeviceCsr::from_csr(ctx, 4, 4, m.rp, m.ci, m.v);
+        DeviceCsr s = a.submatrix({3, 1, 2});
+        std::vector<uint64_t> rp, ci; std::vector<double> v;
+        s.to_csr(rp, ci, v);
+        REQUIRE((rp == std::vector<uint64_t>{0, 2, 4, 7}));
+        REQUIRE((ci == std::vector<uint64_t>{0, 2, 1, 2, 0, 1, 2}));
+        REQUIRE((v == std::vector<double>{4, -1, 4, -1, -1, -1, 4}));
+        std::vector<double> xt = {1, 2, 3, 4}, b(4), x(4, 0.0);
+        a.matvec(xt, b);
+        Jacobi pc; pc.setup(a);
+        PcgSolver solver(1e-12, 50);
+        SolveStats st = solver.with_fused_reduction(true).solve(a, &pc, b, x);
+        REQUIRE(st.converged);
+        for (int i = 0; i < 4; ++i) REQUIRE(std::fabs(x[i] - xt[i]) < 1e-9);
+    }
     {   // bicgstab_solves_well_conditioned_nonsym (src/solver/bicgstab.rs:303-328)
         Csr m; m.n = 3; m.rp = {0, 3, 6, 9}; m.ci = {0, 1, 2, 0, 1, 2, 0, 1, 2};
         for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) m.v.push_back(i == j ? 4.0 : double(i + 2 * j + 1));

@@ -89,6 +89,8 @@ def lib():
         L.ko_bicgstab.restype = C.c_int
         L.ko_bicgstab.argtypes = [C.POINTER(KoCsr), C.c_void_p, f64p, f64p, C.c_double, C.c_uint64,
                                   C.c_int, C.c_uint64, C.POINTER(KoStats)]
+        L.ko_submatrix.restype = C.c_uint64
+        L.ko_submatrix.argtypes = [C.POINTER(KoCsr), u64p, C.c_uint64, u64p, u64p, f64p]
         L.ko_partition_range.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64, u64p, u64p]
         L.ko_ghost_list.restype = C.c_uint64
         L.ko_ghost_list.argtypes = [C.POINTER(KoCsr), C.c_uint64, C.c_uint64, u64p]
@@ -302,6 +304,19 @@ def pcg(A, pc, b, x0, tol, max_iters, norm_type=1, nshards=1, hist_cap=0):
     rc = lib().ko_pcg(A.ptr(), _h(pc), _f(b), _f(x), tol, max_iters, norm_type, nshards,
                       _f(hist), hist_cap, C.byref(hl), C.byref(st))
     return rc, x, st, hist[:min(int(hl.value), hist_cap)]
+
+
+def submatrix(A, indices):
+    """SubmatrixExtract::submatrix (sparse.rs:72-93) -> OCsr; raises IndexError when an index is out of range."""
+    idx = np.ascontiguousarray(indices, dtype=np.uint64)
+    rp = np.zeros(idx.size + 1, dtype=np.uint64)
+    nnz = int(lib().ko_submatrix(A.ptr(), _u(idx), idx.size, _u(rp), None, None))
+    if nnz == 2 ** 64 - 1:
+        raise IndexError("submatrix index out of range")
+    ci = np.zeros(nnz, dtype=np.uint64)
+    v = np.zeros(nnz, dtype=np.float64)
+    lib().ko_submatrix(A.ptr(), _u(idx), idx.size, _u(rp), _u(ci), _f(v))
+    return OCsr(idx.size, idx.size, rp, ci, v)
 
 
 def pcg_sr(A, pc, b, x0, tol, max_iters, norm_type=1, nshards=1, hist_cap=0):
