@@ -12,6 +12,8 @@
  *   AdditiveSchwarz (overlap 0, chunk partition)     src/preconditioner/asm.rs:34-57
  *   LinearSolver<M,V>::solve(&mut self,&A,pc,&b,&mut x) -> Result<SolveStats,KError>   src/solver/mod.rs:30-52
  *   PcgSolver / GmresSolver / BiCgStabSolver         src/solver/pcg.rs:114, gmres.rs:216, bicgstab.rs:69
+ *   FgmresSolver::solve_flex                         src/solver/fgmres.rs:114-340
+ *   SubmatrixExtract::submatrix                      src/matrix/sparse.rs:72-93 (used by asm.rs:58-65)
  *   SolveStats{iterations,final_residual,converged}  src/utils/convergence.rs:9-14
  *   KError                                           src/error.rs:6-19
  *   Comm{rank,size,barrier,all_reduce}               src/parallel/mod.rs:4-35
