@@ -303,6 +303,7 @@ extern "C" int kb_bicgstab_solve(kb_csr A, kb_pc pc, const double* b, double* x,
         stats->iterations = h->iter; stats->final_residual = h->res; stats->converged = h->converged; stats->breakdown = h->breakdown;
         st = h->status;
         if (dist && kb_p2p_error(c)) { kb_set_error("%s: peer-memory collective timed out", "bicgstab"); st = KB_SOLVE_ERROR; break; }
+        if (pc && kb_ilu0_error(const_cast<kb_pc_s*>(pc))) { kb_set_error("%s: a triangular-solve dependency wait timed out", "bicgstab"); st = KB_SOLVE_ERROR; break; }
         if (st == KB_OK) {
             if (cudaMemcpyAsync(x, w->x, w->n * sizeof(double), dev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, c->stream) != cudaSuccess ||
                 cudaStreamSynchronize(c->stream) != cudaSuccess) { kb_set_error("bicgstab: copy-out of x failed"); st = KB_SOLVE_ERROR; }

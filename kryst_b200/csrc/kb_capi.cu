@@ -510,6 +510,7 @@ extern "C" int kb_pc_apply_device(kb_pc pc, const double* d_r, double* d_z) {
     KB_CUDA(cudaSetDevice(pc->a->ctx->device));
     KB_TRY(kb_pc_apply_dev(pc, d_r, d_z));
     KB_CUDA(cudaStreamSynchronize(pc->a->ctx->stream));
+    if (kb_ilu0_error(pc)) { kb_set_error("ilu0: a triangular-solve dependency wait timed out"); return KB_SOLVE_ERROR; }
     return KB_OK;
 }
 extern "C" int kb_pc_apply(kb_pc pc, const double* r, double* z) {
@@ -522,6 +523,7 @@ extern "C" int kb_pc_apply(kb_pc pc, const double* r, double* z) {
     KB_TRY(kb_pc_apply_dev(pc, pc->r_tmp, pc->z_tmp));
     KB_CUDA(cudaMemcpyAsync(z, pc->z_tmp, A->n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     KB_CUDA(cudaStreamSynchronize(c->stream));
+    if (kb_ilu0_error(pc)) { kb_set_error("ilu0: a triangular-solve dependency wait timed out"); return KB_SOLVE_ERROR; }
     return KB_OK;
 }
 extern "C" int kb_pc_destroy(kb_pc pc) {

@@ -601,6 +601,7 @@ static int gmres_solve_impl(kb_csr A, kb_pc pc, const double* b, double* x, uint
         stats->iterations = h->iter; stats->final_residual = flex ? h->res0_true : h->res; stats->converged = h->converged; stats->breakdown = h->happy;
         st = h->status;
         if (dist && kb_p2p_error(c)) { kb_set_error("%s: peer-memory collective timed out", "gmres"); st = KB_SOLVE_ERROR; break; }
+        if (pc && kb_ilu0_error(const_cast<kb_pc_s*>(pc))) { kb_set_error("%s: a triangular-solve dependency wait timed out", "gmres"); st = KB_SOLVE_ERROR; break; }
         if (st == KB_OK) {
             if (cudaMemcpyAsync(x, w->x, w->n * sizeof(double), dev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, c->stream) != cudaSuccess ||
                 cudaStreamSynchronize(c->stream) != cudaSuccess) { kb_set_error("gmres: copy-out of x failed"); st = KB_SOLVE_ERROR; }

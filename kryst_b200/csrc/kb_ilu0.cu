@@ -331,6 +331,10 @@ __global__ void __launch_bounds__(KB_THREADS) kb_trsv_persistent(KbTrsvEll a) {
 }
 
 // ---- host ---------------------------------------------------------------------------------------------
+struct KbTileSolve;                                  // kb_trsv_tiles.cu: block-wavefront solves for grid-structured factors
+int kb_tiles_build(kb_pc_s* pc, unsigned* d_err, KbTileSolve** out);
+int kb_tiles_apply(kb_pc_s* pc, KbTileSolve* t, const double* d_r, double* d_z, const KbCtl* skip_ctl, int skip_mask);
+void kb_tiles_free(KbTileSolve* t);
 struct KbIluExtra {
     int* level[2] = {nullptr, nullptr};
     unsigned* counters = nullptr;
@@ -348,6 +352,7 @@ struct KbIluExtra {
     int* done[2] = {nullptr, nullptr};
     int gate = 3;
     int kind = 1;            // 1 persistent chunk-ELL solve, 0 ticketed CSR solve
+    KbTileSolve* tiles = nullptr;   // non-null: the factor's pattern is a 5-/7-point box grid -> block-wavefront solves
     int sleep_ns = 0;
 };
 static KbIluExtra* extra_of(kb_pc_s* pc) { return reinterpret_cast<KbIluExtra*>(pc->extra); }
@@ -357,6 +362,7 @@ void kb_ilu0_free(kb_pc_s* pc) {
     KbIluExtra* x = extra_of(pc);
     if (x) {
         if (x->owns_pattern) { KB_FREE(pc->l_rp); KB_FREE(pc->l_col); }
+        kb_tiles_free(x->tiles); x->tiles = nullptr;
         KB_FREE(x->level[0]); KB_FREE(x->level[1]); KB_FREE(x->counters); KB_FREE(x->ediag);
         for (int u = 0; u < 2; ++u) { KB_FREE(x->width[u]); KB_FREE(x->off[u]); KB_FREE(x->ecol[u]); KB_FREE(x->eval[u]); KB_FREE(x->spad[u]); KB_FREE(x->chunk_lev[u]); KB_FREE(x->done[u]); }
         delete x;
@@ -525,7 +531,9 @@ int kb_ilu0_build(kb_pc_s* pc) {
         kb_set_error("zero pivot at row %llu", (unsigned long long)pc->bad_row);
         return KB_ZERO_PIVOT;
     }
-    // 5. level-ordered chunk-ELL copies of L and U for the persistent solves
+    // 5. grid-structured pattern (5-/7-point box stencil, detected from the CSR): block-wavefront solves
+    if (!(getenv("KB_TRSV_TILES") && atoi(getenv("KB_TRSV_TILES")) == 0)) KB_TRY(kb_tiles_build(pc, x->counters + 2, &x->tiles));
+    // 6. level-ordered chunk-ELL copies of L and U for the persistent (general-pattern) solves
     if (getenv("KB_TRSV_KIND")) x->kind = atoi(getenv("KB_TRSV_KIND"));
     if (getenv("KB_TRSV_SLEEP")) x->sleep_ns = atoi(getenv("KB_TRSV_SLEEP"));
     for (int u = 0; u < 2 && x->kind == 1; ++u) {
@@ -568,6 +576,7 @@ int kb_ilu0_apply_dev(kb_pc_s* pc, const double* d_r, double* d_z, const KbCtl* 
     kb_ctx_s* c = A->ctx;
     if (A->n == 0) return KB_OK;
     KbIluExtra* x = extra_of(pc);
+    if (x->tiles) return kb_tiles_apply(pc, x->tiles, d_r, d_z, skip_ctl, skip_mask);
     {
         KbLaunch L(c, KB_K_TRSV);
         kb_trsv_fill<<<(unsigned)((A->n + 255) / 256), 256, 0, c->stream>>>(pc->tmp, d_z, (long long)A->n, skip_ctl, skip_mask, x->done[0], pc->nlev[0], x->done[1], pc->nlev[1]);
@@ -607,6 +616,17 @@ int kb_ilu0_apply_dev(kb_pc_s* pc, const double* d_r, double* d_z, const KbCtl* 
     }
     KB_CUDA(cudaGetLastError());
     return KB_OK;
+}
+
+// 1 when a bounded spin of a triangular solve expired (a dependency never arrived): the solve's result is invalid
+int kb_ilu0_error(kb_pc_s* pc) {
+    KbIluExtra* x = pc && pc->kind == KB_PC_ILU0 ? extra_of(pc) : nullptr;
+    if (!x || !x->counters) return 0;
+    unsigned e = 0;
+    kb_ctx_s* c = pc->ctx;
+    if (cudaMemcpyAsync(&e, x->counters + 2, sizeof(e), cudaMemcpyDeviceToHost, c->stream) != cudaSuccess ||
+        cudaStreamSynchronize(c->stream) != cudaSuccess) return 1;
+    return e != 0;
 }
 
 extern "C" int kb_pc_create_ilu0(kb_csr A, kb_pc* out) {

@@ -100,5 +100,6 @@ void kb_bicg_ws_free(KbBicgWs* w);
 void kb_gmres_ws_free(KbGmresWs* w);
 void kb_halo_free(KbHalo* h);
 int kb_ilu0_build(kb_pc_s* pc);
+int kb_ilu0_error(kb_pc_s* pc);                   // 1 if a triangular-solve spin timed out
 void kb_ilu0_free(kb_pc_s* pc);
 int kb_upload_or_alias(kb_ctx_s* c, const double* src, double* dst, uint64_t n, bool device_ptrs);

@@ -466,6 +466,7 @@ extern "C" int kb_pcg_solve(kb_csr A, kb_pc pc, const double* b, double* x, doub
         stats->iterations = h->iter; stats->final_residual = h->res; stats->converged = h->converged; stats->breakdown = 0;
         st = h->status;
         if (dist && kb_p2p_error(c)) { kb_set_error("%s: peer-memory collective timed out", "pcg"); st = KB_SOLVE_ERROR; break; }
+        if (pc && kb_ilu0_error(const_cast<kb_pc_s*>(pc))) { kb_set_error("%s: a triangular-solve dependency wait timed out", "pcg"); st = KB_SOLVE_ERROR; break; }
         uint64_t hl = std::min<uint64_t>(h->hist_len, hist_cap);
         if (hist_len) *hist_len = h->hist_len;
         if (hl && cudaMemcpyAsync(history, w->hist, hl * sizeof(double), cudaMemcpyDeviceToHost, c->stream) != cudaSuccess) { st = KB_SOLVE_ERROR; break; }

@@ -38,6 +38,44 @@ def test_ilu0_factors_levels_apply_bit_exact(ctx, kind, N):
     assert np.array_equal(z, o.ilu0_apply(Ao, lu_o, dp_o, iud_o, r))
 
 
+@pytest.mark.parametrize("tiles", ["0", "1"])
+@pytest.mark.parametrize("kind,N", [("convdiff2d", 70), ("poisson2d", 130), ("poisson3d", 20), ("convdiff3d", 17), ("varcoef27", 10)])
+def test_trsv_schedules_bit_exact(ctx, kind, N, tiles):
+    """Both triangular-solve schedules on the same factors: block-wavefront tiles (5-/7-point box grids, detected from
+    the pattern; sizes are not multiples of the tile shape) and the level-scheduled persistent kernel (forced with
+    KB_TRSV_TILES=0; the 27-point operator always takes it)."""
+    import os
+    import kryst_b200 as kb
+    A, Ao = _mk(kind, N, ctx)
+    os.environ["KB_TRSV_TILES"] = tiles
+    try:
+        pc = kb.Ilu0().setup(A)
+    finally:
+        del os.environ["KB_TRSV_TILES"]
+    st, lu_o, dp_o, iud_o, bad = o.ilu0_factor(Ao)
+    rng = np.random.default_rng(5)
+    for _ in range(3):
+        r = rng.standard_normal(Ao.n)
+        z = np.zeros(Ao.n)
+        pc.apply(r, z)
+        assert np.array_equal(z, o.ilu0_apply(Ao, lu_o, dp_o, iud_o, r))
+
+
+def test_trsv_tiles_on_a_slab_submatrix(ctx):
+    """A z-slab block (what block-Jacobi ILU(0) factors on a shard), incl. a ragged last plane."""
+    import kryst_b200 as kb
+    A, Ao = _mk("poisson3d", 14, ctx)
+    for lo, hi in ((14 * 14 * 3, 14 * 14 * 11), (0, 14 * 14 * 2 + 37)):
+        idx = np.arange(lo, hi)
+        S, So = A.submatrix(idx), o.submatrix(Ao, idx)
+        pc = kb.Ilu0().setup(S)
+        st, lu_o, dp_o, iud_o, bad = o.ilu0_factor(So)
+        r = np.random.default_rng(9).standard_normal(So.n)
+        z = np.zeros(So.n)
+        pc.apply(r, z)
+        assert np.array_equal(z, o.ilu0_apply(So, lu_o, dp_o, iud_o, r))
+
+
 def test_ilu0_level_counts(ctx):
     import kryst_b200 as kb
     for kind, N, expect in (("poisson2d", 20, 39), ("poisson3d", 10, 28)):
