@@ -7,6 +7,8 @@ algorithms in dense numpy (left-to-right Python sums instead of the oracle's can
   PCG        src/solver/pcg.rs:114-222          GMRES (None/Left/Right, MGS+2nd pass) src/solver/gmres.rs:216-402
   BiCGStab   src/solver/bicgstab.rs:69-293      Jacobi src/preconditioner/jacobi.rs:69-95
   Ilu0 (dense, literal) src/preconditioner/ilu.rs:59-122       Convergence::check src/utils/convergence.rs:18-34
+  FGMRES (classical GS, flexible right pc) src/solver/fgmres.rs:114-340
+plus the Chronopoulos-Gear single-reduction PCG (the reference's flag of that name is a no-op),
 plus a dense textbook ILU(0) (Saad Alg. 10.4, IKJ) used to pin the Tier-T factorisation.
 The JSON holds iteration counts, final residuals and solutions for small problems; tests/test_oracle_golden.py
 requires the C++ oracle to reproduce them (counts exactly, floats to 1e-10: the reduction order differs).
@@ -72,6 +74,129 @@ def pcg(a, inv, b, x0, tol, max_iters):
         p = z + beta * p
         rz = rz_new
     return dict(iterations=it, final_residual=res, converged=conv, x=x.tolist(), history=hist)
+
+
+def pcg_single_reduction(a, inv, b, x0, tol, max_iters):
+    """Chronopoulos-Gear PCG with the literal PCG's conventions (res0 = sqrt|r.u|, history, Convergence::check)."""
+    x = np.array(x0, dtype=float)
+    r = b - a @ x
+    u = inv * r if inv is not None else r.copy()
+    w = a @ u
+    gamma = dot(r, u)
+    delta = dot(u, w)
+    res0 = math.sqrt(abs(gamma))
+    hist = [norm(r)]
+    if max_iters == 0:
+        return dict(iterations=0, final_residual=res0, converged=False, x=x.tolist(), history=hist)
+    if delta <= 0.0:
+        return dict(err="IndefiniteMatrix", iterations=1)
+    alpha, beta = gamma / delta, 0.0
+    p = np.zeros_like(x)
+    s = np.zeros_like(x)
+    it, res, conv = 0, res0, False
+    for i in range(max_iters):
+        p = u + beta * p
+        s = w + beta * s
+        x = x + alpha * p
+        r = r - alpha * s
+        u = inv * r if inv is not None else r.copy()
+        gamma_new = dot(r, u)
+        res = norm(r)
+        w = a @ u
+        delta = dot(u, w)
+        hist.append(res)
+        it = i + 1
+        conv = check(res, res0, it, tol, max_iters)
+        if conv:
+            break
+        beta = gamma_new / gamma
+        if beta < 0.0:
+            return dict(err="IndefinitePreconditioner", iterations=i + 1)
+        pap = delta - beta * gamma_new / alpha
+        if pap <= 0.0:
+            return dict(err="IndefiniteMatrix", iterations=i + 2)
+        alpha = gamma_new / pap
+        gamma = gamma_new
+    return dict(iterations=it, final_residual=res, converged=conv, x=x.tolist(), history=hist)
+
+
+def fgmres_literal(a, pc_apply, b, x0, tol, max_iters, restart, haptol=1e-12):
+    """fgmres.rs:114-340 with the defaults of FgmresSolver::new (Orthog::Classical, preallocate = false)."""
+    n = len(b)
+    x = np.array(x0, dtype=float)
+    r = b - a @ x
+    beta = norm(r)
+    if beta == 0.0:
+        return dict(iterations=0, final_residual=0.0, converged=True, x=x.tolist())
+    v = [np.zeros(n) for _ in range(restart + 1)]
+    z = [np.zeros(n) for _ in range(restart)]
+    h = [[0.0] * restart for _ in range(restart + 1)]
+    cs, sn, s = [0.0] * restart, [0.0] * restart, [0.0] * (restart + 1)
+    s[0] = beta
+    v[0] = r / beta
+    total = 0
+    res_norm_outer = beta                      # fgmres.rs:171: the value the epilogue reports (:334)
+    stats = dict(iterations=0, final_residual=res_norm_outer, converged=False)
+    while total < max_iters:
+        m = min(restart, max_iters - total)
+        converged = False
+        steps = m
+        for j in range(m):
+            z[j] = pc_apply(v[j]) if pc_apply is not None else v[j].copy()
+            w = a @ z[j]
+            hcol = [dot(w, v[i]) for i in range(j + 1)]
+            for i in range(j + 1):
+                w = w - hcol[i] * v[i]
+            h[j + 1][j] = norm(w)
+            for i in range(j + 1):
+                h[i][j] = hcol[i]
+            if not (abs(h[j + 1][j]) < haptol * abs(s[j])):
+                v[j + 1] = w / h[j + 1][j]
+            else:
+                v[j + 1] = np.zeros(n)
+            for i in range(j):
+                t = cs[i] * h[i][j] + sn[i] * h[i + 1][j]
+                h[i + 1][j] = -sn[i] * h[i][j] + cs[i] * h[i + 1][j]
+                h[i][j] = t
+            h1, h2 = h[j][j], h[j + 1][j]
+            den = math.sqrt(h1 * h1 + h2 * h2)
+            c, s_ = (1.0, 0.0) if den == 0.0 else (h1 / den, h2 / den)
+            cs[j], sn[j] = c, s_
+            t = c * s[j] + s_ * s[j + 1]
+            s[j + 1] = -s_ * s[j] + c * s[j + 1]
+            s[j] = t
+            h[j][j] = c * h[j][j] + s_ * h[j + 1][j]
+            h[j + 1][j] = 0.0
+            res = abs(s[j + 1])
+            total += 1
+            stop = check(res, s[0], total, tol, max_iters)      # NB: s[0] was just rotated when j == 0 (fgmres.rs:290)
+            stats = dict(iterations=total, final_residual=res, converged=stop)
+            if stop:
+                steps = j + 1
+                converged = True
+                break
+        k = steps
+        y = [0.0] * k
+        for i in reversed(range(k)):
+            acc = s[i]
+            for l in range(i + 1, k):
+                acc = acc - h[i][l] * y[l]
+            y[i] = acc / h[i][i]
+        for i in range(k):
+            x = x + y[i] * z[i]
+        r_new = b - a @ x
+        rn = norm(r_new)
+        if rn < tol or converged:
+            stats = dict(iterations=total, final_residual=rn, converged=True)
+            break
+        beta = rn
+        v[0] = r_new / beta
+        s = [0.0] * (restart + 1)
+        s[0] = beta
+    stats["final_residual"] = res_norm_outer   # fgmres.rs:334-335 (shadowed variable: always ||r0||)
+    stats["iterations"] = total
+    stats["x"] = x.tolist()
+    return stats
 
 
 def gmres_literal(a, pc_apply, b, x0, restart, tol, max_iters, mode):
@@ -314,6 +439,11 @@ def convdiff2d(N, px=0.4, py=0.2):
     return a
 
 
+def rowscaled(a):
+    """Row scaling with a non-constant factor: makes Jacobi a genuinely different preconditioner from the identity."""
+    return np.diag(1.0 + 0.05 * np.arange(a.shape[0])) @ a
+
+
 def main():
     out = {}
     # PCG + Jacobi / no pc on small Poisson and the reference's tridiagonal
@@ -334,6 +464,17 @@ def main():
     b = a @ np.ones(10)
     out["gmres_literal_left_iluliteral/tridiag_nonsym_10"] = gmres_literal(a, lambda v: ilu_literal_apply(l, u, v), b, np.zeros(10), 10, 1e-12, 100, "left")
     out["ilu_literal_apply/tridiag_nonsym_6"] = dict(z=ilu_literal_apply(*ilu_literal(tridiag(6, -1, 2, 0.5)), np.arange(1.0, 7.0)).tolist())
+    # single-reduction PCG and literal FGMRES
+    for name, a in (("poisson2d_8", poisson2d(8)), ("tridiag_spd_10", tridiag(10, -1, 2, -1))):
+        b = a @ np.ones(a.shape[0])
+        out["pcg_sr_jacobi/" + name] = pcg_single_reduction(a, jacobi_inv(a), b, np.zeros(len(b)), 1e-10, 500)
+        out["pcg_sr_none/" + name] = pcg_single_reduction(a, None, b, np.zeros(len(b)), 1e-10, 500)
+    for name, a in (("convdiff2d_8", convdiff2d(8)), ("tridiag_nonsym_10", tridiag(10, -1, 2, 0.5)),
+                    ("rowscaled_convdiff2d_8", rowscaled(convdiff2d(8)))):
+        b = a @ np.ones(a.shape[0])
+        inv = jacobi_inv(a)
+        out["fgmres_literal_jacobi/" + name] = fgmres_literal(a, lambda v, inv=inv: inv * v, b, np.zeros(len(b)), 1e-9, 400, 5)
+        out["fgmres_literal_none/" + name] = fgmres_literal(a, None, b, np.zeros(len(b)), 1e-9, 400, 5)
     # BiCGStab literal
     for name, a in (("convdiff2d_8", convdiff2d(8)),):
         b = a @ np.ones(a.shape[0])

@@ -175,6 +175,8 @@ def _dense(name):
     spec.loader.exec_module(mg)
     kind, size = name.rsplit("_", 1)
     size = int(size)
+    if kind.startswith("rowscaled_"):
+        return mg.rowscaled(_dense(name[len("rowscaled_"):]))
     if kind == "poisson2d":
         return mg.poisson2d(size)
     if kind == "convdiff2d":
@@ -221,6 +223,33 @@ def test_golden_gmres_literal_ilu_literal():
     assert np.allclose(z, GS["ilu_literal_apply/tridiag_nonsym_6"]["z"], rtol=1e-13)
     # the literal Ilu0 is not an ILU (documented deviation F5)
     assert np.allclose(z, [0.237, 1.525, 1.949, 4.602, 3.047, 10.031], atol=2e-3)
+
+
+@pytest.mark.parametrize("key", sorted(k for k in GS if k.startswith("pcg_sr_")))
+def test_golden_pcg_single_reduction(key):
+    """the oracle's Chronopoulos-Gear PCG against the independent numpy restatement."""
+    g = GS[key]
+    a = _dense(key.split("/")[1])
+    A = o.OCsr.from_dense(a)
+    b = a @ np.ones(a.shape[0])
+    rc, x, st, h = o.pcg_sr(A, o.OPc.jacobi(A) if key.startswith("pcg_sr_jacobi") else None, b, np.zeros(len(b)), 1e-10, 500, hist_cap=600)
+    assert rc == 0 and st.iterations == g["iterations"] and bool(st.converged) == g["converged"]
+    assert np.allclose(x, g["x"], rtol=1e-10, atol=1e-12)
+    assert np.allclose(h, g["history"], rtol=1e-6, atol=1e-13)
+
+
+@pytest.mark.parametrize("key", sorted(k for k in GS if k.startswith("fgmres_literal_")))
+def test_golden_fgmres_literal(key):
+    """the oracle's fgmres.rs restatement against the independent numpy transliteration, incl. the
+    reference's quirk that the reported final_residual is always ||r0|| (fgmres.rs:171,334)."""
+    g = GS[key]
+    a = _dense(key.split("/")[1])
+    A = o.OCsr.from_dense(a)
+    b = a @ np.ones(a.shape[0])
+    rc, x, st = o.fgmres(A, o.OPc.jacobi(A) if "_jacobi/" in key else None, b, np.zeros(len(b)), 5, 1e-9, 400)
+    assert rc == 0 and st.iterations == g["iterations"] and bool(st.converged) == g["converged"]
+    assert abs(st.final_residual - g["final_residual"]) <= 1e-12 * g["final_residual"]
+    assert np.allclose(x, g["x"], rtol=1e-8, atol=1e-10)
 
 
 def test_golden_bicgstab_literal():
