@@ -81,7 +81,7 @@ __global__ void __launch_bounds__(KB_THREADS) kb_trsv_tiles(KbTileArgs a) {
     const int tid = threadIdx.x;
     const int bxy = a.bx * a.by, trows = bxy * a.bz;
     const int nlevels = a.bx + a.by + a.bz - 2;          // internal wavefront depth of a full tile
-    const int sx = a.nx, sy = a.nx * a.ny;
+    const int sx = a.nx;                                 // column stride of a j-step; anything else that is not 1 is a k-step
     for (int t = blockIdx.x; t < a.ntiles; t += gridDim.x) {
         const int tile = a.order[t];
         const int TI = tile % a.tx, TJ = (tile / a.tx) % a.ty, TK = tile / (a.tx * a.ty);
