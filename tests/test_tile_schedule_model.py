@@ -131,3 +131,93 @@ def test_detector_rejects_wrapped_and_irregular_patterns():
     assert detect(W.row_ptr.astype(np.int64), W.col_idx.astype(np.int64), W.n) is None
     T = o.OCsr.from_dense(np.diag(np.full(70, 2.0)) + np.diag(np.full(69, -1.0), 1) + np.diag(np.full(69, -1.0), -1))
     assert detect(T.row_ptr.astype(np.int64), T.col_idx.astype(np.int64), T.n) is None      # 1-D: no second axis
+
+
+# ---- next step: the same schedule for 9-/27-point patterns through a unimodular skew -------------------
+# Executable specification for the kernel that is not written yet: cube tiles are illegal for these patterns (a lower
+# neighbour (i+1, j-1, k) can sit in a later cube); in skewed coordinates u = i+j+2k, v = j+k, w = k every dependency is
+# non-positive, cube tiles in (u,v,w) are convex, their predecessors are the <= 7 tiles one step back, and the in-tile
+# wavefront i+2j+4k is simply lu+lv+lw.
+def detect_box(rp, col, n):
+    """-> (nx, ny, nz) if every off-diagonal entry is a (+-1, +-1, +-1) box-stencil neighbour, else None."""
+    offs = set()
+    for r in range(n):
+        for p in range(rp[r], rp[r + 1]):
+            if col[p] != r:
+                offs.add(abs(r - col[p]))
+    big = sorted(d for d in offs if d > 1)
+    if not big:
+        return None
+    for nx in (big[0], big[0] + 1):
+        if nx < 3:
+            continue
+        for nxy in {big[-1], big[-1] - nx - 1, big[-1] - nx, big[-1] - 1, nx * ((n + nx - 1) // nx)}:
+            if nxy < nx or nxy % nx:
+                continue
+            ny = nxy // nx
+            nz = (n + nxy - 1) // nxy
+            good = True
+            for r in range(n):
+                i, j, k = r % nx, (r // nx) % ny, r // nxy
+                for p in range(rp[r], rp[r + 1]):
+                    c = col[p]
+                    ci, cj, ck = c % nx, (c // nx) % ny, c // nxy
+                    if max(abs(ci - i), abs(cj - j), abs(ck - k)) > 1:
+                        good = False
+                        break
+                if not good:
+                    break
+            if good:
+                return (int(nx), int(nz), 1) if ny == 1 else (int(nx), int(ny), int(nz))     # two-dimensional: canonical form
+    return None
+
+
+def solve_skewed(rp, col, lu, dptr, invd, rhs, n, grid, upper, B=4):
+    nx, ny, nz = grid
+    two_d = nz == 1
+    def skew(i, j, k):
+        return (i + j, j, 0) if two_d else (i + j + 2 * k, j + k, k)
+    umax, vmax, wmax = skew(nx - 1, ny - 1, nz - 1)
+    tx, ty, tz = umax // B + 1, vmax // B + 1, wmax // B + 1
+    tiles = {}
+    for r in range(n):
+        u, v, w = skew(r % nx, (r // nx) % ny, r // (nx * ny))
+        tiles.setdefault((u // B, v // B, w // B), []).append((u + v + w, r))
+    order = sorted(tiles, key=lambda t: (t[0] + t[1] + t[2], t[2], t[1], t[0]))
+    if upper:
+        order = order[::-1]
+    done, out = set(), np.full(n, np.nan)
+    tile_of = {}
+    for t, rows in tiles.items():
+        for _, r in rows:
+            tile_of[r] = t
+    for t in order:
+        for da, db, dc in [(a, b, c) for a in (0, 1) for b in (0, 1) for c in (0, 1) if a + b + c]:
+            p = (t[0] + da, t[1] + db, t[2] + dc) if upper else (t[0] - da, t[1] - db, t[2] - dc)
+            assert p not in tiles or p in done, "predecessor tile not finished"
+        for _, r in sorted(tiles[t], reverse=upper):          # in-tile wavefront lu+lv+lw
+            pd = dptr[r]
+            p0, p1 = (pd + 1, rp[r + 1]) if upper else (rp[r], pd)
+            s = rhs[r]
+            for p in range(p0, p1):
+                c = col[p]
+                tc = tile_of[c]
+                d = tuple((tc[x] - t[x]) if upper else (t[x] - tc[x]) for x in range(3))
+                assert min(d) >= 0 and max(d) <= 1, "dependency outside the 7 predecessor tiles"
+                assert not np.isnan(out[c]), "operand not ready"
+                s = s - lu[p] * out[c]
+            out[r] = s * invd[r] if upper else s
+        done.add(t)
+    return out
+
+
+@pytest.mark.parametrize("kind,N,grid", [("varcoef27", 7, (7, 7, 7)), ("poisson3d", 9, (9, 9, 9)), ("convdiff2d", 21, (21, 21, 1))])
+def test_skewed_tile_schedule_is_legal_and_exact(kind, N, grid):
+    A = o.stencil(kind, N)
+    st, lu, dp, iud, bad = o.ilu0_factor(A)
+    rp, col, dp = A.row_ptr.astype(np.int64), A.col_idx.astype(np.int64), dp.astype(np.int64)
+    assert detect_box(rp, col, A.n) == grid
+    rhs = np.random.default_rng(2).standard_normal(A.n)
+    y = solve_skewed(rp, col, lu, dp, iud, rhs, A.n, grid, False)
+    z = solve_skewed(rp, col, lu, dp, iud, y, A.n, grid, True)
+    assert np.array_equal(z, o.ilu0_apply(A, lu, dp.astype(np.uint64), iud, rhs))
