@@ -113,7 +113,7 @@ def run_reference(args):
     A = o.stencil(kind, N)
     b = o.spmv(A, np.ones(A.n))
     pc = o.OPc.jacobi(A)
-    cores = o.num_threads()
+    cores = o.use_all_cores()        # torchrun sets OMP_NUM_THREADS=1 for its workers
     # bounded sample: S iterations of the same solve (from x0 = 0) per step
     t0 = time.perf_counter()
     o.pcg(A, pc, b, np.zeros(A.n), TOL, 2)
@@ -147,6 +147,7 @@ def cpu_baseline(args, kind, N):
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import numpy as np
     import oracle_ffi as o
+    o.use_all_cores()
     A = o.stencil(kind, N)
     b = o.spmv(A, np.ones(A.n))
     pc = o.OPc.jacobi(A)

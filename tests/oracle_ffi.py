@@ -364,3 +364,12 @@ def bicgstab(A, pc, b, x0, tol, max_iters, variant=BICG_LITERAL, nshards=1):
 
 def num_threads():
     return int(lib().ko_num_threads())
+
+
+def use_all_cores():
+    """OpenMP threads = the cores this process may run on.  torchrun exports OMP_NUM_THREADS=1 to its workers, which
+    would silently turn the CPU baseline into a single-thread run."""
+    import os
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    lib().ko_set_num_threads(max(1, n))
+    return num_threads()

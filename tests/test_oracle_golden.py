@@ -423,3 +423,14 @@ def test_ref_fgmres_2x2_fixture():
     assert st.final_residual == o.norm(a @ xt)
     rc, x, st = o.fgmres(A, None, np.zeros(2), np.zeros(2), 25, 1e-10, 100)      # beta == 0 early return (fgmres.rs:152-154)
     assert st.converged and st.iterations == 0 and st.final_residual == 0.0
+
+
+def test_cpu_baseline_uses_all_cores_even_under_torchrun_env():
+    """torchrun exports OMP_NUM_THREADS=1 to its workers; bench.py's CPU arms must not inherit that."""
+    import subprocess
+    import sys
+    code = ("import sys, os; sys.path.insert(0, %r); import oracle_ffi as o; "
+            "print(o.num_threads(), o.use_all_cores(), len(os.sched_getaffinity(0)))" % HERE)
+    env = dict(os.environ, OMP_NUM_THREADS="1")
+    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, check=True).stdout.split()
+    assert out[0] == "1" and out[1] == out[2]
