@@ -311,7 +311,7 @@ def main():
 
     if rank == 0:
         cpu = None
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:     # reported at N=1 only (the other ranks would idle meanwhile)
             cpu = cpu_baseline(args, kind, N)
         line = {
             "metric": "krylov_iterations_per_sec", "value": its / sec, "unit": "it/s", "n_gpus": args.gpus, "steps": args.steps,
