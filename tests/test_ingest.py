@@ -172,3 +172,63 @@ def test_gpu_download_and_submatrix_edges(ctx):
     Z = kb.DeviceCsr.from_csr(3, 3, [0, 1, 2, 3], [0, 1, 2], [0.0, -0.0, 5.0], ctx)      # stored zeros are dropped
     rp, ci, v = Z.submatrix([2, 1, 0]).to_csr()
     assert rp.tolist() == [0, 1, 1, 1] and ci.tolist() == [0] and v.tolist() == [5.0]
+
+
+# ---- C++ host reader (include/kryst_mmio.hpp) against the Python one ------------------------------------------------
+def _cpp_mmio(tmp_path):
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "test_mmio")
+    subprocess.check_call(["/usr/bin/g++", "-std=c++17", "-O1", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(root, "include"),
+                           os.path.join(root, "tests", "cpp", "test_mmio.cpp"), "-o", exe])
+    return exe
+
+
+def _run_cpp(exe, *args):
+    import subprocess
+    r = subprocess.run([exe] + [str(a) for a in args], capture_output=True, text=True)
+    if r.returncode != 0:
+        return r.returncode, r.stderr
+    lines = r.stdout.split("\n")
+    n, m, nnz = (int(t) for t in lines[0].split())
+    rp = np.array([int(t) for t in lines[1].split()], dtype=np.uint64)
+    ci = np.array([int(t) for t in lines[2].split()], dtype=np.uint64)
+    v = np.array([float.fromhex(t) for t in lines[3].split()], dtype=np.float64)
+    assert ci.size == nnz and v.size == nnz
+    return 0, (n, m, rp, ci, v)
+
+
+def test_cpp_matrix_market_reader_matches_python(tmp_path):
+    mm = _mmio()
+    exe = _cpp_mmio(tmp_path)
+    A = _rand_csr(30, 41, 0.2, seed=4, zeros=True)
+    p, q = tmp_path / "a.mtx", tmp_path / "b.mtx"
+    mm.write_matrix_market(str(p), A.n, A.ncols, A.row_ptr, A.col_idx, A.vals)
+    rc, (n, m, rp, ci, v) = _run_cpp(exe, p, q)
+    assert rc == 0 and (n, m) == (A.n, A.ncols)
+    assert np.array_equal(rp, A.row_ptr) and np.array_equal(ci, A.col_idx) and np.array_equal(v, A.vals)
+    n2, m2, rp2, ci2, v2 = mm.read_matrix_market(str(q))                    # C++ writer -> Python reader: exact round trip
+    assert np.array_equal(rp2, A.row_ptr) and np.array_equal(ci2, A.col_idx) and np.array_equal(v2, A.vals)
+    cases = ["%%MatrixMarket matrix coordinate real symmetric\n% lower triangle\n3 3 4\n1 1 2.0\n2 1 -1.0\n3 2 -1.0\n3 3 2.0\n",
+             "%%MatrixMarket matrix coordinate pattern general\n2 3 3\n1 3\n2 1\n1 1\n",
+             "%%MatrixMarket matrix coordinate real general\n2 2 4\n1 1 1.0\n2 2 5.0\n1 1 0.25\n1 1 0.5\n",
+             "%%MatrixMarket matrix coordinate real skew-symmetric\n2 2 1\n2 1 3.0\n",
+             "%%MatrixMarket matrix coordinate integer symmetric\n4 4 5\n1 1 4\n4 1 -2\n2 2 4\n4 1 -1\n3 3 7\n",
+             "%%MatrixMarket matrix coordinate real general\n0 0 0\n"]
+    for text in cases:
+        p.write_text(text)
+        want = mm.read_matrix_market(str(p))
+        rc, got = _run_cpp(exe, p)
+        assert rc == 0 and got[:2] == want[:2], text
+        assert all(np.array_equal(g, w) for g, w in zip(got[2:], want[2:])), text
+    for bad in ("%%MatrixMarket matrix array real general\n2 2\n1\n2\n3\n4\n",
+                "%%MatrixMarket matrix coordinate complex general\n1 1 1\n1 1 1.0 0.0\n",
+                "%%MatrixMarket matrix coordinate real general\n2 2 1\n3 1 1.0\n",
+                "%%MatrixMarket matrix coordinate real general\n2 2 2\n1 1 1.0\n",
+                "%%MatrixMarket matrix coordinate real skew-symmetric\n2 2 1\n1 1 3.0\n",
+                "not a header\n"):
+        p.write_text(bad)
+        rc, msg = _run_cpp(exe, p)
+        assert rc == 2 and "MatrixMarketError" in msg, bad
+        with pytest.raises(mm.MatrixMarketError):
+            mm.read_matrix_market(str(p))
