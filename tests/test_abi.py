@@ -81,3 +81,12 @@ def test_stencil_generators_match_oracle_twin(built):
     # symmetric, diagonally dominant variable-coefficient operator
     a = o.stencil("varcoef27", 4).to_dense()
     assert np.array_equal(a, a.T) and np.all(np.diag(a) >= np.abs(a - np.diag(np.diag(a))).sum(axis=1) - 1e-12)
+
+
+def test_header_is_plain_c(tmp_path):
+    """The drop-in boundary is a C ABI: include/kryst_b200.h must compile as strict C99 (no C++/torch types)."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = tmp_path / "abi.c"
+    src.write_text('#include "kryst_b200.h"\nint main(void) { kb_stats s; kb_profile p; (void)s; (void)p; return KB_OK; }\n')
+    subprocess.check_call(["gcc", "-std=c99", "-pedantic", "-Wall", "-Werror", "-I", os.path.join(root, "include"), "-fsyntax-only", str(src)])
