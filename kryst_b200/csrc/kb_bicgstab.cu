@@ -295,7 +295,7 @@ extern "C" int kb_bicgstab_solve(kb_csr A, kb_pc pc, const double* b, double* x,
         }
         const double bytes_iter = 24.0 * (double)A->nnz + 170.0 * (double)A->n;
         const int B = kb_batch_size(bytes_iter, 5);
-        st = kb_run_iterations(c, &w->gc, ((uint64_t)(uintptr_t)pc + 1) * 4 + (uint64_t)mode, B, max_iters, use_graph, w->ctl, h,
+        st = kb_run_iterations(c, &w->gc, (kb_pc_serial(pc) + 1) * 4 + (uint64_t)mode, B, max_iters, use_graph, w->ctl, h,
                                [&]() { return bicg_iteration(A, pc, w, mode, dist); });
         if (st != KB_OK) break;
         if (cudaMemcpyAsync(h, w->ctl, offsetof(KbCtl, h), cudaMemcpyDeviceToHost, c->stream) != cudaSuccess ||

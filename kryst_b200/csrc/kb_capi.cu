@@ -19,6 +19,8 @@ void kb_set_error(const char* fmt, ...) {
 }
 extern "C" const char* kb_last_error(void) { return g_err; }
 extern "C" int kb_abi_version(void) { return KB_ABI_VERSION; }
+#include <atomic>
+uint64_t kb_next_serial() { static std::atomic<uint64_t> g{0}; return ++g; }
 
 // ---------------------------------------------------------------------------------------------
 // launch bookkeeping / profiling
@@ -227,7 +229,7 @@ int kb_csr_alloc(kb_ctx c, uint64_t nrows, uint64_t ncols_global, uint64_t nnz, 
     }
     kb_csr_s* A = new kb_csr_s;
     A->ctx = c; A->n = nrows; A->ncols_global = ncols_global; A->ncols_local = ncols_global; A->nnz = nnz;
-    A->ntiles = kb_num_tiles(nrows);
+    A->ntiles = std::max(1, kb_num_tiles(nrows));   // an empty shard still launches one (empty) tile: it must join the in-kernel all-reduces
     A->dist = false; A->n_global = nrows; A->row_lo = 0; A->row_hi = nrows;
     c->refs++;
     int st = KB_OK;
@@ -420,7 +422,10 @@ struct DotOp : KbRedBase {
 
 static int dot_host(kb_ctx c, uint64_t n, const double* x, const double* y, double* out) {
     KB_CUDA(cudaSetDevice(c->device));
-    if (n == 0) { *out = 0.0; return KB_OK; }
+    if (n == 0) {      // an empty shard still takes part in the collective
+        if (c->size > 1) return kb_comm_all_reduce(c, 0.0, out);
+        *out = 0.0; return KB_OK;
+    }
     double *dx = nullptr, *dy = nullptr, *part = nullptr;
     int P = kb_num_tiles(n);
     KB_TRY(kb_alloc(&dx, n));

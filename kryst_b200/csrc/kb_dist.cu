@@ -154,8 +154,10 @@ const KbP2PDev* kb_p2p_dev_ptr(kb_ctx_s* c) { return c->p2p ? reinterpret_cast<K
 int kb_p2p_error(kb_ctx_s* c) {
     if (!c->p2p) return 0;
     unsigned e = 0;
-    cudaMemcpy(&e, reinterpret_cast<KbP2PHost*>(c->p2p)->dev.err, sizeof(unsigned), cudaMemcpyDeviceToHost);
-    return (int)e;
+    unsigned* d = reinterpret_cast<KbP2PHost*>(c->p2p)->dev.err;
+    cudaMemcpy(&e, d, sizeof(unsigned), cudaMemcpyDeviceToHost);
+    if (e) cudaMemset(d, 0, sizeof(unsigned));     // reported once; the sequence counters of the peers may be out of
+    return (int)e;                                 // step after a timeout: the caller must re-create the communicator
 }
 
 extern "C" int kb_comm_unique_id(void* id128) {

@@ -126,7 +126,7 @@ static int kb_launch_spmv(kb_csr_s* A, const double* x, double* y, const double*
                           size_t pstride, Epi epi, double* halo_x = nullptr) {
     kb_ctx_s* c = A->ctx;
     const bool dist = halo_x != nullptr && A->dist && c->size > 1;
-    if (A->n == 0) { if (dist) return kb_halo_exchange(A, halo_x); return KB_OK; }
+    if (A->n == 0 && !dist) return KB_OK;
     KbSpmvArgs a{};
     a.row_ptr = A->row_ptr; a.col = A->col; a.vals = A->vals; a.x = x; a.y = y; a.b = b; a.w = w;
     a.n = (int)A->n; a.ntiles_total = A->ntiles;

@@ -593,7 +593,7 @@ static int gmres_solve_impl(kb_csr A, kb_pc pc, const double* b, double* x, uint
             }
         }
         if ((st = gm_start_vector(P)) != KB_OK) break;
-        const uint64_t key = (((uint64_t)(uintptr_t)pc + 1) * 4 + (uint64_t)side) * 256 + restart;
+        const uint64_t key = ((kb_pc_serial(pc) + 1) * 4 + (uint64_t)side) * 256 + restart;
         st = kb_run_iterations(c, &w->gc, key, 1, (uint64_t)h->n_outer, use_graph, w->ctl, h, [&]() { return gm_cycle(P); });
         if (st != KB_OK) break;
         if (cudaMemcpyAsync(h, w->ctl, offsetof(KbCtl, h), cudaMemcpyDeviceToHost, c->stream) != cudaSuccess ||

@@ -164,7 +164,9 @@ __global__ void __launch_bounds__(KB_THREADS) kb_trsv_syncfree(KbTrsvArgs a) {
                 s = s * a.inv_ud[i];
             }
             // publish: a single 64-bit store is the data and the ready flag at once
-            *reinterpret_cast<volatile unsigned long long*>(a.out + i) = (unsigned long long)__double_as_longlong(s);
+            unsigned long long sb = (unsigned long long)__double_as_longlong(s);
+            if (sb == KB_SENTINEL) sb = 0x7FF8000000000000ull;      // never publish the "not ready" pattern as a value
+            *reinterpret_cast<volatile unsigned long long*>(a.out + i) = sb;
         }
     }
     __syncthreads();
@@ -313,7 +315,9 @@ __global__ void __launch_bounds__(KB_THREADS) kb_trsv_persistent(KbTrsvEll a) {
                     if (cc[u] >= 0) s = s - vv[u] * __longlong_as_double((long long)dv[u]);
             }
             if (UPPER) s = s * dg;
-            kb_st_relaxed_gpu(a.out + row, (unsigned long long)__double_as_longlong(s));
+            unsigned long long sb = (unsigned long long)__double_as_longlong(s);
+            if (sb == KB_SENTINEL) sb = 0x7FF8000000000000ull;      // never publish the "not ready" pattern as a value
+            kb_st_relaxed_gpu(a.out + row, sb);
         }
         // ---- publish per-level completion (slots of every level present in this chunk)
         __syncthreads();
@@ -626,6 +630,10 @@ int kb_ilu0_error(kb_pc_s* pc) {
     kb_ctx_s* c = pc->ctx;
     if (cudaMemcpyAsync(&e, x->counters + 2, sizeof(e), cudaMemcpyDeviceToHost, c->stream) != cudaSuccess ||
         cudaStreamSynchronize(c->stream) != cudaSuccess) return 1;
+    if (e) {    // reported once, then cleared: later applies on this preconditioner start clean
+        cudaMemsetAsync(x->counters, 0, 4 * sizeof(unsigned), c->stream);
+        cudaStreamSynchronize(c->stream);
+    }
     return e != 0;
 }
 

@@ -45,6 +45,8 @@ struct kb_csr_s {
 };
 
 enum { KB_PC_JACOBI = 1, KB_PC_ILU0 = 2 };
+uint64_t kb_next_serial();
+static inline uint64_t kb_pc_serial(const struct kb_pc_s* pc);
 
 struct kb_pc_s {
     kb_csr_s* a = nullptr;           // operator it was set up for (must outlive every apply/solve using this pc)
@@ -67,7 +69,12 @@ struct kb_pc_s {
     double* r_tmp = nullptr;
     double* z_tmp = nullptr;
     void* extra = nullptr;            // ILU(0) bookkeeping (kb_ilu0.cu)
+    // Unique for the lifetime of the process.  The solvers' CUDA-graph caches are keyed on it, never on the
+    // handle's address: a new preconditioner can be allocated where a destroyed one lived.
+    uint64_t serial = kb_next_serial();
 };
+
+static inline uint64_t kb_pc_serial(const kb_pc_s* pc) { return pc ? pc->serial : 0; }
 
 // allocation helpers
 template <class T>

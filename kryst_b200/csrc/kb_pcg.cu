@@ -457,7 +457,7 @@ extern "C" int kb_pcg_solve(kb_csr A, kb_pc pc, const double* b, double* x, doub
         // iterations per graph replay: ~2 ms of work, so the per-replay host poll is amortised
         const int B = kb_batch_size(12.0 * (double)A->nnz + 108.0 * (double)A->n, 3);
         // graph key: the captured launches differ between the two variants
-        st = kb_run_iterations(c, &w->gc, ((uint64_t)(uintptr_t)pc + 1) ^ (single_red ? 0x5352ull << 48 : 0ull), B, max_iters, use_graph, w->ctl, h,
+        st = kb_run_iterations(c, &w->gc, (kb_pc_serial(pc) + 1) ^ (single_red ? 0x5352ull << 48 : 0ull), B, max_iters, use_graph, w->ctl, h,
                                [&]() { return single_red ? pcg_sr_iteration(A, pc, w) : pcg_iteration(A, pc, w); });
         }
         if (st != KB_OK) break;

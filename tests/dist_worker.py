@@ -10,6 +10,43 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 
+def empty_shard_cases(kb, o, parallel, ctx, rank, world):
+    """the chunk partition leaves ranks without rows whenever ceil(n/p)*(p-1) >= n (n = 1, or
+    n = p+1 for p >= 3).  An empty rank must still launch the reducing kernels and join every in-kernel all-reduce."""
+    for nn in (1, world + 1):
+        # 1-D Laplacian tridiag(-1, 2, -1)
+        rp, ci, v = [0], [], []
+        for i in range(nn):
+            for j, a in ((i - 1, -1.0), (i, 2.0), (i + 1, -1.0)):
+                if 0 <= j < nn:
+                    ci.append(j); v.append(a)
+            rp.append(len(ci))
+        rp = np.array(rp, dtype=np.uint64); ci = np.array(ci, dtype=np.uint64); v = np.array(v)
+        Ao = o.OCsr(nn, nn, rp, ci, v)
+        lo, hi = kb.partition_range(nn, world, rank)
+        base = int(rp[lo])
+        A = kb.DeviceCsr.from_csr_shard(nn, lo, hi, rp[lo:hi + 1] - np.uint64(base), ci[base:int(rp[hi])], v[base:int(rp[hi])], ctx)
+        bg = o.spmv(Ao, np.ones(nn))
+        b = bg[lo:hi].copy()
+        x = np.zeros(hi - lo)
+        st = kb.PcgSolver(1e-10, 100).solve(A, kb.Jacobi().setup(A), b, x)
+        rc, xo, so, _ = o.pcg(Ao, o.OPc.jacobi(Ao), bg, np.zeros(nn), 1e-10, 100, nshards=world)
+        assert rc == 0 and (st.iterations, st.converged) == (so.iterations, bool(so.converged)), ("empty-shard pcg", nn, st.iterations, so.iterations)
+        assert st.final_residual == so.final_residual and np.array_equal(x, xo[lo:hi]), "empty-shard pcg"
+        x = np.zeros(hi - lo)
+        st = kb.GmresSolver(5, 1e-10, 100).solve(A, kb.Ilu0().setup(A), b, x)
+        rc, xo, so = o.gmres(Ao, o.OPc.ilu0(Ao, nblocks=world), bg, np.zeros(nn), 5, 1e-10, 100, mode=1, variant=o.GMRES_CGS2, nshards=world)
+        assert (st.iterations, st.converged) == (so.iterations, bool(so.converged)), ("empty-shard gmres", nn, st.iterations, so.iterations)
+        assert st.final_residual == so.final_residual and np.array_equal(x, xo[lo:hi]), "empty-shard gmres"
+        x = np.zeros(hi - lo)
+        st = kb.BiCgStabSolver(1e-10, 100, textbook=True).solve(A, kb.Jacobi().setup(A), b, x)
+        rc, xo, so = o.bicgstab(Ao, o.OPc.jacobi(Ao), bg, np.zeros(nn), 1e-10, 100, variant=o.BICG_TEXTBOOK, nshards=world)
+        assert (st.iterations, st.converged) == (so.iterations, bool(so.converged)), ("empty-shard bicgstab", nn)
+        assert np.array_equal(x, xo[lo:hi]), "empty-shard bicgstab"
+        assert ctx.dot(b, b) == o.dot(bg, bg, nshards=world)
+        A.close()
+
+
 def main():
     import torch
     import torch.distributed as dist
@@ -25,6 +62,7 @@ def main():
     assert ctx.rank() == rank and ctx.size() == world
     assert ctx.all_reduce(float(rank + 1)) == float(sum(range(1, world + 1)))
 
+    empty_shard_cases(kb, o, parallel, ctx, rank, world)
     for kind, N in (("poisson3d", 12), ("convdiff3d", 10), ("convdiff2d", 20), ("varcoef27", 7)):
         n, lo, hi, rp, ci, v = parallel.shard_stencil(kind, N, world, rank)
         A = kb.DeviceCsr.from_csr_shard(n, lo, hi, rp, ci, v, ctx)
@@ -41,12 +79,24 @@ def main():
         bg = o.spmv(Ao, np.ones(n))
         b = bg[lo:hi].copy()
         # PCG + Jacobi
+        # (all four stencils: on the nonsymmetric ones PCG either converges or fails with the same KError as the oracle)
         x = np.zeros(hi - lo)
-        st = kb.PcgSolver(1e-8, 3000).solve(A, kb.Jacobi().setup(A), b, x)
+        pcg = kb.PcgSolver(1e-8, 3000)
         rc, xo, so, _ = o.pcg(Ao, o.OPc.jacobi(Ao), bg, np.zeros(n), 1e-8, 3000, nshards=world)
-        if kind in ("poisson3d", "varcoef27"):
-            assert rc == 0 and (st.iterations, st.converged) == (so.iterations, bool(so.converged)), (kind, st.iterations, so.iterations)
-            assert st.final_residual == so.final_residual and np.array_equal(x, xo[lo:hi]), "dist pcg"
+        try:
+            st = pcg.solve(A, kb.Jacobi().setup(A), b, x)
+            dev_rc = 0
+        except kb.IndefiniteMatrix:
+            dev_rc, st = 3, pcg.last_stats
+        except kb.IndefinitePreconditioner:
+            dev_rc, st = 4, pcg.last_stats
+        assert dev_rc == rc, ("dist pcg status", kind, dev_rc, rc)
+        assert (st.iterations, st.converged) == (so.iterations, bool(so.converged)), (kind, st.iterations, so.iterations)
+        assert st.final_residual == so.final_residual, "dist pcg residual"
+        if rc == 0:
+            assert np.array_equal(x, xo[lo:hi]), "dist pcg"
+        else:
+            assert not x.any(), "x must stay untouched on Err (pcg.rs:171,212)"
         # single-reduction PCG: one all-reduce of three sums per iteration.  On the nonsymmetric
         # operators the recurrence for p.Ap goes non-positive: device and oracle must raise the same IndefiniteMatrix.
         x = np.zeros(hi - lo)

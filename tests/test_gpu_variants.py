@@ -24,6 +24,13 @@ def _rand_csr(n, m, row_len, seed, dense_rows=()):
     return np.array(rp, dtype=np.uint64), np.array(ci, dtype=np.uint64), np.array(v)
 
 
+def _mk(kind, N, ctx):
+    import kryst_b200 as kb
+    from kryst_b200 import stencils
+    n, rp, ci, v = stencils.stencil(kind, N)
+    return kb.DeviceCsr.from_csr(n, n, rp, ci, v, ctx), o.OCsr(n, n, rp, ci, v)
+
+
 def _check_spmv(ctx, n, m, rp, ci, v, exact=True, kind=None):
     import kryst_b200 as kb
     A = kb.DeviceCsr.from_csr(n, m, rp, ci, v, ctx)
@@ -272,3 +279,31 @@ def test_ksp_context_dispatch(ctx):
         assert st.iterations == so.iterations and np.array_equal(x, xo)
     with pytest.raises(kb.Unsupported):
         kb.KspContext(kb.SolverKind.Minres, S).solve_context(bs, np.zeros(ns))
+
+
+@pytest.mark.parametrize("order", ["jacobi_then_ilu", "ilu_then_jacobi"])
+@pytest.mark.parametrize("solver", ["pcg", "gmres", "bicgstab"])
+def test_graph_cache_survives_preconditioner_replacement(ctx, order, solver):
+    """the solvers' CUDA-graph caches live on the operator; they must never be replayed for a new
+    preconditioner that happens to be allocated where a destroyed one lived.  Solve with one preconditioner, destroy
+    it, solve with the other kind on the same operator: every solve is bit-identical to the oracle."""
+    import kryst_b200 as kb
+    A, Ao = _mk("poisson3d", 14, ctx)
+    b = o.spmv(Ao, np.ones(Ao.n))
+    seq = ["jacobi", "ilu0", "jacobi", "ilu0"] if order == "jacobi_then_ilu" else ["ilu0", "jacobi", "ilu0", "jacobi"]
+    for kind in seq:
+        pc = (kb.Jacobi() if kind == "jacobi" else kb.Ilu0()).setup(A)
+        pco = o.OPc.jacobi(Ao) if kind == "jacobi" else o.OPc.ilu0(Ao)
+        x = np.zeros(Ao.n)
+        if solver == "pcg":
+            st = kb.PcgSolver(1e-8, 2000).solve(A, pc, b, x)
+            rc, xo, so, _ = o.pcg(Ao, pco, b, np.zeros(Ao.n), 1e-8, 2000)
+        elif solver == "gmres":
+            st = kb.GmresSolver(10, 1e-8, 2000).solve(A, pc, b, x)
+            rc, xo, so = o.gmres(Ao, pco, b, np.zeros(Ao.n), 10, 1e-8, 2000, mode=o.MODE_LEFT, variant=o.GMRES_CGS2)
+        else:
+            st = kb.BiCgStabSolver(1e-8, 2000, textbook=True).solve(A, pc, b, x)
+            rc, xo, so = o.bicgstab(Ao, pco, b, np.zeros(Ao.n), 1e-8, 2000, variant=o.BICG_TEXTBOOK)
+        assert rc == 0 and st.iterations == so.iterations and st.final_residual == so.final_residual, (kind, st.iterations, so.iterations)
+        assert np.array_equal(x, xo), kind
+        pc.close()      # the next preconditioner may reuse this handle's address
