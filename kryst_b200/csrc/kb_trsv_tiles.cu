@@ -178,6 +178,7 @@ __global__ void __launch_bounds__(KB_THREADS) kb_trsv_tiles(KbTileArgs a) {
 }
 
 // ---- host ------------------------------------------------------------------------------------------------------
+void kb_tiles_grid(const KbTileSolve* t, int* nx, int* ny, int* nz) { *nx = t->nx; *ny = t->ny; *nz = t->nz; }
 void kb_tiles_free(KbTileSolve* t) {
     if (!t) return;
     KB_FREE(t->order[0]); KB_FREE(t->order[1]); KB_FREE(t->flags);

@@ -38,27 +38,66 @@ def test_ilu0_factors_levels_apply_bit_exact(ctx, kind, N):
     assert np.array_equal(z, o.ilu0_apply(Ao, lu_o, dp_o, iud_o, r))
 
 
-@pytest.mark.parametrize("tiles", ["0", "1"])
-@pytest.mark.parametrize("kind,N", [("convdiff2d", 70), ("poisson2d", 130), ("poisson3d", 20), ("convdiff3d", 17), ("varcoef27", 10)])
-def test_trsv_schedules_bit_exact(ctx, kind, N, tiles):
-    """Both triangular-solve schedules on the same factors: block-wavefront tiles (5-/7-point box grids, detected from
-    the pattern; sizes are not multiples of the tile shape) and the level-scheduled persistent kernel (forced with
-    KB_TRSV_TILES=0; the 27-point operator always takes it)."""
-    import os
+@pytest.mark.parametrize("sched", ["levels", "tiles", "march"])
+@pytest.mark.parametrize("kind,N", [("convdiff2d", 70), ("poisson2d", 130), ("poisson3d", 20), ("convdiff3d", 17), ("varcoef27", 10),
+                                    ("poisson3d", 41), ("convdiff2d", 201)])
+def test_trsv_schedules_bit_exact(ctx, kind, N, sched, monkeypatch):
+    """All three triangular-solve schedules on the same factors: pencil-marching warps (default for full 5-/7-point
+    box-grid stencils, detected from the pattern; sizes are not multiples of the pencil / tile shapes), block-wavefront
+    tiles (KB_TRSV_MARCH=0) and the level-scheduled persistent kernel (KB_TRSV_TILES=0; the 27-point operator always
+    takes it).  Repeated applies exercise the epoch-tagged mailbox (never cleared between applies)."""
     import kryst_b200 as kb
     A, Ao = _mk(kind, N, ctx)
-    os.environ["KB_TRSV_TILES"] = tiles
-    try:
-        pc = kb.Ilu0().setup(A)
-    finally:
-        del os.environ["KB_TRSV_TILES"]
+    monkeypatch.setenv("KB_TRSV_TILES", "0" if sched == "levels" else "1")
+    monkeypatch.setenv("KB_TRSV_MARCH", "1" if sched == "march" else "0")      # 1 forces the march on 3-D grids too
+    pc = kb.Ilu0().setup(A)
     st, lu_o, dp_o, iud_o, bad = o.ilu0_factor(Ao)
     rng = np.random.default_rng(5)
-    for _ in range(3):
+    for _ in range(4):
         r = rng.standard_normal(Ao.n)
         z = np.zeros(Ao.n)
         pc.apply(r, z)
         assert np.array_equal(z, o.ilu0_apply(Ao, lu_o, dp_o, iud_o, r))
+
+
+@pytest.mark.parametrize("warps", ["1", "3", "16"])
+def test_trsv_march_more_pencils_than_warps(ctx, warps, monkeypatch):
+    """Pencils are handed to warps in level order; with few warps per CTA and a capped grid every warp marches
+    several pencils one after the other (the C5-shard regime)."""
+    import kryst_b200 as kb
+    monkeypatch.setenv("KB_MARCH_GROUP", {"1": "1", "3": "2", "16": "4"}[warps])     # 1, 4, 16 pencils per CTA
+    monkeypatch.setenv("KB_MARCH_GRID", "3")                                          # few CTAs: every CTA marches several groups
+    monkeypatch.setenv("KB_TRSV_MARCH", "1")
+    A, Ao = _mk("convdiff3d", 33, ctx)
+    pc = kb.Ilu0().setup(A)
+    st, lu_o, dp_o, iud_o, bad = o.ilu0_factor(Ao)
+    r = np.random.default_rng(2).standard_normal(Ao.n)
+    z = np.zeros(Ao.n)
+    pc.apply(r, z)
+    assert np.array_equal(z, o.ilu0_apply(Ao, lu_o, dp_o, iud_o, r))
+
+
+def test_trsv_march_falls_back_without_a_full_stencil(ctx):
+    """A box-grid pattern with one coupling removed is not a full stencil: the march kernel must decline it (the tile
+    kernel handles absent entries) and the result stays bit-exact."""
+    import kryst_b200 as kb
+    from kryst_b200 import stencils
+    n, rp, ci, v = stencils.stencil("poisson3d", 12)
+    rp, ci, v = rp.astype(np.int64), ci.astype(np.int64), v.copy()
+    row = 700
+    k = [p for p in range(rp[row], rp[row + 1]) if ci[p] == row - 1][0]        # drop (row, row-1) and its mirror
+    k2 = [p for p in range(rp[row - 1], rp[row]) if ci[p] == row][0]
+    keep = np.ones(ci.size, bool); keep[[k, k2]] = False
+    cnt = np.diff(rp); cnt[row] -= 1; cnt[row - 1] -= 1
+    rp2 = np.concatenate([[0], np.cumsum(cnt)]).astype(np.uint64)
+    A = kb.DeviceCsr.from_csr(n, n, rp2, ci[keep].astype(np.uint64), v[keep], ctx)
+    Ao = o.OCsr(n, n, rp2, ci[keep].astype(np.uint64), v[keep])
+    pc = kb.Ilu0().setup(A)
+    st, lu_o, dp_o, iud_o, bad = o.ilu0_factor(Ao)
+    r = np.random.default_rng(4).standard_normal(n)
+    z = np.zeros(n)
+    pc.apply(r, z)
+    assert np.array_equal(z, o.ilu0_apply(Ao, lu_o, dp_o, iud_o, r))
 
 
 def test_trsv_tiles_on_a_slab_submatrix(ctx):
