@@ -68,7 +68,7 @@ struct KbP2PHost {
     void* local = nullptr;                 // my mailbox (cudaMalloc)
     void* peers[KB_MAX_RANKS] = {nullptr}; // opened handles (peers[rank] == local)
 };
-static size_t mailbox_bytes(int size) { return (size_t)2 * size * KB_AR_MAX * sizeof(double) + (size_t)2 * size * sizeof(unsigned long long) + 64; }
+static size_t mailbox_bytes(int size) { return (size_t)2 * size * KB_AR_MAX * 16 + (size_t)2 * size * sizeof(unsigned long long) + 64; }
 
 // collective: allocate `bytes` locally (zeroed), export it, and map every peer's allocation.
 // ptrs[q] = address of rank q's allocation in this process (ptrs[me] = local).
@@ -130,7 +130,7 @@ static int kb_p2p_setup(kb_ctx_s* c) {
     for (int q = 0; q < c->size; ++q) {
         P->peers[q] = ptrs[q];
         P->dev.vals[q] = reinterpret_cast<double*>(ptrs[q]);
-        P->dev.flags[q] = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(ptrs[q]) + (size_t)2 * c->size * KB_AR_MAX * sizeof(double));
+        P->dev.flags[q] = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(ptrs[q]) + (size_t)2 * c->size * KB_AR_MAX * 16);
     }
     P->local = ptrs[c->rank];
     P->dev.rank = c->rank; P->dev.size = c->size;
@@ -242,19 +242,6 @@ extern "C" int kb_comm_barrier(kb_ctx c) {
 }
 
 // ---- partition maps ----------------------------------------------------------------------------------------
-struct KbHaloDev {                 // device view of the peer-memory halo exchange
-    int rank, size, nsend, nghost, n_loc;
-    long long gstride;                           // my ghost_in parity stride (doubles)
-    long long peer_gstride[KB_MAX_RANKS];
-    double* ghost[KB_MAX_RANKS];                 // rank q's ghost_in[2][gstride_q]
-    unsigned long long* flags[KB_MAX_RANKS];     // rank q's flags[2][size]   : flags[q][par*size + src] = seq pushed by src
-    unsigned long long* acks[KB_MAX_RANKS];      // rank q's acks[size]       : acks[q][dst] = last push of q consumed by dst
-    int is_dest[KB_MAX_RANKS], is_src[KB_MAX_RANKS];
-    const int* send_idx; const int* send_q; const int* send_pos;
-    unsigned long long* seqs;                    // [0] pushes done, [1] receives done (device counters)
-    unsigned* tickets;                           // [0] push, [1] recv last-block tickets
-    unsigned* err;
-};
 struct KbHalo {
     int p = 1;
     std::vector<int> send_cnt, send_off, recv_cnt, recv_off;   // per peer rank
@@ -265,6 +252,7 @@ struct KbHalo {
     bool p2p = false;
     void* ptrs[KB_MAX_RANKS] = {nullptr};
     int* send_q = nullptr; int* send_pos = nullptr;
+    int* tile_send_ptr = nullptr; int* ts_idx = nullptr; int* ts_q = nullptr; int* ts_pos = nullptr; int* tile_perm = nullptr;
     unsigned long long* seqs = nullptr; unsigned* tickets = nullptr;
     KbHaloDev dev{};
     KbHaloDev* dev_copy = nullptr;
@@ -274,7 +262,7 @@ struct KbHalo {
 void kb_halo_free(KbHalo* h) {
     if (!h) return;
     if (h->p2p && h->ctx) kb_ipc_release(h->ctx, h->ptrs);
-    KB_FREE(h->send_idx); KB_FREE(h->send_buf); KB_FREE(h->send_q); KB_FREE(h->send_pos); KB_FREE(h->seqs); KB_FREE(h->tickets); KB_FREE(h->dev_copy);
+    KB_FREE(h->send_idx); KB_FREE(h->send_buf); KB_FREE(h->send_q); KB_FREE(h->send_pos); KB_FREE(h->tile_send_ptr); KB_FREE(h->ts_idx); KB_FREE(h->ts_q); KB_FREE(h->ts_pos); KB_FREE(h->tile_perm); KB_FREE(h->seqs); KB_FREE(h->tickets); KB_FREE(h->dev_copy);
     delete h;
 }
 
@@ -498,6 +486,34 @@ int kb_csr_build_dist(kb_csr_s* A) {
                     KB_CUDA(cudaMemcpyAsync(H->send_pos, hp.data(), (size_t)H->nsend * sizeof(int), cudaMemcpyHostToDevice, c->stream));
                 }
                 D.send_idx = H->send_idx; D.send_q = H->send_q; D.send_pos = H->send_pos;
+                {   // tile-sorted copy of the send list (stable: ascending row inside a tile, destinations interleaved)
+                    std::vector<int> hidx((size_t)H->nsend), ord((size_t)H->nsend), tptr((size_t)A->ntiles + 1, 0);
+                    if (H->nsend) KB_CUDA(cudaMemcpyAsync(hidx.data(), H->send_idx, (size_t)H->nsend * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+                    KB_CUDA(cudaStreamSynchronize(c->stream));
+                    for (int k = 0; k < H->nsend; ++k) { ord[k] = k; tptr[(size_t)(hidx[k] / KB_TILE) + 1]++; }
+                    int nst = 0;
+                    for (int t = 0; t < A->ntiles; ++t) { nst += tptr[(size_t)t + 1] > 0; tptr[(size_t)t + 1] += tptr[t]; }
+                    std::stable_sort(ord.begin(), ord.end(), [&](int x, int y) { return hidx[x] / KB_TILE < hidx[y] / KB_TILE; });
+                    std::vector<int> ti((size_t)H->nsend), tq((size_t)H->nsend), tp((size_t)H->nsend);
+                    for (int k = 0; k < H->nsend; ++k) { ti[k] = hidx[ord[k]]; tq[k] = hq[ord[k]]; tp[k] = hp[ord[k]]; }
+                    KB_TRY(kb_alloc(&H->tile_send_ptr, (size_t)A->ntiles + 1)); KB_TRY(kb_alloc(&H->ts_idx, (size_t)H->nsend + 1));
+                    KB_TRY(kb_alloc(&H->ts_q, (size_t)H->nsend + 1)); KB_TRY(kb_alloc(&H->ts_pos, (size_t)H->nsend + 1));
+                    KB_CUDA(cudaMemcpyAsync(H->tile_send_ptr, tptr.data(), tptr.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+                    if (H->nsend) {
+                        KB_CUDA(cudaMemcpyAsync(H->ts_idx, ti.data(), ti.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+                        KB_CUDA(cudaMemcpyAsync(H->ts_q, tq.data(), tq.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+                        KB_CUDA(cudaMemcpyAsync(H->ts_pos, tp.data(), tp.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+                    }
+                    KB_CUDA(cudaStreamSynchronize(c->stream));
+                    std::vector<int> perm;
+                    perm.reserve((size_t)A->ntiles);
+                    for (int t = 0; t < A->ntiles; ++t) if (tptr[(size_t)t + 1] > tptr[t]) perm.push_back(t);
+                    for (int t = 0; t < A->ntiles; ++t) if (tptr[(size_t)t + 1] == tptr[t]) perm.push_back(t);
+                    KB_TRY(kb_alloc(&H->tile_perm, (size_t)A->ntiles));
+                    KB_CUDA(cudaMemcpyAsync(H->tile_perm, perm.data(), perm.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+                    KB_CUDA(cudaStreamSynchronize(c->stream));
+                    D.tile_send_ptr = H->tile_send_ptr; D.ts_idx = H->ts_idx; D.ts_q = H->ts_q; D.ts_pos = H->ts_pos; D.n_send_tiles = nst; D.tile_perm = H->tile_perm;
+                }
                 D.seqs = H->seqs; D.tickets = H->tickets;
                 D.err = reinterpret_cast<KbP2PHost*>(c->p2p)->dev.err;
                 H->push_grid = std::max(1, std::min(2 * c->sm_count, (H->nsend + KB_THREADS - 1) / KB_THREADS));   // one value per thread: latency-bound kernel
@@ -578,4 +594,13 @@ bool kb_halo_fill_args(kb_csr_s* A, KbSpmvArgs* a) {
     for (int q = 0; q < D.size; ++q) if (D.is_src[q]) m |= 1u << q;
     a->hsrc_mask = m;
     return true;
+}
+
+// Fused push (kb_halo_push_tile, kb_p2p.cuh): available on the peer-memory path when this rank has something to send.
+// (A rank that only receives keeps the separate push launch: somebody has to write the acknowledgements.)
+const KbHaloDev* kb_halo_fused_dev(kb_csr_s* A) {
+    static const bool off = getenv("KB_HALO_FUSE") && atoi(getenv("KB_HALO_FUSE")) == 0;
+    KbHalo* H = A->halo;
+    if (off || !H || !H->p2p || H->dev.n_send_tiles <= 0) return nullptr;
+    return H->dev_copy;
 }

@@ -17,6 +17,7 @@ struct KbSpmvArgs;
 bool kb_halo_fill_args(kb_csr_s* A, KbSpmvArgs* a);   // peer path: point the SpMV at the IPC mailbox (false: NCCL path)
 const KbP2PDev* kb_p2p_dev(kb_ctx_s* c);        // host copy
 const KbP2PDev* kb_p2p_dev_ptr(kb_ctx_s* c);    // device-resident copy (kernel argument)
+const KbHaloDev* kb_halo_fused_dev(kb_csr_s* A); // non-null: the operand's producer may push the halo itself (kb_halo_push_tile)
 
 // What the last CTA of a reducing kernel does with the local canonical sums (called by ALL its threads):
 //   single GPU            : thread 0 runs the scalar epilogue `fin`
@@ -123,7 +124,7 @@ static int kb_launch_spmv_tiles(kb_csr_s* A, KbSpmvArgs a, Epi epi, const int* l
 // CTA of the second one, so the reduction tree is unchanged.
 template <class Epi, bool RESID>
 static int kb_launch_spmv(kb_csr_s* A, const double* x, double* y, const double* b, const double* w, double* partials,
-                          size_t pstride, Epi epi, double* halo_x = nullptr) {
+                          size_t pstride, Epi epi, double* halo_x = nullptr, bool halo_prepushed = false) {
     kb_ctx_s* c = A->ctx;
     const bool dist = halo_x != nullptr && A->dist && c->size > 1;
     if (A->n == 0 && !dist) return KB_OK;
@@ -131,7 +132,7 @@ static int kb_launch_spmv(kb_csr_s* A, const double* x, double* y, const double*
     a.row_ptr = A->row_ptr; a.col = A->col; a.vals = A->vals; a.x = x; a.y = y; a.b = b; a.w = w;
     a.n = (int)A->n; a.ntiles_total = A->ntiles;
     a.partials = partials; a.pstride = pstride; a.ticket = c->ticket;
-    if (dist) KB_TRY(kb_halo_begin(A, halo_x));
+    if (dist && !halo_prepushed) KB_TRY(kb_halo_begin(A, halo_x));     // prepushed: the kernel that produced x pushed its boundary entries itself
     static const int split_env = getenv("KB_HALO_SPLIT") ? atoi(getenv("KB_HALO_SPLIT")) : -1;
     // Interior/boundary split hides the NVLink latency behind the interior rows but costs one more launch.
     // Measured on B200 (256^3, 2 and 8 GPUs) the single launch whose CTAs wait on the flags themselves is

@@ -165,6 +165,18 @@ struct PcgXpayOp : KbRedBase {        // K4: p = z + beta p  (pcg.rs:215-217)
     __device__ void finish_block(double*) const {}
 };
 
+// K4 on a shard: p = z + beta p, and the tile's boundary entries of the new p go straight into the neighbours' ghost
+// mailboxes (NVLink peer stores) - the separate 29 us kb_halo_push launch of round 1 is gone, and the transfer
+// overlaps the rest of this kernel and the launch gap before the SpMV that consumes it.
+__global__ void __launch_bounds__(KB_THREADS) kb_pcg_xpay_push(PcgXpayOp op, const KbHaloDev* __restrict__ hp) {
+    if (op.skip()) return;
+    const int tile = hp->tile_perm[blockIdx.x];            // sending tiles first
+    const long long i = (long long)tile * KB_TILE + 2 * threadIdx.x;
+    if (i + 1 < op.n) op.pair(i, true, nullptr);
+    else if (i < op.n) op.pair(i, false, nullptr);
+    kb_halo_push_tile(*hp, op.p, tile);
+}
+
 // ---- single-reduction variant (Chronopoulos-Gear) ---------------------------------------
 // One iteration = two kernels and ONE reduction (one all-reduce on shards) instead of three kernels and two:
 //   S1  p = u + beta p ; s = w + beta s ; x += alpha p ; r -= alpha s ; u = D^-1 r ; local sums of r.u and the norm
@@ -294,10 +306,11 @@ static int pcg_ws_get(kb_csr_s* A, uint64_t hist_cap, KbPcgWs** out) {
 template <bool DIST>
 static int pcg_launch_iteration(kb_csr_s* A, const kb_pc_s* pc, KbPcgWs* w) {
     kb_ctx_s* c = A->ctx;
+    const KbHaloDev* fused_push = DIST ? kb_halo_fused_dev(A) : nullptr;
     const double* inv = pc ? pc->inv_diag : nullptr;
     {   // K2
         KbSpmvEpi<PcgApFin, true, false> epi; epi.ctl = w->ctl; epi.fin = kb_make_fin(c, PcgApFin{w->ctl}, DIST, w->slots, 1);
-        KB_TRY((kb_launch_spmv<KbSpmvEpi<PcgApFin, true, false>, false>(A, w->p, w->ap, nullptr, w->p, w->partials, w->pstride, epi, DIST ? w->p : nullptr)));
+        KB_TRY((kb_launch_spmv<KbSpmvEpi<PcgApFin, true, false>, false>(A, w->p, w->ap, nullptr, w->p, w->partials, w->pstride, epi, DIST ? w->p : nullptr, fused_push != nullptr)));
         if (DIST) KB_TRY((kb_finish_dist<PcgApFin>(c, PcgApFin{w->ctl}, w->ctl, w->slots, 1)));
     }
     if (pc && pc->kind != KB_PC_JACOBI) {   // K3 with a generic preconditioner
@@ -322,7 +335,8 @@ static int pcg_launch_iteration(kb_csr_s* A, const kb_pc_s* pc, KbPcgWs* w) {
     {   // K4
         PcgXpayOp op; op.n = (long long)w->n; op.partials = nullptr; op.pstride = 0; op.ticket = c->ticket;
         op.z = w->z; op.p = w->p; op.ctl = w->ctl;
-        { KbLaunch L(c, KB_K_XPAY); kb_tile_kernel<<<A->ntiles, KB_THREADS, 0, c->stream>>>(op); }
+        if (fused_push) { KbLaunch L(c, KB_K_XPAY); kb_pcg_xpay_push<<<A->ntiles, KB_THREADS, 0, c->stream>>>(op, fused_push); }
+        else { KbLaunch L(c, KB_K_XPAY); kb_tile_kernel<<<A->ntiles, KB_THREADS, 0, c->stream>>>(op); }
         KB_CUDA(cudaGetLastError());
     }
     return KB_OK;
@@ -444,6 +458,8 @@ extern "C" int kb_pcg_solve(kb_csr A, kb_pc pc, const double* b, double* x, doub
         // Optional: the whole loop in one persistent cooperative kernel (KB_PCG_PERSISTENT=1).  Measured on B200 the
         // software grid barriers (3 per iteration over 296 CTAs, ~3 us each) cost more than the three kernel
         // boundaries of the graph path (C1: 22.3 vs 18.5 us per iteration), so it is opt-in.
+        // the loop's SpMV expects p's halo already pushed by the kernel that produced p: push the initial p = z here
+        if (dist && !single_red && kb_halo_fused_dev(A) && (st = kb_halo_begin(A, w->p)) != KB_OK) break;
         const int mega_env = getenv("KB_PCG_PERSISTENT") ? atoi(getenv("KB_PCG_PERSISTENT")) : 0;
         const bool mega_ok = !single_red && !dist && jacobi_like && A->kind == 2 && !A->prod && !profile && max_iters > 0;
         const bool mega = mega_ok && mega_env != 0;
