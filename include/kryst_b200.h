@@ -16,7 +16,8 @@
  *   SubmatrixExtract::submatrix                      src/matrix/sparse.rs:72-93 (used by asm.rs:58-65)
  *   SolveStats{iterations,final_residual,converged}  src/utils/convergence.rs:9-14
  *   KError                                           src/error.rs:6-19
- *   Comm{rank,size,barrier,all_reduce}               src/parallel/mod.rs:4-35
+ *   Comm{rank,size,barrier,scatter,gather,all_reduce,dot}   src/parallel/mod.rs:4-35 ; DistributedInnerProduct  src/core/wrappers.rs:134-156
+ *   KspContext::solve_context / SolverKind / PC<T>   src/context/ksp_context.rs:25-148, src/context/pc_context.rs:36-76
  *
  * Conventions: plain pointers and sizes only; no C++/torch types.  Host pointers are borrowed
  * for the duration of the call.  All device memory, streams and communicators are owned by the
@@ -78,6 +79,14 @@ int kb_comm_rank(kb_ctx ctx);
 int kb_comm_size(kb_ctx ctx);
 int kb_comm_barrier(kb_ctx ctx);
 int kb_comm_all_reduce(kb_ctx ctx, double local, double* global);   /* rank-ordered sum: deterministic */
+/* Comm::dot (parallel/mod.rs:19-22) and DistributedInnerProduct::{dot,norm} (src/core/wrappers.rs:134-156): every rank
+ * passes its slice; canonical-tree local part on the GPU, rank-ordered sum across ranks.  Collective.                   */
+int kb_comm_dot(kb_ctx ctx, uint64_t n_local, const double* a, const double* b, double* out);
+int kb_comm_norm(kb_ctx ctx, uint64_t n_local, const double* x, double* out);
+/* Comm::scatter / Comm::gather (parallel/mod.rs:9-16, mpi_comm.rs:74-109): equal chunks of bytes_per_rank bytes; `global`
+ * (scatter) and `out` (gather) are read / written on `root` only.  Host slices; collective.                             */
+int kb_comm_scatter(kb_ctx ctx, const void* global, uint64_t bytes_per_rank, void* out, int root);
+int kb_comm_gather(kb_ctx ctx, const void* local, uint64_t bytes_per_rank, void* out, int root);
 /* uniform row-chunk partition, chunk = ceil(n/p) (src/preconditioner/asm.rs:46-57); host-only */
 void kb_partition_range(uint64_t n, uint64_t p, uint64_t r, uint64_t* lo, uint64_t* hi);
 
@@ -115,6 +124,18 @@ int kb_norm(kb_ctx ctx, uint64_t n, const double* x, double* out);
 /* ---- preconditioners: Preconditioner::setup (create) / apply (mod.rs:8-13) ------------- */
 int kb_pc_create_jacobi(kb_csr a, kb_pc* out);         /* jacobi.rs:53-73 values, direct diagonal read */
 int kb_pc_create_ilu0(kb_csr a, kb_pc* out);           /* textbook ILU(0); on a shard: block-Jacobi ILU(0) */
+/* AdditiveSchwarz::new(overlap, subdomains) + setup (src/preconditioner/asm.rs:34-65), apply = asm.rs:76-116: z = sum over
+ * blocks, in order, of R_b^T inner(A_b, R_b r), A_b = a.submatrix(block rows).  sub_ptr == NULL: nsub uniform row chunks
+ * (asm.rs:46-57); else block b = sub_idx[sub_ptr[b] .. sub_ptr[b+1]) in the caller's order (rows of a block distinct).
+ * inner: one application of the block's ILU(0) (block-Jacobi ILU(0) for disjoint blocks) or of its Jacobi.  overlap = 0 is
+ * the reference (which stores `overlap` and never reads it); overlap = k grows each set by k layers of graph neighbours
+ * (PETSc PCASM) and orders it ascending.  Single-GPU operators; on a shard kb_pc_create_ilu0 is the per-GPU block.      */
+enum { KB_ASM_INNER_ILU0 = 0, KB_ASM_INNER_JACOBI = 1 };
+int kb_pc_create_asm(kb_csr a, uint64_t overlap, uint64_t nsub, const uint64_t* sub_ptr, const uint64_t* sub_idx,
+                     int inner, kb_pc* out);
+uint64_t kb_pc_asm_num_blocks(kb_pc pc);
+uint64_t kb_pc_asm_block_size(kb_pc pc, uint64_t b);
+int kb_pc_asm_block_indices(kb_pc pc, uint64_t b, uint64_t* out);   /* after overlap growth */
 int kb_pc_apply(kb_pc pc, const double* r, double* z); /* host slices */
 int kb_pc_apply_device(kb_pc pc, const double* d_r, double* d_z);
 int kb_pc_destroy(kb_pc pc);
@@ -131,6 +152,17 @@ int kb_pc_ilu0_get_levels(kb_pc pc, int upper, uint64_t* nlevels, uint64_t* leve
 #define KB_FLAG_NO_GRAPH    8u    /* plain launches instead of CUDA-graph replay                   */
 #define KB_FLAG_SINGLE_REDUCTION 16u /* PCG: Chronopoulos-Gear recurrences, ONE fused reduction (one all-reduce on
                                         shards) per iteration - what pcg.rs:36-37's flag is named after; SURVEY 8(f3) */
+
+#define KB_FLAG_HISTORY 32u       /* record the per-iteration residuals on the device; fetch with kb_get_history        */
+#define KB_FLAG_MONITOR 64u       /* slow mode: one iteration (GMRES family: one restart cycle) per launch batch,
+                                     the observer set with kb_set_monitor runs on the host for every new history entry */
+/* monitor: Option<Box<dyn FnMut(usize, T)>> (pcg.rs:43,81-86,143-145,196-198; fgmres.rs:45-46,92-97,286-289) */
+typedef void (*kb_monitor_fn)(uint64_t iteration, double residual, void* user);
+int kb_set_monitor(kb_csr a, kb_monitor_fn fn, void* user);        /* fn == NULL clears; used by solves with KB_FLAG_MONITOR */
+/* residual_history (pcg.rs:45,146,199; fgmres.rs:48,290) of the last solve on `a` that ran with KB_FLAG_HISTORY or
+ * KB_FLAG_MONITOR: PCG = initial norm + one entry per iteration; GMRES / FGMRES = |g[j+1]| per inner iteration;
+ * BiCGStab = ||r|| per iteration (the reference keeps no history for those two).  len = entries produced.               */
+int kb_get_history(kb_csr a, double* out, uint64_t cap, uint64_t* len);
 
 /* CgNormType (pcg.rs:25) */
 enum { KB_NORM_PRECONDITIONED = 0, KB_NORM_UNPRECONDITIONED = 1, KB_NORM_NATURAL = 2, KB_NORM_NONE = 3 };
@@ -157,6 +189,31 @@ int kb_fgmres_solve(kb_csr a, kb_pc pc, const double* b, double* x, uint64_t res
  * (pc ignored, absolute tol); KB_FLAG_TEXTBOOK = right-preconditioned, relative tol.             */
 int kb_bicgstab_solve(kb_csr a, kb_pc pc, const double* b, double* x, double tol, uint64_t max_iters,
                       uint32_t flags, kb_stats* stats);
+
+/* ---- the caller above the path: PC<T> factory and KspContext::solve_context ------------------------------ */
+/* PC<T> (src/context/pc_context.rs:36-76), same variant order */
+enum { KB_PCK_JACOBI = 0, KB_PCK_SSOR = 1, KB_PCK_ILU0 = 2, KB_PCK_ILUP = 3, KB_PCK_ILUT = 4, KB_PCK_CHEBYSHEV = 5, KB_PCK_APPROXINV = 6,
+       KB_PCK_BLOCK_JACOBI = 7, KB_PCK_MULTICOLOR = 8, KB_PCK_AMG = 9, KB_PCK_ADDITIVE_SCHWARZ = 10 };
+typedef struct kb_pc_spec {
+    int32_t kind;                 /* KB_PCK_* */
+    uint64_t fill;                /* Ilup { fill } / Ilut { fill, .. } */
+    double droptol;               /* Ilut { droptol } */
+    uint64_t overlap;             /* AdditiveSchwarz overlap layers (0 = the reference) */
+    uint64_t nblocks;             /* BlockJacobi { blocks } / AdditiveSchwarz subdomains (uniform chunks when block_ptr is NULL) */
+    const uint64_t* block_ptr;    /* [nblocks + 1] */
+    const uint64_t* block_idx;
+} kb_pc_spec;
+/* Device kinds: Jacobi, Ilu0, Ilup{fill:0}, BlockJacobi{blocks}, AdditiveSchwarz; the rest -> KB_UNSUPPORTED.           */
+int kb_pc_create_from_spec(kb_csr a, const kb_pc_spec* spec, kb_pc* out);
+/* SolverKind (src/context/ksp_context.rs:25-48), same variant order */
+enum { KB_KSP_CG = 0, KB_KSP_PCG = 1, KB_KSP_GMRES_LEFT = 2, KB_KSP_GMRES_RIGHT = 3, KB_KSP_FGMRES = 4, KB_KSP_BICGSTAB = 5,
+       KB_KSP_CGS = 6, KB_KSP_QMR = 7, KB_KSP_TFQMR = 8, KB_KSP_MINRES = 9, KB_KSP_CGNR = 10 };
+/* KspContext{kind, tol, max_it, restart} (ksp_context.rs:54-69); `a` and `pc` are passed alongside */
+typedef struct kb_ksp { int32_t kind; double tol; uint64_t max_it; uint64_t restart; } kb_ksp;
+/* KspContext::solve_context(&mut self, b, x, comm) (ksp_context.rs:88-148): builds the solver named by `kind` with
+ * (tol, max_it[, restart]) and forwards to its solve; Cg ignores pc (cg.rs:114-115); Fgmres takes pc as the flexible
+ * preconditioner; a row-partitioned operator carries its communicator (the reference accepts `comm` and never uses it). */
+int kb_ksp_solve(kb_csr a, kb_pc pc, const kb_ksp* ksp, const double* b, double* x, uint32_t flags, kb_stats* stats);
 
 /* ---- measurement hooks (bench.py) ------------------------------------------------------ */
 #define KB_PROF_CLASSES 12

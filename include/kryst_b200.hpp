@@ -56,6 +56,17 @@ public:
     // InnerProduct<Vec<f64>> for () (src/core/wrappers.rs:87-129)
     double dot(const std::vector<double>& x, const std::vector<double>& y) const { double d = 0; check(kb_dot(h_, x.size(), x.data(), y.data(), &d)); return d; }
     double norm(const std::vector<double>& x) const { double d = 0; check(kb_norm(h_, x.size(), x.data(), &d)); return d; }
+    // Comm::dot (parallel/mod.rs:19-22), DistributedInnerProduct::{dot,norm} (core/wrappers.rs:134-156): every rank passes its slice
+    double comm_dot(const std::vector<double>& a, const std::vector<double>& b) const { double d = 0; check(kb_comm_dot(h_, a.size(), a.data(), b.data(), &d)); return d; }
+    double comm_norm(const std::vector<double>& x) const { double d = 0; check(kb_comm_norm(h_, x.size(), x.data(), &d)); return d; }
+    // Comm::scatter / Comm::gather (parallel/mod.rs:9-16): equal chunks; `global` is read and `out` written on root only
+    template <class T> void scatter(const std::vector<T>& global, std::vector<T>& out, int root) const {
+        check(kb_comm_scatter(h_, global.data(), out.size() * sizeof(T), out.data(), root));
+    }
+    template <class T> void gather(const std::vector<T>& local, std::vector<T>& out, int root) const {
+        if (rank() == root) out.assign(local.size() * static_cast<size_t>(size()), T()); else out.clear();
+        check(kb_comm_gather(h_, local.data(), local.size() * sizeof(T), out.data(), root));
+    }
 private:
     kb_ctx h_ = nullptr;
 };
@@ -126,6 +137,62 @@ public:
     }
 };
 
+// AdditiveSchwarz::new(overlap, subdomains) (src/preconditioner/asm.rs:17-116) on one GPU: sub-operators from SubmatrixExtract,
+// one ILU(0) (or Jacobi) application per block as the inner solve, block results summed in subdomain order.
+class AdditiveSchwarz : public Preconditioner {
+public:
+    enum class Inner { Ilu0 = KB_ASM_INNER_ILU0, Jacobi = KB_ASM_INNER_JACOBI };
+    AdditiveSchwarz(size_t overlap, std::vector<std::vector<uint64_t>> subdomains, Inner inner = Inner::Ilu0)
+        : overlap_(overlap), nsub_(subdomains.size()), sub_(std::move(subdomains)), inner_(inner) {}
+    // `Vec::with_capacity(p)` idiom of the reference: p uniform row chunks (asm.rs:46-57)
+    AdditiveSchwarz(size_t overlap, size_t p, Inner inner = Inner::Ilu0) : overlap_(overlap), nsub_(p), inner_(inner) {}
+    void setup(const DeviceCsr& a) override {
+        std::vector<uint64_t> ptr, idx;
+        if (!sub_.empty()) {
+            ptr.push_back(0);
+            for (const auto& s : sub_) { idx.insert(idx.end(), s.begin(), s.end()); ptr.push_back(idx.size()); }
+        }
+        kb_pc h = nullptr;
+        int st = kb_pc_create_asm(a.handle(), overlap_, nsub_, sub_.empty() ? nullptr : ptr.data(), sub_.empty() ? nullptr : idx.data(), static_cast<int>(inner_), &h);
+        if (st != KB_OK) { uint64_t row = h ? kb_pc_bad_row(h) : 0; std::string msg = kb_last_error(); kb_pc_destroy(h); throw KError(st, msg, row); }
+        reset(h);
+    }
+private:
+    size_t overlap_, nsub_;
+    std::vector<std::vector<uint64_t>> sub_;
+    Inner inner_;
+};
+
+// PC<T> (src/context/pc_context.rs:36-76) + the factory the reference's enum lacks: PC::Ilu0().build(a)
+struct PC {
+    int kind = KB_PCK_JACOBI; uint64_t fill = 0; double droptol = 0.0; uint64_t overlap = 0, nblocks = 0;
+    std::vector<std::vector<uint64_t>> blocks;
+    static PC Jacobi() { PC p; p.kind = KB_PCK_JACOBI; return p; }
+    static PC Ssor() { PC p; p.kind = KB_PCK_SSOR; return p; }
+    static PC Ilu0() { PC p; p.kind = KB_PCK_ILU0; return p; }
+    static PC Ilup(uint64_t fill) { PC p; p.kind = KB_PCK_ILUP; p.fill = fill; return p; }
+    static PC Ilut(uint64_t fill, double droptol) { PC p; p.kind = KB_PCK_ILUT; p.fill = fill; p.droptol = droptol; return p; }
+    static PC BlockJacobi(std::vector<std::vector<uint64_t>> b) { PC p; p.kind = KB_PCK_BLOCK_JACOBI; p.blocks = std::move(b); return p; }
+    static PC AMG() { PC p; p.kind = KB_PCK_AMG; return p; }
+    static PC AdditiveSchwarz(uint64_t overlap = 0, uint64_t nblocks = 1) { PC p; p.kind = KB_PCK_ADDITIVE_SCHWARZ; p.overlap = overlap; p.nblocks = nblocks; return p; }
+    // -> owning preconditioner handle; variants outside the device path throw KError::Unsupported
+    class Built : public Preconditioner { public: explicit Built(kb_pc h) { reset(h); } void setup(const DeviceCsr&) override {} };
+    Built build(const DeviceCsr& a) const {
+        std::vector<uint64_t> ptr, idx;
+        kb_pc_spec s{};
+        s.kind = kind; s.fill = fill; s.droptol = droptol; s.overlap = overlap; s.nblocks = nblocks;
+        if (!blocks.empty()) {
+            ptr.push_back(0);
+            for (const auto& b : blocks) { idx.insert(idx.end(), b.begin(), b.end()); ptr.push_back(idx.size()); }
+            s.nblocks = blocks.size(); s.block_ptr = ptr.data(); s.block_idx = idx.data();
+        }
+        kb_pc h = nullptr;
+        int st = kb_pc_create_from_spec(a.handle(), &s, &h);
+        if (st != KB_OK) { uint64_t row = h ? kb_pc_bad_row(h) : 0; std::string msg = kb_last_error(); kb_pc_destroy(h); throw KError(st, msg, row); }
+        return Built(h);
+    }
+};
+
 enum class CgNormType { Preconditioned = 0, Unpreconditioned = 1, Natural = 2, None = 3 };   // pcg.rs:25
 enum class Preconditioning { None = 0, Left = 1, Right = 2 };                                // gmres.rs:28-32
 
@@ -190,6 +257,24 @@ public:
     }
 private:
     double tol_; size_t max_iters_; bool textbook_;
+};
+
+// SolverKind + KspContext::solve_context (src/context/ksp_context.rs:25-69,88-148): pure dispatch, behind kb_ksp_solve
+enum class SolverKind { Cg = KB_KSP_CG, Pcg = KB_KSP_PCG, GmresLeft = KB_KSP_GMRES_LEFT, GmresRight = KB_KSP_GMRES_RIGHT, Fgmres = KB_KSP_FGMRES,
+                        Bicgstab = KB_KSP_BICGSTAB, Cgs = KB_KSP_CGS, Qmr = KB_KSP_QMR, Tfqmr = KB_KSP_TFQMR, Minres = KB_KSP_MINRES, Cgnr = KB_KSP_CGNR };
+struct KspContext {          // public fields like the reference's
+    SolverKind kind;
+    const DeviceCsr* a;
+    const Preconditioner* pc = nullptr;        // Fgmres: the flexible preconditioner (flex_pc)
+    double tol = 1e-8;
+    size_t max_it = 1000;
+    size_t restart = 30;
+    SolveStats solve_context(const std::vector<double>& b, std::vector<double>& x) const {
+        kb_ksp k{static_cast<int32_t>(kind), tol, max_it, restart};
+        kb_stats st{};
+        check(kb_ksp_solve(a->handle(), pc ? pc->handle() : nullptr, &k, b.data(), x.data(), 0, &st));
+        return to_stats(st);
+    }
 };
 
 }  // namespace kryst

@@ -19,6 +19,18 @@ class KbStats(C.Structure):
                 ("converged", C.c_int32), ("breakdown", C.c_int32)]
 
 
+class KbPcSpec(C.Structure):      # kb_pc_spec
+    _fields_ = [("kind", C.c_int32), ("fill", C.c_uint64), ("droptol", C.c_double), ("overlap", C.c_uint64),
+                ("nblocks", C.c_uint64), ("block_ptr", u64p), ("block_idx", u64p)]
+
+
+class KbKsp(C.Structure):         # kb_ksp
+    _fields_ = [("kind", C.c_int32), ("tol", C.c_double), ("max_it", C.c_uint64), ("restart", C.c_uint64)]
+
+
+MONITOR_FN = C.CFUNCTYPE(None, C.c_uint64, C.c_double, C.c_void_p)
+
+
 class KbProfile(C.Structure):
     _fields_ = [("launches", C.c_uint64 * KB_PROF_CLASSES), ("ms", C.c_double * KB_PROF_CLASSES)]
 
@@ -39,6 +51,10 @@ SIGNATURES = {
     "kb_comm_size": (C.c_int, [C.c_void_p]),
     "kb_comm_barrier": (C.c_int, [C.c_void_p]),
     "kb_comm_all_reduce": (C.c_int, [C.c_void_p, C.c_double, f64p]),
+    "kb_comm_dot": (C.c_int, [C.c_void_p, C.c_uint64, f64p, f64p, f64p]),
+    "kb_comm_norm": (C.c_int, [C.c_void_p, C.c_uint64, f64p, f64p]),
+    "kb_comm_scatter": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_int]),
+    "kb_comm_gather": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_int]),
     "kb_partition_range": (None, [C.c_uint64, C.c_uint64, C.c_uint64, u64p, u64p]),
     "kb_csr_create": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, u64p, u64p, f64p, C.POINTER(C.c_void_p)]),
     "kb_csr_create_dist": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, u64p, u64p, f64p, C.POINTER(C.c_void_p)]),
@@ -57,6 +73,14 @@ SIGNATURES = {
     "kb_norm": (C.c_int, [C.c_void_p, C.c_uint64, f64p, f64p]),
     "kb_pc_create_jacobi": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
     "kb_pc_create_ilu0": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
+    "kb_pc_create_asm": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, u64p, u64p, C.c_int, C.POINTER(C.c_void_p)]),
+    "kb_pc_asm_num_blocks": (C.c_uint64, [C.c_void_p]),
+    "kb_pc_asm_block_size": (C.c_uint64, [C.c_void_p, C.c_uint64]),
+    "kb_pc_asm_block_indices": (C.c_int, [C.c_void_p, C.c_uint64, u64p]),
+    "kb_pc_create_from_spec": (C.c_int, [C.c_void_p, C.POINTER(KbPcSpec), C.POINTER(C.c_void_p)]),
+    "kb_ksp_solve": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(KbKsp), C.c_void_p, C.c_void_p, C.c_uint32, C.POINTER(KbStats)]),
+    "kb_set_monitor": (C.c_int, [C.c_void_p, MONITOR_FN, C.c_void_p]),
+    "kb_get_history": (C.c_int, [C.c_void_p, f64p, C.c_uint64, u64p]),
     "kb_pc_apply": (C.c_int, [C.c_void_p, f64p, f64p]),
     "kb_pc_apply_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "kb_pc_destroy": (C.c_int, [C.c_void_p]),

@@ -21,6 +21,7 @@ from . import _ffi
 from ._ffi import KbStats, KbProfile, f64p, u64p
 
 KB_FLAG_DEVICE_PTRS, KB_FLAG_TEXTBOOK, KB_FLAG_PROFILE, KB_FLAG_NO_GRAPH, KB_FLAG_SINGLE_REDUCTION = 1, 2, 4, 8, 16
+KB_FLAG_HISTORY, KB_FLAG_MONITOR = 32, 64
 
 
 # ---- KError (src/error.rs:6-19) ----------------------------------------------------------------
@@ -134,6 +135,39 @@ class Context:
         out = C.c_double(0.0)
         _check(_ffi.lib().kb_comm_all_reduce(self._h, float(x), C.byref(out)))
         return out.value
+
+    def comm_dot(self, a, b):
+        """Comm::dot (parallel/mod.rs:19-22) / DistributedInnerProduct::dot (wrappers.rs:143-149): every rank passes its slice."""
+        a, b = _host_vec(a), _host_vec(b)
+        out = C.c_double(0.0)
+        _check(_ffi.lib().kb_comm_dot(self._h, a.size, _f(a), _f(b), C.byref(out)))
+        return out.value
+
+    def comm_norm(self, x):
+        """DistributedInnerProduct::norm (wrappers.rs:150-155)."""
+        x = _host_vec(x)
+        out = C.c_double(0.0)
+        _check(_ffi.lib().kb_comm_norm(self._h, x.size, _f(x), C.byref(out)))
+        return out.value
+
+    def scatter(self, global_arr, out, root=0):
+        """Comm::scatter(global, out, root) (parallel/mod.rs:9-12; mpi_comm.rs:74-84): equal chunks of len(out)."""
+        out_c = np.ascontiguousarray(out)
+        g = np.ascontiguousarray(global_arr, dtype=out_c.dtype) if global_arr is not None else None
+        _check(_ffi.lib().kb_comm_scatter(self._h, g.ctypes.data if g is not None and g.size else None, out_c.nbytes,
+                                          out_c.ctypes.data if out_c.size else None, int(root)))
+        if out_c is not out:
+            out[...] = out_c
+        return out
+
+    def gather(self, local, root=0):
+        """Comm::gather(local, &mut out, root) (parallel/mod.rs:13-16; mpi_comm.rs:91-109): the root gets size*len(local)
+        entries in rank order, every other rank an empty array."""
+        loc = np.ascontiguousarray(local)
+        out = np.zeros(loc.size * self.size(), dtype=loc.dtype) if self.rank() == root else np.zeros(0, dtype=loc.dtype)
+        _check(_ffi.lib().kb_comm_gather(self._h, loc.ctypes.data if loc.size else None, loc.nbytes,
+                                         out.ctypes.data if out.size else None, int(root)))
+        return out
 
     def comm_init(self, rank, size, unique_id):
         buf = C.create_string_buffer(bytes(unique_id), 128)
@@ -426,6 +460,153 @@ class Ilu0(_Pc):
 BlockJacobiIlu0 = Ilu0
 
 
+class AdditiveSchwarz(_Pc):
+    """AdditiveSchwarz::new(overlap, subdomains) (src/preconditioner/asm.rs:34-36) on one GPU.
+
+    `subdomains`: list of index lists (global rows, distinct inside a block), or an int p for p uniform row chunks
+    (asm.rs:46-57, the reference's `Vec::with_capacity(p)` idiom).  setup() extracts every block with
+    SubmatrixExtract on the device and factors it; apply() sums the block results in subdomain order
+    (asm.rs:76-116).  inner = "ilu0" (one ILU(0) application per block) or "jacobi".  overlap = 0 is the reference
+    (it stores the field and never reads it); overlap = k grows every set by k layers of graph neighbours."""
+
+    def __init__(self, overlap=0, subdomains=1, inner="ilu0"):
+        super().__init__()
+        self.overlap, self.subdomains, self.inner = int(overlap), subdomains, inner
+
+    def setup(self, a):
+        self.close()
+        if isinstance(self.subdomains, int):
+            nsub, ptr, idx = max(self.subdomains, 1), None, None
+        else:
+            nsub = len(self.subdomains)
+            ptr = np.zeros(nsub + 1, dtype=np.uint64)
+            ptr[1:] = np.cumsum([len(sd) for sd in self.subdomains])
+            idx = np.ascontiguousarray(np.concatenate([np.asarray(sd, dtype=np.uint64) for sd in self.subdomains])
+                                       if nsub and int(ptr[-1]) else np.zeros(0, dtype=np.uint64))
+        h = C.c_void_p()
+        st = _ffi.lib().kb_pc_create_asm(a.handle, self.overlap, nsub, _u(ptr) if ptr is not None else None,
+                                         _u(idx) if idx is not None else None, {"ilu0": 0, "jacobi": 1}[self.inner], C.byref(h))
+        if st != 0:
+            msg = _ffi.last_error()
+            row = int(_ffi.lib().kb_pc_bad_row(h)) if h else 0
+            if h:
+                _ffi.lib().kb_pc_destroy(h)
+            cls = _ERRORS.get(st, SolveError)
+            raise ZeroPivot(msg, row) if cls is ZeroPivot else cls(msg)
+        self._h, self._a, self._n = h, a, a.nrows()
+        return self
+
+    def blocks(self):
+        """Index lists actually used (after overlap growth)."""
+        out = []
+        for b in range(int(_ffi.lib().kb_pc_asm_num_blocks(self._h))):
+            k = int(_ffi.lib().kb_pc_asm_block_size(self._h, b))
+            idx = np.zeros(max(k, 1), dtype=np.uint64)
+            _check(_ffi.lib().kb_pc_asm_block_indices(self._h, b, _u(idx)))
+            out.append(idx[:k].copy())
+        return out
+
+
+class PC:
+    """PC<T> (src/context/pc_context.rs:36-76): configuration values + the factory the reference lacks.
+
+        PC.Jacobi, PC.Ilu0, PC.Ilup(fill), PC.BlockJacobi(blocks), PC.AdditiveSchwarz(overlap=0, subdomains=1), ...
+        pc = PC.Ilu0.build(a)          # -> device preconditioner handle (kb_pc_create_from_spec)
+    Variants that are not on the device path (Ssor, Ilut, Chebyshev, ApproxInv, Multicolor, AMG, Ilup with fill > 0)
+    raise Unsupported from build()."""
+    KINDS = ("Jacobi", "Ssor", "Ilu0", "Ilup", "Ilut", "Chebyshev", "ApproxInv", "BlockJacobi", "Multicolor", "AMG", "AdditiveSchwarz")
+
+    def __init__(self, kind, fill=0, droptol=0.0, overlap=0, blocks=None, nblocks=0):
+        self.kind, self.fill, self.droptol, self.overlap, self.blocks, self.nblocks = kind, fill, droptol, overlap, blocks, nblocks
+
+    def __repr__(self):
+        return "PC::%s" % self.kind
+
+    def build(self, a):
+        spec = _ffi.KbPcSpec()
+        spec.kind = self.KINDS.index(self.kind)
+        spec.fill, spec.droptol, spec.overlap = int(self.fill), float(self.droptol), int(self.overlap)
+        keep = None
+        if self.blocks is not None:
+            nb = len(self.blocks)
+            ptr = np.zeros(nb + 1, dtype=np.uint64)
+            ptr[1:] = np.cumsum([len(b) for b in self.blocks])
+            idx = np.ascontiguousarray(np.concatenate([np.asarray(b, dtype=np.uint64) for b in self.blocks]) if nb and int(ptr[-1])
+                                       else np.zeros(0, dtype=np.uint64))
+            spec.nblocks, spec.block_ptr, spec.block_idx = nb, _u(ptr), _u(idx)
+            keep = (ptr, idx)
+        else:
+            spec.nblocks = int(self.nblocks)
+        h = C.c_void_p()
+        st = _ffi.lib().kb_pc_create_from_spec(a.handle, C.byref(spec), C.byref(h))
+        del keep
+        if st != 0:
+            msg = _ffi.last_error()
+            row = int(_ffi.lib().kb_pc_bad_row(h)) if h else 0
+            if h:
+                _ffi.lib().kb_pc_destroy(h)
+            cls = _ERRORS.get(st, SolveError)
+            raise ZeroPivot(msg, row) if cls is ZeroPivot else cls(msg)
+        pc = _Pc()
+        pc._h, pc._a, pc._n = h, a, a.nrows()
+        return pc
+
+
+PC.Jacobi = PC("Jacobi")
+PC.Ssor = PC("Ssor")
+PC.Ilu0 = PC("Ilu0")
+PC.AMG = PC("AMG")
+PC.Ilup = staticmethod(lambda fill: PC("Ilup", fill=fill))
+PC.Ilut = staticmethod(lambda fill, droptol: PC("Ilut", fill=fill, droptol=droptol))
+PC.Chebyshev = staticmethod(lambda degree, emin=None, emax=None: PC("Chebyshev", fill=degree))
+PC.BlockJacobi = staticmethod(lambda blocks: PC("BlockJacobi", blocks=blocks))
+PC.AdditiveSchwarz = staticmethod(lambda overlap=0, subdomains=1: PC("AdditiveSchwarz", overlap=overlap,
+                                  blocks=None if isinstance(subdomains, int) else subdomains,
+                                  nblocks=subdomains if isinstance(subdomains, int) else 0))
+
+
+def ksp_solve(kind_index, a, pc, tol, max_it, restart, b, x, flags=0):
+    """KspContext::solve_context through the C ABI (kb_ksp_solve)."""
+    base = _SolverBase()
+    base.flags = flags
+    pb, px, fl, keep = base._solve_args(a, b, x)
+    k = _ffi.KbKsp(int(kind_index), float(tol), int(max_it), int(restart))
+    st = KbStats()
+    rc = _ffi.lib().kb_ksp_solve(a.handle, _pc_handle(pc), C.byref(k), pb, px, fl, C.byref(st))
+    stats = SolveStats(st.iterations, st.final_residual, st.converged, st.breakdown)
+    _check(rc)
+    if keep[2] is not None:
+        keep[2][...] = keep[1]
+    return stats
+
+
+def get_history(a):
+    """residual history of the last KB_FLAG_HISTORY / KB_FLAG_MONITOR solve on operator `a` (kb_get_history)."""
+    n = C.c_uint64(0)
+    _check(_ffi.lib().kb_get_history(a.handle, None, 0, C.byref(n)))
+    out = np.zeros(max(int(n.value), 1))
+    _check(_ffi.lib().kb_get_history(a.handle, _f(out), out.size, C.byref(n)))
+    return out[:min(int(n.value), out.size)].copy()
+
+
+class _MonitorScope:
+    """Installs a host observer on an operator for the duration of one solve (kb_set_monitor + KB_FLAG_MONITOR)."""
+
+    def __init__(self, a, fn):
+        self.a, self.fn = a, fn
+        self.cb = _ffi.MONITOR_FN(lambda it, res, _u: fn(int(it), float(res))) if fn else None
+
+    def __enter__(self):
+        if self.cb:
+            _check(_ffi.lib().kb_set_monitor(self.a.handle, self.cb, None))
+        return KB_FLAG_MONITOR if self.cb else 0
+
+    def __exit__(self, *exc):
+        if self.cb:
+            _ffi.lib().kb_set_monitor(self.a.handle, _ffi.MONITOR_FN(0), None)
+        return False
+
+
 # ---- solvers -------------------------------------------------------------------------------------
 def _pc_handle(pc):
     if pc is None:
@@ -508,14 +689,14 @@ class PcgSolver(_SolverBase):
             hist = np.zeros(max(cap, 1))
         st = KbStats()
         hl = C.c_uint64(0)
-        rc = _ffi.lib().kb_pcg_solve(a.handle, _pc_handle(pc), pb, px, self.tol, self.max_iters, int(self.norm_type), flags,
-                                     _f(hist) if hist is not None else None, cap, C.byref(hl), C.byref(st))
+        # with_monitor: slow mode - the observer runs on the host after every iteration, while the solve is in flight
+        # (pcg.rs:143-145,196-198); without one the history is copied out once at the end
+        with _MonitorScope(a, self.monitor) as mflag:
+            rc = _ffi.lib().kb_pcg_solve(a.handle, _pc_handle(pc), pb, px, self.tol, self.max_iters, int(self.norm_type), flags | mflag,
+                                         _f(hist) if hist is not None else None, cap, C.byref(hl), C.byref(st))
         if hist is not None:
             k = min(int(hl.value), cap)
             self.residual_history.extend(hist[:k].tolist())
-            if self.monitor:
-                for i in range(k):
-                    self.monitor(i, float(hist[i]))
         self.last_stats = SolveStats(st.iterations, st.final_residual, st.converged, st.breakdown)
         _check(rc)
         if keep[2] is not None:
@@ -534,11 +715,23 @@ class GmresSolver(_SolverBase):
         self.preconditioning = Preconditioning(mode)
         return self
 
+    record_history = False
+    monitor = None
+
+    def with_monitor(self, f):
+        self.monitor = f
+        return self
+
     def solve(self, a, pc, b, x):
         pb, px, flags, keep = self._solve_args(a, b, x)
         st = KbStats()
-        rc = _ffi.lib().kb_gmres_solve(a.handle, _pc_handle(pc), pb, px, self.restart, self.tol, self.max_iters,
-                                       int(self.preconditioning), flags, C.byref(st))
+        if self.record_history:
+            flags |= KB_FLAG_HISTORY
+        with _MonitorScope(a, self.monitor) as mflag:
+            rc = _ffi.lib().kb_gmres_solve(a.handle, _pc_handle(pc), pb, px, self.restart, self.tol, self.max_iters,
+                                           int(self.preconditioning), flags | mflag, C.byref(st))
+        if self.record_history or self.monitor:
+            self.residual_history = get_history(a).tolist()
         self.last_stats = SolveStats(st.iterations, st.final_residual, st.converged, st.breakdown)
         _check(rc)
         if keep[2] is not None:
@@ -552,10 +745,25 @@ class FgmresSolver(_SolverBase):
     def __init__(self, tol, max_iters, restart):
         self.tol, self.max_iters, self.restart = float(tol), int(max_iters), int(restart)
 
+    record_history = True       # fgmres.rs:48,290: residual_history is always kept
+    monitor = None
+
+    def with_monitor(self, f):      # fgmres.rs:92-97
+        self.monitor = f
+        return self
+
+    def clear_history(self):        # fgmres.rs:99-101
+        self.residual_history = []
+
     def solve_flex(self, a, pc, b, x):
         pb, px, flags, keep = self._solve_args(a, b, x)
         st = KbStats()
-        rc = _ffi.lib().kb_fgmres_solve(a.handle, _pc_handle(pc), pb, px, self.restart, self.tol, self.max_iters, flags, C.byref(st))
+        if self.record_history:
+            flags |= KB_FLAG_HISTORY
+        with _MonitorScope(a, self.monitor) as mflag:
+            rc = _ffi.lib().kb_fgmres_solve(a.handle, _pc_handle(pc), pb, px, self.restart, self.tol, self.max_iters, flags | mflag, C.byref(st))
+        if self.record_history or self.monitor:
+            self.residual_history = getattr(self, "residual_history", []) + get_history(a).tolist()
         self.last_stats = SolveStats(st.iterations, st.final_residual, st.converged, st.breakdown)
         _check(rc)
         if keep[2] is not None:
@@ -576,10 +784,16 @@ class BiCgStabSolver(_SolverBase):
         self.tol, self.max_iters = float(tol), int(max_iters)
         self.flags = KB_FLAG_TEXTBOOK if textbook else 0
 
+    record_history = False
+
     def solve(self, a, pc, b, x):
         pb, px, flags, keep = self._solve_args(a, b, x)
         st = KbStats()
+        if self.record_history:
+            flags |= KB_FLAG_HISTORY
         rc = _ffi.lib().kb_bicgstab_solve(a.handle, _pc_handle(pc), pb, px, self.tol, self.max_iters, flags, C.byref(st))
+        if self.record_history:
+            self.residual_history = get_history(a).tolist()
         self.last_stats = SolveStats(st.iterations, st.final_residual, st.converged, st.breakdown)
         _check(rc)
         if keep[2] is not None:

@@ -8,7 +8,7 @@ it), a row-partitioned operator already carries its communicator, so `comm` is o
 """
 import enum
 
-from .api import BiCgStabSolver, FgmresSolver, GmresSolver, PcgSolver, Preconditioning, Unsupported
+from .api import PC, Unsupported, ksp_solve  # noqa: F401  (PC: pc_context.rs:36-76 mirror + factory)
 
 
 class SolverKind(enum.Enum):           # ksp_context.rs:25-48
@@ -36,18 +36,8 @@ class KspContext:
         """ksp_context.rs:88-148."""
         if comm is not None and hasattr(comm, "size") and comm.size() != self.a.ctx.size():
             raise Unsupported("comm does not match the communicator the operator was partitioned with")
-        k = self.kind
-        if k is SolverKind.GmresLeft:
-            return GmresSolver(self.restart, self.tol, self.max_it).with_preconditioning(Preconditioning.Left).solve(self.a, self.pc, b, x)
-        if k is SolverKind.GmresRight:
-            return GmresSolver(self.restart, self.tol, self.max_it).with_preconditioning(Preconditioning.Right).solve(self.a, self.pc, b, x)
-        if k is SolverKind.Pcg:
-            return PcgSolver(self.tol, self.max_it).solve(self.a, self.pc, b, x)
-        if k is SolverKind.Cg:
-            # CgSolver ignores the preconditioner (`let _ = pc;`, src/solver/cg.rs:114-115)
-            return PcgSolver(self.tol, self.max_it).solve(self.a, None, b, x)
-        if k is SolverKind.Bicgstab:
-            return BiCgStabSolver(self.tol, self.max_it).solve(self.a, self.pc, b, x)
-        if k is SolverKind.Fgmres:
-            return FgmresSolver(self.tol, self.max_it, self.restart).solve_flex(self.a, self.flex_pc, b, x)
-        raise Unsupported("SolverKind::%s is not on the device hot path" % k.value)
+        # the dispatch itself lives behind the C ABI (kb_ksp_solve, csrc/kb_context.cu), so the Rust / C++ hosts share it;
+        # kinds that are not on the device hot path come back as KError::Unsupported
+        order = [k for k in SolverKind]
+        pc = self.flex_pc if self.kind is SolverKind.Fgmres else self.pc
+        return ksp_solve(order.index(self.kind), self.a, pc, self.tol, self.max_it, self.restart, b, x)

@@ -55,7 +55,11 @@ struct BicgSFin {      // bicgstab.rs:176-206
     __device__ void operator()(const double* s) const {
         KbCtl* c = ctl;
         const double sn = sqrt(s[0]);
-        if (sn <= c->thr) { c->early = 1; c->iter = c->iter + 1; c->res = sn; c->converged = 1; }
+        if (sn <= c->thr) {
+            c->early = 1; c->iter = c->iter + 1; c->res = sn; c->converged = 1;
+            if (c->hist_len < c->hist_cap) c->hist[c->hist_len] = sn;
+            c->hist_len += 1;
+        }
     }
 };
 struct BicgTFin {      // bicgstab.rs:211-239
@@ -74,6 +78,8 @@ struct BicgXrFin {     // bicgstab.rs:266-289 and the head of the next iteration
         const double rn = sqrt(s[0]);
         c->rnorm = rn; c->res = rn;
         c->iter = c->iter + 1;
+        if (c->hist_len < c->hist_cap) c->hist[c->hist_len] = rn;          // one entry per iteration (the reference keeps none)
+        c->hist_len += 1;
         c->converged = (rn <= c->thr) ? 1 : 0;
         if (c->converged) { c->done = 1; return; }
         if (!c->textbook ? (fabs(c->omega) < KB_EPS) : (c->omega == 0.0)) { c->breakdown = 4; c->done = 1; return; }
@@ -276,6 +282,9 @@ extern "C" int kb_bicgstab_solve(kb_csr A, kb_pc pc, const double* b, double* x,
     memset(h, 0, offsetof(KbCtl, h));
     h->max_iters = max_iters; h->tol = tol; h->textbook = textbook ? 1 : 0;
     h->rho_prev = 1.0; h->alpha = 1.0; h->omega_prev = 1.0;
+    KB_TRY(kb_hist_prepare(A, flags, max_iters, h));
+    KbMonitor mon;
+    if ((flags & KB_FLAG_MONITOR) && A->monitor) { mon.fn = A->monitor; mon.user = A->monitor_user; mon.d_hist = h->hist; mon.cap = h->hist_cap; mon.index_offset = 1; }
     KB_CUDA(cudaMemcpyAsync(w->ctl, h, offsetof(KbCtl, h), cudaMemcpyHostToDevice, c->stream));
     const bool profile = (flags & KB_FLAG_PROFILE) != 0;
     const bool use_graph = !(flags & (KB_FLAG_NO_GRAPH | KB_FLAG_PROFILE));
@@ -296,11 +305,12 @@ extern "C" int kb_bicgstab_solve(kb_csr A, kb_pc pc, const double* b, double* x,
         const double bytes_iter = 24.0 * (double)A->nnz + 170.0 * (double)A->n;
         const int B = kb_batch_size(bytes_iter, 5);
         st = kb_run_iterations(c, &w->gc, (kb_pc_serial(pc) + 1) * 4 + (uint64_t)mode, B, max_iters, use_graph, w->ctl, h,
-                               [&]() { return bicg_iteration(A, pc, w, mode, dist); });
+                               [&]() { return bicg_iteration(A, pc, w, mode, dist); }, &mon);
         if (st != KB_OK) break;
         if (cudaMemcpyAsync(h, w->ctl, offsetof(KbCtl, h), cudaMemcpyDeviceToHost, c->stream) != cudaSuccess ||
             cudaStreamSynchronize(c->stream) != cudaSuccess) { kb_set_error("bicgstab: readback failed"); st = KB_SOLVE_ERROR; break; }
         stats->iterations = h->iter; stats->final_residual = h->res; stats->converged = h->converged; stats->breakdown = h->breakdown;
+        A->hist_len = std::min<uint64_t>(h->hist_len, h->hist_cap);
         st = h->status;
         if (dist && kb_p2p_error(c)) { kb_set_error("%s: peer-memory collective timed out", "bicgstab"); st = KB_SOLVE_ERROR; break; }
         if (pc && kb_ilu0_error(const_cast<kb_pc_s*>(pc))) { kb_set_error("%s: a triangular-solve dependency wait timed out", "bicgstab"); st = KB_SOLVE_ERROR; break; }

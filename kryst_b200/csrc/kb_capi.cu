@@ -131,6 +131,34 @@ extern "C" void kb_partition_range(uint64_t n, uint64_t p, uint64_t r, uint64_t*
     *hi = e > n ? n : e;
 }
 
+int kb_hist_prepare(kb_csr_s* A, uint32_t flags, uint64_t max_entries, KbCtl* h) {
+    A->hist_len = 0;
+    if (!(flags & (KB_FLAG_HISTORY | KB_FLAG_MONITOR))) return KB_OK;
+    const uint64_t want = std::min<uint64_t>(std::max<uint64_t>(max_entries, 1), 1ull << 22);
+    if (want > A->hist_cap) {
+        KB_FREE(A->hist_buf);
+        A->hist_cap = 0;
+        KB_TRY(kb_alloc(&A->hist_buf, want));
+        A->hist_cap = want;
+    }
+    h->hist = A->hist_buf; h->hist_cap = A->hist_cap; h->hist_len = 0;
+    return KB_OK;
+}
+extern "C" int kb_set_monitor(kb_csr A, kb_monitor_fn fn, void* user) {
+    if (!A) { kb_set_error("null operator"); return KB_SOLVE_ERROR; }
+    A->monitor = fn; A->monitor_user = user;
+    return KB_OK;
+}
+extern "C" int kb_get_history(kb_csr A, double* out, uint64_t cap, uint64_t* len) {
+    if (!A) { kb_set_error("null operator"); return KB_SOLVE_ERROR; }
+    if (len) *len = A->hist_len;
+    const uint64_t k = std::min<uint64_t>(std::min(A->hist_len, cap), A->hist_cap);
+    if (k && out) {
+        KB_CUDA(cudaSetDevice(A->ctx->device));
+        KB_CUDA(cudaMemcpy(out, A->hist_buf, k * sizeof(double), cudaMemcpyDeviceToHost));
+    }
+    return KB_OK;
+}
 int kb_upload_or_alias(kb_ctx_s* c, const double* src, double* dst, uint64_t n, bool device_ptrs) {
     if (n == 0) return KB_OK;
     KB_CUDA(cudaMemcpyAsync(dst, src, n * sizeof(double), device_ptrs ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, c->stream));
@@ -352,7 +380,7 @@ void kb_csr_unref(kb_csr_s* A) {
     kb_halo_free(A->halo);
     KB_FREE(A->row_ptr); KB_FREE(A->col); KB_FREE(A->vals); KB_FREE(A->ghosts);
     KB_FREE(A->tile_chunk); KB_FREE(A->chunk_row); KB_FREE(A->chunk_nz); KB_FREE(A->tiles_interior); KB_FREE(A->tiles_boundary);
-    KB_FREE(A->x_tmp); KB_FREE(A->y_tmp);
+    KB_FREE(A->x_tmp); KB_FREE(A->y_tmp); KB_FREE(A->hist_buf);
     kb_ctx_s* c = A->ctx;
     delete A;
     kb_ctx_unref(c);
@@ -508,6 +536,7 @@ int kb_pc_apply_dev(kb_pc_s* pc, const double* d_r, double* d_z, const KbCtl* sk
         return KB_OK;
     }
     if (pc->kind == KB_PC_ILU0) return kb_ilu0_apply_dev(pc, d_r, d_z, skip_ctl, skip_mask);
+    if (pc->kind == KB_PC_ASM) return kb_asm_apply_dev(pc, d_r, d_z, skip_ctl, skip_mask);
     kb_set_error("unknown preconditioner kind");
     return KB_UNSUPPORTED;
 }
@@ -515,7 +544,7 @@ extern "C" int kb_pc_apply_device(kb_pc pc, const double* d_r, double* d_z) {
     KB_CUDA(cudaSetDevice(pc->a->ctx->device));
     KB_TRY(kb_pc_apply_dev(pc, d_r, d_z));
     KB_CUDA(cudaStreamSynchronize(pc->a->ctx->stream));
-    if (kb_ilu0_error(pc)) { kb_set_error("ilu0: a triangular-solve dependency wait timed out"); return KB_SOLVE_ERROR; }
+    if (kb_ilu0_error(pc) || kb_asm_error(pc)) { kb_set_error("ilu0: a triangular-solve dependency wait timed out"); return KB_SOLVE_ERROR; }
     return KB_OK;
 }
 extern "C" int kb_pc_apply(kb_pc pc, const double* r, double* z) {
@@ -528,7 +557,7 @@ extern "C" int kb_pc_apply(kb_pc pc, const double* r, double* z) {
     KB_TRY(kb_pc_apply_dev(pc, pc->r_tmp, pc->z_tmp));
     KB_CUDA(cudaMemcpyAsync(z, pc->z_tmp, A->n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     KB_CUDA(cudaStreamSynchronize(c->stream));
-    if (kb_ilu0_error(pc)) { kb_set_error("ilu0: a triangular-solve dependency wait timed out"); return KB_SOLVE_ERROR; }
+    if (kb_ilu0_error(pc) || kb_asm_error(pc)) { kb_set_error("ilu0: a triangular-solve dependency wait timed out"); return KB_SOLVE_ERROR; }
     return KB_OK;
 }
 extern "C" int kb_pc_destroy(kb_pc pc) {
@@ -536,6 +565,7 @@ extern "C" int kb_pc_destroy(kb_pc pc) {
     cudaSetDevice(pc->ctx->device);
     cudaStreamSynchronize(pc->ctx->stream);
     kb_ilu0_free(pc);
+    kb_asm_free(pc);
     KB_FREE(pc->inv_diag); KB_FREE(pc->r_tmp); KB_FREE(pc->z_tmp);
     kb_csr_s* A = pc->a;
     delete pc;

@@ -236,6 +236,62 @@ extern "C" int kb_comm_all_reduce(kb_ctx c, double local, double* global) {
     KB_CUDA(cudaStreamSynchronize(c->stream));
     return KB_OK;
 }
+// Comm::scatter / Comm::gather (parallel/mod.rs:9-16; mpi_comm.rs:74-109): the root's array of size*bytes is split into
+// equal chunks, one per rank / every rank's chunk lands in rank order in the root's array.  Host slices, staged through
+// device memory and moved with NCCL send/recv over NVLink.  size == 1: a copy (rayon_comm.rs:56-69 with root 0).
+static int comm_stage(kb_ctx_s* c, size_t bytes, unsigned char** d) {
+    *d = nullptr;
+    KB_CUDA(cudaMalloc((void**)d, bytes ? bytes : 1));
+    return KB_OK;
+}
+extern "C" int kb_comm_scatter(kb_ctx c, const void* global, uint64_t bytes_per_rank, void* out, int root) {
+    if (!c || root < 0 || root >= c->size || (bytes_per_rank && !out)) { kb_set_error("kb_comm_scatter: bad arguments"); return KB_SOLVE_ERROR; }
+    if (c->size == 1) { if (bytes_per_rank) memcpy(out, global, bytes_per_rank); return KB_OK; }
+    if (c->rank == root && bytes_per_rank && !global) { kb_set_error("kb_comm_scatter: the root needs the global array"); return KB_SOLVE_ERROR; }
+    KB_CUDA(cudaSetDevice(c->device));
+    unsigned char *d_all = nullptr, *d_mine = nullptr;
+    KB_TRY(comm_stage(c, bytes_per_rank, &d_mine));
+    if (c->rank == root) {
+        KB_TRY(comm_stage(c, bytes_per_rank * (size_t)c->size, &d_all));
+        KB_CUDA(cudaMemcpyAsync(d_all, global, bytes_per_rank * (size_t)c->size, cudaMemcpyHostToDevice, c->stream));
+    }
+    if (bytes_per_rank) {
+        KB_NCCL(g_nccl.GroupStart());
+        if (c->rank == root)
+            for (int q = 0; q < c->size; ++q) KB_NCCL(g_nccl.Send(d_all + (size_t)q * bytes_per_rank, bytes_per_rank, ncclChar, q, (ncclComm_t)c->nccl, c->stream));
+        KB_NCCL(g_nccl.Recv(d_mine, bytes_per_rank, ncclChar, root, (ncclComm_t)c->nccl, c->stream));
+        KB_NCCL(g_nccl.GroupEnd());
+        KB_CUDA(cudaMemcpyAsync(out, d_mine, bytes_per_rank, cudaMemcpyDeviceToHost, c->stream));
+    }
+    KB_CUDA(cudaStreamSynchronize(c->stream));
+    cudaFree(d_mine); if (d_all) cudaFree(d_all);
+    return KB_OK;
+}
+extern "C" int kb_comm_gather(kb_ctx c, const void* local, uint64_t bytes_per_rank, void* out, int root) {
+    if (!c || root < 0 || root >= c->size || (bytes_per_rank && !local)) { kb_set_error("kb_comm_gather: bad arguments"); return KB_SOLVE_ERROR; }
+    if (c->size == 1) { if (bytes_per_rank) memcpy(out, local, bytes_per_rank); return KB_OK; }
+    if (c->rank == root && bytes_per_rank && !out) { kb_set_error("kb_comm_gather: the root needs the output array"); return KB_SOLVE_ERROR; }
+    KB_CUDA(cudaSetDevice(c->device));
+    unsigned char *d_all = nullptr, *d_mine = nullptr;
+    KB_TRY(comm_stage(c, bytes_per_rank, &d_mine));
+    if (bytes_per_rank) KB_CUDA(cudaMemcpyAsync(d_mine, local, bytes_per_rank, cudaMemcpyHostToDevice, c->stream));
+    if (c->rank == root) KB_TRY(comm_stage(c, bytes_per_rank * (size_t)c->size, &d_all));
+    if (bytes_per_rank) {
+        KB_NCCL(g_nccl.GroupStart());
+        if (c->rank == root)
+            for (int q = 0; q < c->size; ++q) KB_NCCL(g_nccl.Recv(d_all + (size_t)q * bytes_per_rank, bytes_per_rank, ncclChar, q, (ncclComm_t)c->nccl, c->stream));
+        KB_NCCL(g_nccl.Send(d_mine, bytes_per_rank, ncclChar, root, (ncclComm_t)c->nccl, c->stream));
+        KB_NCCL(g_nccl.GroupEnd());
+        if (c->rank == root) KB_CUDA(cudaMemcpyAsync(out, d_all, bytes_per_rank * (size_t)c->size, cudaMemcpyDeviceToHost, c->stream));
+    }
+    KB_CUDA(cudaStreamSynchronize(c->stream));
+    cudaFree(d_mine); if (d_all) cudaFree(d_all);
+    return KB_OK;
+}
+// Comm::dot (parallel/mod.rs:19-22) and DistributedInnerProduct::{dot,norm} (core/wrappers.rs:134-156): local part on this
+// rank's GPU with the canonical tree, then the rank-ordered all-reduce - bit-identical to the oracle's sharded reduction.
+extern "C" int kb_comm_dot(kb_ctx c, uint64_t n_local, const double* a, const double* b, double* out) { return kb_dot(c, n_local, a, b, out); }
+extern "C" int kb_comm_norm(kb_ctx c, uint64_t n_local, const double* x, double* out) { return kb_norm(c, n_local, x, out); }
 extern "C" int kb_comm_barrier(kb_ctx c) {
     double g = 0.0;
     return kb_comm_all_reduce(c, 0.0, &g);

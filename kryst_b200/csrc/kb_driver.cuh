@@ -3,6 +3,7 @@
 // `done` is set exit immediately, so over-issued iterations change nothing.
 #pragma once
 #include <cstddef>
+#include <vector>
 #include "kb_objects.h"
 
 struct KbGraphCache {
@@ -18,9 +19,37 @@ struct KbGraphCache {
 
 // launch_iter(): enqueue one iteration's kernels on c->stream, return kb_status.
 // units_cap: upper bound on useful iterations (max_iters); the loop stops when done or after the cap.
+// Slow mode (KB_FLAG_MONITOR): one unit per batch, no graph; after every unit the control block is read back
+// and the host observer is called for every residual-history entry it has not seen yet, in order
+// (pcg.rs:143-145,196-198: monitor(0, r0), monitor(i+1, res); fgmres.rs:286-289: monitor(total_iters, res)).
+struct KbMonitor {
+    kb_monitor_fn fn = nullptr; void* user = nullptr;
+    const double* d_hist = nullptr; uint64_t cap = 0, seen = 0, index_offset = 0;
+};
+static inline int kb_monitor_deliver(kb_ctx_s* c, KbMonitor* m, const KbCtl* h_ctl) {
+    const uint64_t have = h_ctl->hist_len < m->cap ? h_ctl->hist_len : m->cap;
+    if (have <= m->seen) return KB_OK;
+    std::vector<double> buf((size_t)(have - m->seen));
+    KB_CUDA(cudaMemcpyAsync(buf.data(), m->d_hist + m->seen, buf.size() * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    KB_CUDA(cudaStreamSynchronize(c->stream));
+    for (size_t k = 0; k < buf.size(); ++k) m->fn(m->seen + k + m->index_offset, buf[k], m->user);
+    m->seen = have;
+    return KB_OK;
+}
+
 template <class F>
 static int kb_run_iterations(kb_ctx_s* c, KbGraphCache* gc, uint64_t key, int B, uint64_t units_cap, bool use_graph,
-                             KbCtl* d_ctl, KbCtl* h_ctl, F&& launch_iter) {
+                             KbCtl* d_ctl, KbCtl* h_ctl, F&& launch_iter, KbMonitor* mon = nullptr) {
+    if (mon && mon->fn) {
+        for (uint64_t u = 0;; ++u) {
+            if (cudaMemcpyAsync(h_ctl, d_ctl, offsetof(KbCtl, h), cudaMemcpyDeviceToHost, c->stream) != cudaSuccess ||
+                cudaStreamSynchronize(c->stream) != cudaSuccess) { kb_set_error("device error during Krylov iterations: %s", cudaGetErrorString(cudaGetLastError())); return KB_SOLVE_ERROR; }
+            KB_TRY(kb_monitor_deliver(c, mon, h_ctl));
+            if (h_ctl->done || u >= units_cap) break;
+            KB_TRY(launch_iter());
+        }
+        return KB_OK;
+    }
     if (units_cap == 0) return KB_OK;
     if (B < 1) B = 1;
     if ((uint64_t)B > units_cap) B = (int)units_cap;

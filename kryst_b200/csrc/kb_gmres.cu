@@ -289,6 +289,8 @@ __device__ void kb_arnoldi_fin(const KbGmresDev& g, double ww, int j) {
         c->g[j] = temp;
         for (int i = 0; i <= j + 1; ++i) c->h[i + (size_t)ldh * j] = hcol[i];
         const double res_norm = fabs(c->g[j + 1]);
+        if (c->hist_len < c->hist_cap) c->hist[c->hist_len] = res_norm;      // residual_history.push(res_norm) (fgmres.rs:290)
+        c->hist_len += 1;
         const unsigned long long it = c->iter + 1;
         c->iter = it;
         const double rel = res_norm / (g.flex ? c->beta_g : c->res0);   // Convergence::check; FGMRES divides by this cycle's s[0] (fgmres.rs:292)
@@ -726,6 +728,9 @@ static int gmres_solve_impl(kb_csr A, kb_pc pc, const double* b, double* x, uint
     h->n_outer = (int)std::min<uint64_t>((max_iters + restart - 1) / restart, 0x7fffffffull);
     if (flex) h->n_outer = (int)std::min<uint64_t>(max_iters, 0x7fffffffull);   // `while total_iters < max_iters` (fgmres.rs:162): every cycle makes >= 1 step
     if (flex && pc && !w->Z) KB_TRY(kb_alloc(&w->Z, w->ld * (size_t)w->restart));
+    KB_TRY(kb_hist_prepare(A, flags, max_iters, h));
+    KbMonitor mon;
+    if ((flags & KB_FLAG_MONITOR) && A->monitor) { mon.fn = A->monitor; mon.user = A->monitor_user; mon.d_hist = h->hist; mon.cap = h->hist_cap; mon.index_offset = 1; }
     KB_CUDA(cudaMemcpyAsync(w->ctl, h, offsetof(KbCtl, h), cudaMemcpyHostToDevice, c->stream));
     GmPlan P{A, pc, w, side, dist, (int)restart, {}};
     P.g.ctl = w->ctl; P.g.V = w->V; P.g.ld = w->ld;
@@ -753,11 +758,12 @@ static int gmres_solve_impl(kb_csr A, kb_pc pc, const double* b, double* x, uint
         }
         if ((st = gm_start_vector(P)) != KB_OK) break;
         const uint64_t key = ((kb_pc_serial(pc) + 1) * 4 + (uint64_t)side) * 256 + restart;
-        st = kb_run_iterations(c, &w->gc, key, 1, (uint64_t)h->n_outer, use_graph, w->ctl, h, [&]() { return gm_cycle(P); });
+        st = kb_run_iterations(c, &w->gc, key, 1, (uint64_t)h->n_outer, use_graph, w->ctl, h, [&]() { return gm_cycle(P); }, &mon);
         if (st != KB_OK) break;
         if (cudaMemcpyAsync(h, w->ctl, offsetof(KbCtl, h), cudaMemcpyDeviceToHost, c->stream) != cudaSuccess ||
             cudaStreamSynchronize(c->stream) != cudaSuccess) { kb_set_error("gmres: readback failed"); st = KB_SOLVE_ERROR; break; }
         stats->iterations = h->iter; stats->final_residual = flex ? h->res0_true : h->res; stats->converged = h->converged; stats->breakdown = h->happy;
+        A->hist_len = std::min<uint64_t>(h->hist_len, h->hist_cap);
         st = h->status;
         if (dist && kb_p2p_error(c)) { kb_set_error("%s: peer-memory collective timed out", "gmres"); st = KB_SOLVE_ERROR; break; }
         if (pc && kb_ilu0_error(const_cast<kb_pc_s*>(pc))) { kb_set_error("%s: a triangular-solve dependency wait timed out", "gmres"); st = KB_SOLVE_ERROR; break; }

@@ -643,6 +643,7 @@ int kb_ilu0_apply_dev(kb_pc_s* pc, const double* d_r, double* d_z, const KbCtl* 
 
 // 1 when a bounded spin of a triangular solve expired (a dependency never arrived): the solve's result is invalid
 int kb_ilu0_error(kb_pc_s* pc) {
+    if (pc && pc->kind == KB_PC_ASM) return kb_asm_error(pc);      // any inner block
     KbIluExtra* x = pc && pc->kind == KB_PC_ILU0 ? extra_of(pc) : nullptr;
     if (!x || !x->counters) return 0;
     unsigned e = 0;

@@ -42,9 +42,14 @@ struct kb_csr_s {
     KbPcgWs* pcg_ws = nullptr;
     KbBicgWs* bicg_ws = nullptr;
     KbGmresWs* gmres_ws = nullptr;
+    // observability: host observer + device residual history of the last KB_FLAG_HISTORY / KB_FLAG_MONITOR solve
+    kb_monitor_fn monitor = nullptr;
+    void* monitor_user = nullptr;
+    double* hist_buf = nullptr;
+    uint64_t hist_cap = 0, hist_len = 0;
 };
 
-enum { KB_PC_JACOBI = 1, KB_PC_ILU0 = 2 };
+enum { KB_PC_JACOBI = 1, KB_PC_ILU0 = 2, KB_PC_ASM = 3 };
 uint64_t kb_next_serial();
 static inline uint64_t kb_pc_serial(const struct kb_pc_s* pc);
 
@@ -109,4 +114,9 @@ void kb_halo_free(KbHalo* h);
 int kb_ilu0_build(kb_pc_s* pc);
 int kb_ilu0_error(kb_pc_s* pc);                   // 1 if a triangular-solve spin timed out
 void kb_ilu0_free(kb_pc_s* pc);
+int kb_asm_apply_dev(kb_pc_s* pc, const double* d_r, double* d_z, const KbCtl* skip_ctl, int skip_mask);   // kb_asm.cu
+int kb_asm_error(kb_pc_s* pc);
+void kb_asm_free(kb_pc_s* pc);
 int kb_upload_or_alias(kb_ctx_s* c, const double* src, double* dst, uint64_t n, bool device_ptrs);
+// history buffer of the operator (grown on demand, capped at 4 Mi entries); sets h->hist / h->hist_cap when the flags ask for it
+int kb_hist_prepare(kb_csr_s* A, uint32_t flags, uint64_t max_entries, KbCtl* h);

@@ -401,7 +401,7 @@ extern "C" int kb_pcg_solve(kb_csr A, kb_pc pc, const double* b, double* x, doub
                             uint32_t flags, double* history, uint64_t hist_cap, uint64_t* hist_len, kb_stats* stats) {
     if (!A || !b || !x || !stats) { kb_set_error("kb_pcg_solve: null argument"); return KB_SOLVE_ERROR; }
     if (pc && pc->a != A) { kb_set_error("preconditioner was set up for a different operator"); return KB_SOLVE_ERROR; }
-    if (pc && pc->kind != KB_PC_JACOBI && pc->kind != KB_PC_ILU0) { kb_set_error("unsupported preconditioner"); return KB_UNSUPPORTED; }
+    if (pc && pc->kind != KB_PC_JACOBI && pc->kind != KB_PC_ILU0 && pc->kind != KB_PC_ASM) { kb_set_error("unsupported preconditioner"); return KB_UNSUPPORTED; }
     if (norm_type < 0 || norm_type > 3) { kb_set_error("bad norm_type"); return KB_SOLVE_ERROR; }
     kb_ctx_s* c = A->ctx;
     KB_CUDA(cudaSetDevice(c->device));
@@ -424,6 +424,11 @@ extern "C" int kb_pcg_solve(kb_csr A, kb_pc pc, const double* b, double* x, doub
     KbCtl* h = w->h_ctl;
     memset(h, 0, offsetof(KbCtl, h));
     h->max_iters = max_iters; h->tol = tol; h->norm_type = norm_type; h->hist = w->hist; h->hist_cap = hist_cap;
+    const bool own_hist = hist_cap == 0 && (flags & (KB_FLAG_HISTORY | KB_FLAG_MONITOR));
+    if (own_hist) KB_TRY(kb_hist_prepare(A, flags, max_iters + 1, h));     // the operator's buffer (kb_get_history)
+    else A->hist_len = 0;
+    KbMonitor mon;
+    if ((flags & KB_FLAG_MONITOR) && A->monitor) { mon.fn = A->monitor; mon.user = A->monitor_user; mon.d_hist = h->hist; mon.cap = h->hist_cap; }
     KB_CUDA(cudaMemcpyAsync(w->ctl, h, offsetof(KbCtl, h), cudaMemcpyHostToDevice, c->stream));
 
     const bool profile = (flags & KB_FLAG_PROFILE) != 0;
@@ -462,7 +467,7 @@ extern "C" int kb_pcg_solve(kb_csr A, kb_pc pc, const double* b, double* x, doub
         if (dist && !single_red && kb_halo_fused_dev(A) && (st = kb_halo_begin(A, w->p)) != KB_OK) break;
         const int mega_env = getenv("KB_PCG_PERSISTENT") ? atoi(getenv("KB_PCG_PERSISTENT")) : 0;
         const bool mega_ok = !single_red && !dist && jacobi_like && A->kind == 2 && !A->prod && !profile && max_iters > 0;
-        const bool mega = mega_ok && mega_env != 0;
+        const bool mega = mega_ok && mega_env != 0 && !mon.fn;
         if (mega) {
             if ((st = pcg_persistent(A, pc, w)) != KB_OK) break;
             unsigned berr = 0;
@@ -474,12 +479,13 @@ extern "C" int kb_pcg_solve(kb_csr A, kb_pc pc, const double* b, double* x, doub
         const int B = kb_batch_size(12.0 * (double)A->nnz + 108.0 * (double)A->n, 3);
         // graph key: the captured launches differ between the two variants
         st = kb_run_iterations(c, &w->gc, (kb_pc_serial(pc) + 1) ^ (single_red ? 0x5352ull << 48 : 0ull), B, max_iters, use_graph, w->ctl, h,
-                               [&]() { return single_red ? pcg_sr_iteration(A, pc, w) : pcg_iteration(A, pc, w); });
+                               [&]() { return single_red ? pcg_sr_iteration(A, pc, w) : pcg_iteration(A, pc, w); }, &mon);
         }
         if (st != KB_OK) break;
         if (cudaMemcpyAsync(h, w->ctl, offsetof(KbCtl, h), cudaMemcpyDeviceToHost, c->stream) != cudaSuccess ||
             cudaStreamSynchronize(c->stream) != cudaSuccess) { kb_set_error("pcg: readback failed"); st = KB_SOLVE_ERROR; break; }
         stats->iterations = h->iter; stats->final_residual = h->res; stats->converged = h->converged; stats->breakdown = 0;
+        if (own_hist) A->hist_len = std::min<uint64_t>(h->hist_len, A->hist_cap);
         st = h->status;
         if (dist && kb_p2p_error(c)) { kb_set_error("%s: peer-memory collective timed out", "pcg"); st = KB_SOLVE_ERROR; break; }
         if (pc && kb_ilu0_error(const_cast<kb_pc_s*>(pc))) { kb_set_error("%s: a triangular-solve dependency wait timed out", "pcg"); st = KB_SOLVE_ERROR; break; }

@@ -333,14 +333,14 @@ void ko_ilu_literal_apply(u64 n, const double* l, const double* u, const double*
 // ----------------------------------------------------------------------------
 // Preconditioner object used by the oracle solvers
 // ----------------------------------------------------------------------------
-enum { KO_PC_NONE = 0, KO_PC_JACOBI = 1, KO_PC_ILU0 = 2, KO_PC_BLOCK_ILU0 = 3, KO_PC_ILU_LITERAL = 4 };
+enum { KO_PC_NONE = 0, KO_PC_JACOBI = 1, KO_PC_ILU0 = 2, KO_PC_BLOCK_ILU0 = 3, KO_PC_ILU_LITERAL = 4, KO_PC_ASM = 5 };
 
 struct ko_pc {
     int kind = KO_PC_NONE;
     u64 n = 0;
     std::vector<double> inv_diag;                 // jacobi
     // ilu0 / block ilu0: one factor per block, on the block-local CSR
-    struct Block { u64 lo, hi; std::vector<u64> rp, ci, dp; std::vector<double> av, lu, inv_ud; };
+    struct Block { u64 lo, hi; std::vector<u64> rp, ci, dp; std::vector<double> av, lu, inv_ud; std::vector<u64> idx; int inner = 0; };
     std::vector<Block> blocks;
     std::vector<double> dl, du;                   // literal dense
     int status = KO_OK; u64 bad_row = 0;
@@ -360,6 +360,19 @@ static void pc_apply(const ko_pc* pc, const double* r, double* z, u64 n) {
         }
         break; }
     case KO_PC_ILU_LITERAL: ko_ilu_literal_apply(n, pc->dl.data(), pc->du.data(), r, z); break;
+    case KO_PC_ASM: {   // asm.rs:76-116: z = 0, then the blocks IN ORDER: z[idx] += inner(A_b, r[idx])
+        std::fill(z, z + n, 0.0);
+        for (const ko_pc::Block& B : pc->blocks) {
+            const u64 m = B.idx.size();
+            std::vector<double> rb(m), xb(m);
+            for (u64 j = 0; j < m; ++j) rb[j] = r[B.idx[j]];
+            if (B.inner == 0) {
+                ko_csr L{m, m, B.rp.data(), B.ci.data(), B.av.data()};
+                ko_ilu0_apply(&L, B.lu.data(), B.dp.data(), B.inv_ud.data(), rb.data(), xb.data());
+            } else ko_jacobi_apply(m, B.inv_ud.data(), rb.data(), xb.data());
+            for (u64 j = 0; j < m; ++j) z[B.idx[j]] = z[B.idx[j]] + xb[j];
+        }
+        break; }
     }
 }
 
@@ -396,6 +409,51 @@ ko_pc* ko_pc_create_ilu_literal(u64 n, const double* dense_row_major) {
     ko_pc* pc = new ko_pc; pc->kind = KO_PC_ILU_LITERAL; pc->n = n; pc->dl.resize(n * n); pc->du.resize(n * n);
     ko_ilu_literal_setup(n, dense_row_major, pc->dl.data(), pc->du.data()); return pc;
 }
+u64 ko_submatrix(const ko_csr* A, const u64* indices, u64 k, u64* row_ptr, u64* col_idx, double* vals);
+// AdditiveSchwarz (asm.rs:34-116) with one inner preconditioner application per block (inner 0: ILU(0) of the block's
+// submatrix, 1: its Jacobi).  sub_ptr == nullptr: nsub uniform chunks (asm.rs:46-57).  overlap = 0: the reference (index
+// lists as given, caller's order); overlap = k: grow by k layers of neighbours through the stored pattern, ascending.
+ko_pc* ko_pc_create_asm(const ko_csr* A, u64 overlap, u64 nsub, const u64* sub_ptr, const u64* sub_idx, int inner) {
+    ko_pc* pc = new ko_pc; pc->kind = KO_PC_ASM; pc->n = A->n;
+    if (nsub == 0) nsub = 1;
+    pc->blocks.resize(nsub);
+    for (u64 b = 0; b < nsub; ++b) {
+        ko_pc::Block& B = pc->blocks[b];
+        B.inner = inner;
+        if (sub_ptr) B.idx.assign(sub_idx + sub_ptr[b], sub_idx + sub_ptr[b + 1]);
+        else { u64 lo, hi; ko_partition_range(A->n, nsub, b, &lo, &hi); for (u64 i = lo; i < hi; ++i) B.idx.push_back(i); }
+        if (overlap > 0 && !B.idx.empty()) {
+            std::vector<int> mark(A->n, 0);
+            for (u64 g : B.idx) mark[g] = 1;
+            for (u64 l = 1; l <= overlap; ++l) {
+                std::vector<u64> add;
+                for (u64 r = 0; r < A->n; ++r)
+                    if (mark[r] == (int)l)
+                        for (u64 p = A->row_ptr[r]; p < A->row_ptr[r + 1]; ++p) { u64 c = A->col_idx[p]; if (c < A->n && mark[c] == 0) add.push_back(c); }
+                for (u64 c : add) if (mark[c] == 0) mark[c] = (int)l + 1;
+            }
+            B.idx.clear();
+            for (u64 g = 0; g < A->n; ++g) if (mark[g]) B.idx.push_back(g);
+        }
+        const u64 m = B.idx.size();
+        B.lo = 0; B.hi = m;
+        B.rp.assign(m + 1, 0);
+        const u64 nnz = ko_submatrix(A, B.idx.data(), m, B.rp.data(), nullptr, nullptr);
+        if (nnz == ~(u64)0) { pc->status = KO_SOLVE_ERROR; continue; }
+        B.ci.resize(nnz); B.av.resize(nnz);
+        ko_submatrix(A, B.idx.data(), m, B.rp.data(), B.ci.data(), B.av.data());
+        B.lu.resize(nnz); B.dp.resize(m); B.inv_ud.resize(m);
+        ko_csr L{m, m, B.rp.data(), B.ci.data(), B.av.data()};
+        if (inner == 0) {
+            u64 bad = 0;
+            int st = ko_ilu0_factor(&L, B.lu.data(), B.dp.data(), B.inv_ud.data(), &bad);
+            if (st != KO_OK && pc->status == KO_OK) { pc->status = st; pc->bad_row = bad < m ? B.idx[bad] : 0; }
+        } else ko_jacobi_setup(&L, B.inv_ud.data());
+    }
+    return pc;
+}
+u64 ko_pc_asm_block_size(const ko_pc* pc, u64 b) { return pc->blocks[b].idx.size(); }
+void ko_pc_asm_block_indices(const ko_pc* pc, u64 b, u64* out) { std::copy(pc->blocks[b].idx.begin(), pc->blocks[b].idx.end(), out); }
 int ko_pc_status(const ko_pc* pc, u64* bad_row) { if (bad_row) *bad_row = pc->bad_row; return pc->status; }
 void ko_pc_apply(const ko_pc* pc, const double* r, double* z) { pc_apply(pc, r, z, pc->n); }
 void ko_pc_destroy(ko_pc* pc) { delete pc; }

@@ -104,6 +104,41 @@ int main() {
         REQUIRE(std::fabs(ctx.dot({1, 2, 3}, {4, -5, 6}) - 12.0) < 1e-12);
         REQUIRE(std::fabs(ctx.norm({1, 2, 3}) - std::sqrt(14.0)) < 1e-12);
     }
+    {   // asm_dense_lu_blocks (src/preconditioner/asm.rs:124-136): identity, two blocks -> apply(r) == r; PC factory; KspContext
+        Csr m; m.n = 4; m.rp = {0, 1, 2, 3, 4}; m.ci = {0, 1, 2, 3}; m.v = {1, 1, 1, 1};
+        DeviceCsr a = DeviceCsr::from_csr(ctx, 4, 4, m.rp, m.ci, m.v);
+        AdditiveSchwarz asm_pc(0, std::vector<std::vector<uint64_t>>{{0, 1}, {2, 3}});
+        asm_pc.setup(a);
+        std::vector<double> r = {1, 2, 3, 4}, z(4, 0.0);
+        asm_pc.apply(r, z);
+        REQUIRE(z == r);
+        Csr t = tridiag(12, -1, 2.5, -0.5);
+        DeviceCsr at = DeviceCsr::from_csr(ctx, t.n, t.n, t.rp, t.ci, t.v);
+        std::vector<double> ones(t.n, 1.0), b(t.n), x(t.n, 0.0), x2(t.n, 0.0);
+        at.matvec(ones, b);
+        PC::Built pc = PC::AdditiveSchwarz(0, 3).build(at);                 // pc_context.rs:75 -> device preconditioner
+        KspContext ksp{SolverKind::GmresLeft, &at, &pc, 1e-12, 200, 12};    // ksp_context.rs:54-69
+        SolveStats st = ksp.solve_context(b, x);
+        REQUIRE(st.converged); REQUIRE(rel_error(x, 1.0) < 1e-10);
+        SolveStats st2 = GmresSolver(12, 1e-12, 200).with_preconditioning(Preconditioning::Left).solve(at, &pc, b, x2);
+        REQUIRE(st2.iterations == st.iterations); REQUIRE(x == x2);
+        bool unsupported = false;
+        try { PC::AMG().build(at); } catch (const KError& e) { unsupported = (e.kind == KError::Unsupported); }
+        REQUIRE(unsupported);
+        unsupported = false;
+        try { KspContext k2{SolverKind::Minres, &at, nullptr, 1e-8, 10, 5}; k2.solve_context(b, x2); } catch (const KError& e) { unsupported = (e.kind == KError::Unsupported); }
+        REQUIRE(unsupported);
+    }
+    {   // Comm surface on one rank (src/parallel/mod.rs:4-35; rayon_comm.rs:56-78)
+        std::vector<double> g = {1, 2, 3}, out(3, 0.0), gathered;
+        ctx.scatter(g, out, 0);
+        REQUIRE(out == g);
+        ctx.gather(out, gathered, 0);
+        REQUIRE(gathered == g);
+        REQUIRE(std::fabs(ctx.comm_dot({1, 2, 3}, {4, -5, 6}) - 12.0) < 1e-12);
+        REQUIRE(std::fabs(ctx.comm_norm({1, 2, 3}) - std::sqrt(14.0)) < 1e-12);
+        REQUIRE(ctx.rank() == 0 && ctx.size() == 1);
+    }
     std::puts("CPP_HOST_API_OK");
     return 0;
 }

@@ -62,6 +62,21 @@ def main():
     assert ctx.rank() == rank and ctx.size() == world
     assert ctx.all_reduce(float(rank + 1)) == float(sum(range(1, world + 1)))
 
+    # rest of the Comm surface (parallel/mod.rs:9-22; mpi_comm.rs:74-109; core/wrappers.rs:134-156)
+    g = np.arange(3 * world, dtype=np.float64) * 1.5
+    out = np.zeros(3)
+    ctx.scatter(g if rank == 1 % world else None, out, root=1 % world)
+    assert np.array_equal(out, g[3 * rank:3 * rank + 3]), "comm scatter"
+    got = ctx.gather(np.array([rank, 10 * rank], dtype=np.int64), root=0)
+    if rank == 0:
+        assert np.array_equal(got, np.array([v for r in range(world) for v in (r, 10 * r)], dtype=np.int64)), "comm gather"
+    else:
+        assert got.size == 0
+    xs = np.random.default_rng(11).standard_normal(1000 * world)
+    ys = np.random.default_rng(12).standard_normal(1000 * world)
+    lo_, hi_ = kb.partition_range(xs.size, world, rank)
+    assert ctx.comm_dot(xs[lo_:hi_], ys[lo_:hi_]) == o.dot(xs, ys, nshards=world), "comm dot"
+    assert ctx.comm_norm(xs[lo_:hi_]) == float(np.sqrt(o.dot(xs, xs, nshards=world))), "distributed norm"
     empty_shard_cases(kb, o, parallel, ctx, rank, world)
     for kind, N in (("poisson3d", 12), ("convdiff3d", 10), ("convdiff2d", 20), ("varcoef27", 7)):
         n, lo, hi, rp, ci, v = parallel.shard_stencil(kind, N, world, rank)

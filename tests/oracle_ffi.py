@@ -67,6 +67,11 @@ def lib():
         L.ko_pc_create_ilu0.argtypes = [C.POINTER(KoCsr), C.c_uint64]
         L.ko_pc_create_ilu_literal.restype = C.c_void_p
         L.ko_pc_create_ilu_literal.argtypes = [C.c_uint64, f64p]
+        L.ko_pc_create_asm.restype = C.c_void_p
+        L.ko_pc_create_asm.argtypes = [C.POINTER(KoCsr), C.c_uint64, C.c_uint64, u64p, u64p, C.c_int]
+        L.ko_pc_asm_block_size.restype = C.c_uint64
+        L.ko_pc_asm_block_size.argtypes = [C.c_void_p, C.c_uint64]
+        L.ko_pc_asm_block_indices.argtypes = [C.c_void_p, C.c_uint64, u64p]
         L.ko_pc_status.restype = C.c_int
         L.ko_pc_status.argtypes = [C.c_void_p, u64p]
         L.ko_pc_apply.argtypes = [C.c_void_p, f64p, f64p]
@@ -255,6 +260,31 @@ class OPc:
     @classmethod
     def ilu0(cls, A, nblocks=1):
         return cls(lib().ko_pc_create_ilu0(A.ptr(), nblocks), A.n)
+
+    @classmethod
+    def asm(cls, A, overlap=0, subdomains=1, inner="ilu0"):
+        """AdditiveSchwarz (asm.rs:34-116): subdomains = int p (uniform chunks) or a list of index lists."""
+        if isinstance(subdomains, int):
+            nsub, ptr, idx = max(subdomains, 1), None, None
+        else:
+            nsub = len(subdomains)
+            ptr = np.zeros(nsub + 1, dtype=np.uint64)
+            ptr[1:] = np.cumsum([len(s) for s in subdomains])
+            idx = np.ascontiguousarray(np.concatenate([np.asarray(s, dtype=np.uint64) for s in subdomains]) if nsub and int(ptr[-1])
+                                       else np.zeros(0, dtype=np.uint64))
+        pc = cls(lib().ko_pc_create_asm(A.ptr(), overlap, nsub, _u(ptr) if ptr is not None else None,
+                                        _u(idx) if idx is not None else None, {"ilu0": 0, "jacobi": 1}[inner]), A.n)
+        pc.nsub = nsub
+        return pc
+
+    def asm_blocks(self):
+        out = []
+        for b in range(self.nsub):
+            k = int(lib().ko_pc_asm_block_size(self.h, b))
+            idx = np.zeros(max(k, 1), dtype=np.uint64)
+            lib().ko_pc_asm_block_indices(self.h, b, _u(idx))
+            out.append(idx[:k].copy())
+        return out
 
     @classmethod
     def ilu_literal(cls, dense):
