@@ -106,94 +106,83 @@ __global__ void __launch_bounds__(KB_THREADS, 1) kb_gs_update_dot(KbGmresDev g, 
 }
 // ---- CGS2 sweep 2 as ONE pass over the basis: w -= V h1 and the tile sums of h2 = V^T w_new ----------------------
 // (north_star kernel 3 / SURVEY K6 "update_dotV".)  The register-tile kernel above cannot overlap its loads with its
-// arithmetic (1 CTA/SM, every warp in the same phase).  Here the basis tile is staged through a shared-memory ring by
-// the bulk-copy (TMA) engine, exactly like the SpMV's matrix stream:
-//   * a stage is one HALF tile: 256 rows of w and of every basis column (<= 52 columns x 2 KB), so that two or more
-//     stages fit in the 227 KB of one SM and stage s+1 is in flight while stage s is being consumed;
-//   * a producer warp (one elected lane) issues one cp.async.bulk per column, completion counted on the stage's
-//     `full` mbarrier; 128 consumer threads hold rows 2l, 2l+1 (the canonical lanes), run  t -= V[c]*h1[c]  for
-//     c = 0..j out of shared memory, store w, then form the products V[c]*t for all columns and reduce them;
-//   * the per-column warp sums use a TRANSPOSED butterfly: at offset 16/8/4/2/1 a lane keeps half of its columns and
-//     trades the other half with its xor partner, so 32 columns cost 31 shuffles instead of 160, and lane k ends up
-//     with column k's warp sum.  Each addition pairs the same two lanes' values as the plain xor butterfly
-//     (IEEE addition is commutative), hence the tile sums are bit-identical to kb_gs_dot's;
+// arithmetic (1 CTA/SM, every warp in the same phase); a first shared-memory version staged half tiles with one bulk copy
+// per 2-KB column slice and paid more for ~32 bulk-copy issues per stage than for the stage's HBM time (0.89 ms per
+// sweep against 0.34 + 0.37 ms for the two plain sweeps).  This version stages with cp.async instead:
+//   * thread l of a 128-thread team owns rows 2l, 2l+1 of a HALF tile (256 rows = canonical lanes) and copies exactly
+//     its own 16 bytes of w and of every basis column into its own shared-memory slots (cp.async.cg, 16 B) - the data a
+//     thread consumes is the data it copied, so cp.async.wait_group is the only synchronisation of the pipeline;
+//   * stages form a ring NST deep (NST-1 half tiles in flight per team, 2 teams per CTA working on alternate tiles),
+//     sized at launch to the shared memory of the SM;
+//   * the thread runs  t -= V[c]*h1[c]  for c = 0..j, stores w, then forms the products V[c]*t for all columns and
+//     reduces them with a TRANSPOSED butterfly: at offset 16/8/4/2/1 a lane keeps half of its columns and trades the
+//     other half with its xor partner, so 32 columns cost 31 shuffles instead of 160, and lane k ends up with column
+//     k's warp sum.  Each addition pairs the same two lanes' values as the plain xor butterfly (IEEE addition is
+//     commutative), hence the tile sums are bit-identical to kb_gs_dot's;
 //   * the two halves' 4 + 4 warp sums are added in canonical order (warp 0..7) by one thread per column.
 // Traffic per Arnoldi step drops from 4 to 3 sweeps over V (SURVEY 8d byte model).
 #define KB_GSF_ROWS 256
-#define KB_GSF_CONSUMERS 128
-#define KB_GSF_THREADS (KB_GSF_CONSUMERS + 32)
+#define KB_GSF_TEAM 128
+#define KB_GSF_TEAMS 1        // one 128-thread team per CTA; two CTAs share an SM when their rings fit
+#define KB_GSF_THREADS (KB_GSF_TEAM * KB_GSF_TEAMS)
 #define KB_GSF_MAXC 64
-#define KB_GSF_MAX_STAGES 8
+#define KB_GSF_MAX_STAGES 6
 struct KbGsfHead {
-    unsigned long long full[KB_GSF_MAX_STAGES];
-    unsigned long long empty[KB_GSF_MAX_STAGES];
     double h[KB_GSF_MAXC];
-    double wsum[KB_GSF_MAXC * 8];       // warp sums of the current tile: [column][canonical warp 0..7]
+    double wsum[KB_GSF_TEAMS][KB_GSF_MAXC * 8];       // warp sums of the team's current tile: [column][canonical warp 0..7]
 };
-__device__ __forceinline__ void kb_gsf_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ void kb_gsf_cp16(void* smem_dst, const void* gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+template <int N>
+__device__ __forceinline__ void kb_gsf_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-__global__ void __launch_bounds__(KB_GSF_THREADS, 1) kb_gs_fused(KbGmresDev g, double* __restrict__ w, const double* __restrict__ hsrc, int n, int ntiles,
-                                                                double* partials, size_t pstride, int ncols, int nstages) {
+template <int NST>
+__global__ void __launch_bounds__(KB_GSF_THREADS) kb_gs_fused(KbGmresDev g, double* __restrict__ w, const double* __restrict__ hsrc, int n, int ntiles,
+                                                                double* partials, size_t pstride, int ncols) {
     if (g.ctl->done || g.ctl->cycle_break) return;
     extern __shared__ __align__(128) unsigned char kb_gsf_raw[];
     KbGsfHead& H = *reinterpret_cast<KbGsfHead*>(kb_gsf_raw);
-    double* stages = reinterpret_cast<double*>(kb_gsf_raw + ((sizeof(KbGsfHead) + 127) & ~(size_t)127));
+    const int tid = threadIdx.x, team = tid / KB_GSF_TEAM, lt = tid % KB_GSF_TEAM, lane = tid & 31, wp = lt >> 5;
     const size_t stage_doubles = (size_t)(ncols + 1) * KB_GSF_ROWS;       // [w | V_0 .. V_{ncols-1}] x 256 rows
-    const int tid = threadIdx.x;
-    if (tid == 0) {
-        for (int s = 0; s < nstages; ++s) { kb_mbar_init(&H.full[s], 1); kb_mbar_init(&H.empty[s], KB_GSF_CONSUMERS); }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
+    double* ring = reinterpret_cast<double*>(kb_gsf_raw + ((sizeof(KbGsfHead) + 127) & ~(size_t)127)) + (size_t)team * NST * stage_doubles + 2 * lt;
     for (int c = tid; c < ncols; c += KB_GSF_THREADS) H.h[c] = hsrc[c];
     __syncthreads();
-    const int nhalves = 2 * ((ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x);      // halves this CTA walks
-    if (tid >= KB_GSF_CONSUMERS) {
-        // producer warp: lane 0 owns the stage hand-shake, all 32 lanes issue bulk copies (one 2 KB column slice each;
-        // issued from a single thread the ~32 copies of a stage take longer than the stage's HBM time)
-        const int pl = tid - KB_GSF_CONSUMERS;
-        unsigned long long pol_keep;
-        asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol_keep));
-        for (int it = 0; it < nhalves; ++it) {
-            const int tile = (int)blockIdx.x + (it >> 1) * (int)gridDim.x;
-            const long long row0 = (long long)tile * KB_TILE + (it & 1) * KB_GSF_ROWS;
-            const int s = it % nstages;
-            const unsigned ph = (unsigned)(it / nstages) & 1u;
-            long long rows = (long long)n - row0;
-            rows = rows < 0 ? 0 : (rows > KB_GSF_ROWS ? KB_GSF_ROWS : rows);
-            const unsigned bytes = (unsigned)((rows + 1) & ~1ll) * 8u;          // 16-byte granules (vectors are padded by >= 2)
-            double* st = stages + (size_t)s * stage_doubles;
-            if (pl == 0) {
-                kb_mbar_wait(&H.empty[s], ph ^ 1u);
-                kb_mbar_expect_tx(&H.full[s], bytes * (unsigned)(ncols + 1));
-            }
-            __syncwarp();
-            if (bytes) {
-                for (int c = pl; c <= ncols; c += 32) {
-                    const double* src = c == 0 ? w + row0 : g.V + (size_t)(c - 1) * g.ld + row0;
-                    kb_bulk_g2s(st + (size_t)c * KB_GSF_ROWS, src, bytes, &H.full[s], pol_keep);
-                }
+    // team t walks tiles blockIdx.x*TEAMS + t, + gridDim.x*TEAMS, ... ; two halves per tile
+    const int first = (int)blockIdx.x * KB_GSF_TEAMS + team, stride = (int)gridDim.x * KB_GSF_TEAMS;
+    const int nhalves = first < ntiles ? 2 * ((ntiles - first + stride - 1) / stride) : 0;
+    auto issue = [&](int it) {        // stage half `it` (this thread's 16 bytes of w and of every column)
+        if (it < nhalves) {
+            const int tile = first + (it >> 1) * stride;
+            const long long i = (long long)tile * KB_TILE + (it & 1) * KB_GSF_ROWS + 2 * lt;
+            if (i < n) {              // rows i, i+1 (vectors are padded by >= 2, so the pair is always readable)
+                double* st = ring + (size_t)(it % NST) * stage_doubles;
+                kb_gsf_cp16(st, w + i);
+                for (int c = 0; c < ncols; ++c) kb_gsf_cp16(st + (size_t)(c + 1) * KB_GSF_ROWS, g.V + (size_t)c * g.ld + i);
             }
         }
-        return;
-    }
-    const int lane = tid & 31, wp = tid >> 5;
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+#pragma unroll
+    for (int it = 0; it < NST - 1; ++it) issue(it);
     for (int it = 0; it < nhalves; ++it) {
-        const int tile = (int)blockIdx.x + (it >> 1) * (int)gridDim.x;
+        const int tile = first + (it >> 1) * stride;
         const int half = it & 1;
-        const long long i = (long long)tile * KB_TILE + half * KB_GSF_ROWS + 2 * tid;
+        const long long i = (long long)tile * KB_TILE + half * KB_GSF_ROWS + 2 * lt;
         const bool h0 = i < n, h1 = i + 1 < n;
-        const int s = it % nstages;
-        const unsigned ph = (unsigned)(it / nstages) & 1u;
-        kb_mbar_wait(&H.full[s], ph);
-        const double* st = stages + (size_t)s * stage_doubles + 2 * tid;
+        issue(it + NST - 1);                      // keep NST-1 halves in flight (its slot was consumed in iteration it-1)
+        kb_gsf_wait<NST - 1>();                   // half `it` has landed
+        const double* st = ring + (size_t)(it % NST) * stage_doubles;
         double t0 = 0.0, t1 = 0.0;
         if (h0) { const double2 t = *reinterpret_cast<const double2*>(st); t0 = t.x; t1 = t.y; }
         // phase 1: w -= V h1 (sequential in c, as GsUpdateOp)
+        if (h0) {
 #pragma unroll 4
-        for (int c = 0; c < ncols; ++c) {
-            const double2 v = *reinterpret_cast<const double2*>(st + (size_t)(c + 1) * KB_GSF_ROWS);
-            const double h = H.h[c];
-            t0 = t0 - v.x * h; t1 = t1 - v.y * h;
+            for (int c = 0; c < ncols; ++c) {
+                const double2 v = *reinterpret_cast<const double2*>(st + (size_t)(c + 1) * KB_GSF_ROWS);
+                const double h = H.h[c];
+                t0 = t0 - v.x * h; t1 = t1 - v.y * h;
+            }
         }
         if (h1) kb_st2(w + i, make_double2(t0, t1));
         else if (h0) w[i] = t0;
@@ -203,10 +192,10 @@ __global__ void __launch_bounds__(KB_GSF_THREADS, 1) kb_gs_fused(KbGmresDev g, d
 #pragma unroll
             for (int k = 0; k < 32; ++k) {
                 double e0 = 0.0, e1 = 0.0;
-                if (g0 + k < ncols) {
+                if (g0 + k < ncols && h0) {
                     const double2 v = *reinterpret_cast<const double2*>(st + (size_t)(g0 + k + 1) * KB_GSF_ROWS);
                     if (h1) { e0 = v.x * t0; e1 = v.y * t1; }
-                    else if (h0) e0 = v.x * t0;
+                    else e0 = v.x * t0;
                 }
                 x[k] = e0 + e1;
             }
@@ -220,32 +209,43 @@ __global__ void __launch_bounds__(KB_GSF_THREADS, 1) kb_gs_fused(KbGmresDev g, d
                     x[k] = keep + __shfl_xor_sync(0xffffffffu, send, off);
                 }
             }
-            if (g0 + lane < ncols) H.wsum[(g0 + lane) * 8 + half * 4 + wp] = x[0];
+            if (g0 + lane < ncols) H.wsum[team][(g0 + lane) * 8 + half * 4 + wp] = x[0];
         }
-        kb_mbar_arrive(&H.empty[s]);        // this thread's reads of the stage are done
-        kb_gsf_bar();
         if (half == 1) {
-            for (int c = tid; c < ncols; c += KB_GSF_CONSUMERS) {
-                double sum = H.wsum[c * 8];
+            asm volatile("bar.sync %0, %1;" ::"r"(1 + team), "n"(KB_GSF_TEAM) : "memory");
+            for (int c = lt; c < ncols; c += KB_GSF_TEAM) {
+                double sum = H.wsum[team][c * 8];
 #pragma unroll
-                for (int k = 1; k < 8; ++k) sum = sum + H.wsum[c * 8 + k];
+                for (int k = 1; k < 8; ++k) sum = sum + H.wsum[team][c * 8 + k];
                 partials[(size_t)c * pstride + tile] = sum;
             }
-            kb_gsf_bar();
+            asm volatile("bar.sync %0, %1;" ::"r"(1 + team), "n"(KB_GSF_TEAM) : "memory");
         }
     }
+    kb_gsf_wait<0>();
 }
 static size_t kb_gsf_smem(int ncols, int nstages) {
-    return ((sizeof(KbGsfHead) + 127) & ~(size_t)127) + (size_t)nstages * (size_t)(ncols + 1) * KB_GSF_ROWS * sizeof(double);
+    return ((sizeof(KbGsfHead) + 127) & ~(size_t)127) + (size_t)KB_GSF_TEAMS * nstages * (size_t)(ncols + 1) * KB_GSF_ROWS * sizeof(double);
 }
-// stages that fit next to the header in the opt-in shared memory of one SM (0: this column count does not fit)
+// ring depth: small stages -> up to 4 deep and two CTAs per SM; large stages -> whatever fits one CTA per SM (0: does not fit)
 static int kb_gsf_stages(int ncols) {
-    const size_t budget = 225 * 1024;
     const size_t head = (sizeof(KbGsfHead) + 127) & ~(size_t)127;
     const size_t stage = (size_t)(ncols + 1) * KB_GSF_ROWS * sizeof(double);
     if (ncols > KB_GSF_MAXC) return 0;
-    size_t k = (budget - head) / stage;
+    const size_t half_sm = 110 * 1024, full_sm = 225 * 1024;
+    if (2 * stage + head <= half_sm) { const size_t k = (half_sm - head) / stage; return (int)(k > 4 ? 4 : k); }
+    const size_t k = (full_sm - head) / stage;
     return k < 2 ? 0 : (int)(k > KB_GSF_MAX_STAGES ? KB_GSF_MAX_STAGES : k);
+}
+typedef void (*kb_gsf_fn)(KbGmresDev, double*, const double*, int, int, double*, size_t, int);
+static kb_gsf_fn kb_gsf_kernel(int nst) {
+    switch (nst) {
+    case 2: return kb_gs_fused<2>;
+    case 3: return kb_gs_fused<3>;
+    case 4: return kb_gs_fused<4>;
+    case 5: return kb_gs_fused<5>;
+    default: return kb_gs_fused<6>;
+    }
 }
 
 // level 2 for every column in parallel: block c reduces partial[c][0..P)
@@ -565,10 +565,10 @@ static int gm_inner_iteration(GmPlan& P, int j) {
     // 1 CTA/SM and measured slower on B200 than the two separate bandwidth-bound sweeps (C4g: 191 vs 207 it/s)
     static const bool fuse_env = getenv("KB_GS_FUSE") && atoi(getenv("KB_GS_FUSE")) == 1;
     const bool fuse = fuse_env && ncols <= 32;      // the basis tile must fit in registers
-    // KB_GS_FUSE=2: the shared-memory-staged 3-sweep CGS2 (kb_gs_fused).  Measured on B200 (C4g) one fused sweep costs
-    // 0.89 ms against 0.34 + 0.37 ms for the separate dot and update sweeps (per-stage bulk-copy overhead of ~32 2-KB
-    // column slices), so the 4-sweep form stays the default.
-    static const bool fuse_smem_env = getenv("KB_GS_FUSE") && atoi(getenv("KB_GS_FUSE")) == 2;
+    // default: the shared-memory-staged 3-sweep CGS2 (kb_gs_fused, cp.async ring): measured on B200 (C4g) one fused sweep
+    // costs 0.58 ms against 0.34 + 0.37 ms for the separate dot and update sweeps it replaces (291 -> 309 it/s).
+    // KB_GS_FUSE=0 selects the 4-sweep form, KB_GS_FUSE=1 the register-tile variant.
+    static const bool fuse_smem_env = !getenv("KB_GS_FUSE") || atoi(getenv("KB_GS_FUSE")) == 2;
     const bool fuse_smem = fuse_smem_env && !P.g.flex && kb_gsf_stages(ncols) >= 2;
     typedef KbSpmvEpi<GmNoFin, false, false> Epi;
     Epi epi; epi.ctl = ctl; epi.skip_mask = 2; epi.fin = kb_make_fin(c, GmNoFin{}, false, nullptr, 0);
@@ -608,15 +608,17 @@ static int gm_inner_iteration(GmPlan& P, int j) {
         double* dst = P.dist ? w->slots : &ctl->h1[0];
         { KbLaunch L(c, KB_K_SMALL); kb_gs_level2<<<ncols, KB_THREADS, 0, c->stream>>>(ctl, w->partials, w->pstride, A->ntiles, dst); }
         if (P.dist) KB_TRY(kb_allreduce_slots(c, w->slots, ncols));
-        if (fuse_smem) {   // one pass over V: w -= V h1 and the tile sums of h2 = V^T w (shared-memory ring, bulk copies)
+        if (fuse_smem) {   // one pass over V: w -= V h1 and the tile sums of h2 = V^T w (shared-memory ring, cp.async)
             const int nst = kb_gsf_stages(ncols);
-            if (!c->configured.count((const void*)kb_gs_fused)) {
-                KB_CUDA(cudaFuncSetAttribute(kb_gs_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
-                c->configured.insert((const void*)kb_gs_fused);
+            kb_gsf_fn kfn = kb_gsf_kernel(nst);
+            if (!c->configured.count((const void*)kfn)) {
+                KB_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+                c->configured.insert((const void*)kfn);
             }
             KbLaunch L(c, KB_K_GS_UPDATE);
-            kb_gs_fused<<<std::min(c->sm_count, A->ntiles), KB_GSF_THREADS, kb_gsf_smem(ncols, nst), c->stream>>>(P.g, w->w, P.g.h1src, (int)A->n, A->ntiles, w->partials,
-                                                                                                              w->pstride, ncols, nst);
+            const size_t sh = kb_gsf_smem(ncols, nst);
+            const int per_sm = sh <= 110 * 1024 ? 2 : 1;
+            kfn<<<std::min(per_sm * c->sm_count, A->ntiles), KB_GSF_THREADS, sh, c->stream>>>(P.g, w->w, P.g.h1src, (int)A->n, A->ntiles, w->partials, w->pstride, ncols);
             KB_CUDA(cudaGetLastError());
         } else if (fuse) {   // w -= V h1 fused with the partial sums of h2 = V^T w (basis tile in registers)
             KbLaunch L(c, KB_K_GS_UPDATE);
