@@ -340,6 +340,7 @@ int kb_tiles_build(kb_pc_s* pc, unsigned* d_err, KbTileSolve** out);
 int kb_tiles_apply(kb_pc_s* pc, KbTileSolve* t, const double* d_r, double* d_z, const KbCtl* skip_ctl, int skip_mask);
 void kb_tiles_free(KbTileSolve* t);
 void kb_tiles_grid(const KbTileSolve* t, int* nx, int* ny, int* nz);
+int kb_tiles_trace_get(KbTileSolve* t, unsigned long long* out, int* tx, int* ty, int* tz);
 struct KbMarch;                                      // kb_trsv_march.cu: pencil-marching solves (full-stencil box grids)
 int kb_march_build(kb_pc_s* pc, int gx, int gy, int gz, unsigned* d_err, KbMarch** out);
 int kb_march_apply(kb_pc_s* pc, KbMarch* m, const double* d_r, double* d_z, const KbCtl* skip_ctl, int skip_mask);
@@ -710,4 +711,12 @@ extern "C" int kb_debug_march_trace(kb_pc pc, unsigned long long* out, int* px, 
     cudaSetDevice(pc->ctx->device);
     cudaStreamSynchronize(pc->ctx->stream);
     return kb_march_trace_get(x->march, out, px, py);
+}
+
+extern "C" int kb_debug_tiles_trace(kb_pc pc, unsigned long long* out, int* tx, int* ty, int* tz) {
+    KbIluExtra* x = pc && pc->kind == KB_PC_ILU0 ? extra_of(pc) : nullptr;
+    if (!x || !x->tiles) return 0;
+    cudaSetDevice(pc->ctx->device);
+    cudaStreamSynchronize(pc->ctx->stream);
+    return kb_tiles_trace_get(x->tiles, out, tx, ty, tz);
 }
