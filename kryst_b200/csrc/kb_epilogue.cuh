@@ -91,7 +91,7 @@ static int kb_finish_dist(kb_ctx_s* c, Fin fin, KbCtl* ctl, double* slots, int n
 
 // one launch over a set of canonical tiles (all tiles when list == nullptr); dispatches on the kernel kind
 template <class Epi, bool RESID, bool GH>
-static int kb_launch_spmv_tiles(kb_csr_s* A, KbSpmvArgs a, Epi epi, const int* list, int count, int finalize) {
+static int kb_launch_spmv_tiles(kb_csr_s* A, KbSpmvArgs a, Epi epi, const int* list, int count, int finalize, bool pdl = false) {
     if (count <= 0) return KB_OK;
     kb_ctx_s* c = A->ctx;
     a.tile_list = list; a.tile0 = 0; a.ntiles_launch = count; a.finalize = finalize;
@@ -105,12 +105,11 @@ static int kb_launch_spmv_tiles(kb_csr_s* A, KbSpmvArgs a, Epi epi, const int* l
         static const int per_sm = getenv("KB_BULK_CTAS_PER_SM") ? atoi(getenv("KB_BULK_CTAS_PER_SM")) : 2;
         const int grid = std::min(per_sm * c->sm_count, count);
         KbLaunch L(c, KB_K_SPMV);
-        kfn<<<grid, KB_BULK_THREADS, sizeof(KbBulkSmem), c->stream>>>(a, tb, epi);
-        KB_CUDA(cudaGetLastError());
+        KB_CUDA(kb_launch_ex(pdl && kb_pdl_enabled(), kfn, dim3(grid), dim3(KB_BULK_THREADS), sizeof(KbBulkSmem), c->stream, a, tb, epi));
         return KB_OK;
     }
     KbLaunch L(c, KB_K_SPMV);
-    if (A->kind == 0) kb_spmv_stream<Epi, RESID, GH><<<count, KB_THREADS, 0, c->stream>>>(a, epi);
+    if (A->kind == 0) KB_CUDA(kb_launch_ex(pdl && kb_pdl_enabled(), kb_spmv_stream<Epi, RESID, GH>, dim3(count), dim3(KB_THREADS), 0, c->stream, a, epi));
     else if (A->vec == 8) kb_spmv_vector<Epi, RESID, 8, GH><<<count, KB_THREADS, 0, c->stream>>>(a, epi);
     else if (A->vec == 16) kb_spmv_vector<Epi, RESID, 16, GH><<<count, KB_THREADS, 0, c->stream>>>(a, epi);
     else kb_spmv_vector<Epi, RESID, 32, GH><<<count, KB_THREADS, 0, c->stream>>>(a, epi);
@@ -124,7 +123,7 @@ static int kb_launch_spmv_tiles(kb_csr_s* A, KbSpmvArgs a, Epi epi, const int* l
 // CTA of the second one, so the reduction tree is unchanged.
 template <class Epi, bool RESID>
 static int kb_launch_spmv(kb_csr_s* A, const double* x, double* y, const double* b, const double* w, double* partials,
-                          size_t pstride, Epi epi, double* halo_x = nullptr, bool halo_prepushed = false) {
+                          size_t pstride, Epi epi, double* halo_x = nullptr, bool halo_prepushed = false, bool pdl = false) {
     kb_ctx_s* c = A->ctx;
     const bool dist = halo_x != nullptr && A->dist && c->size > 1;
     if (A->n == 0 && !dist) return KB_OK;
@@ -146,6 +145,6 @@ static int kb_launch_spmv(kb_csr_s* A, const double* x, double* y, const double*
         if (gh) return kb_launch_spmv_tiles<Epi, RESID, true>(A, a, epi, A->tiles_boundary, A->n_boundary, 1);
         return kb_launch_spmv_tiles<Epi, RESID, false>(A, a, epi, A->tiles_boundary, A->n_boundary, 1);
     }
-    if (gh) return kb_launch_spmv_tiles<Epi, RESID, true>(A, a, epi, nullptr, A->ntiles, 1);
-    return kb_launch_spmv_tiles<Epi, RESID, false>(A, a, epi, nullptr, A->ntiles, 1);
+    if (gh) return kb_launch_spmv_tiles<Epi, RESID, true>(A, a, epi, nullptr, A->ntiles, 1, pdl);
+    return kb_launch_spmv_tiles<Epi, RESID, false>(A, a, epi, nullptr, A->ntiles, 1, pdl);
 }

@@ -15,6 +15,8 @@
 #include <cuda_runtime.h>
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
+#include <utility>
 #include <string>
 #include <vector>
 #include <set>
@@ -172,6 +174,15 @@ __device__ __forceinline__ bool kb_arrive_last(unsigned* ticket, unsigned nblock
     return *sflag != 0;
 }
 
+// Programmatic dependent launch (PDL): the kernels of an iteration are launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization, so the next kernel's CTAs are scheduled (and run their prologue)
+// while the current kernel drains, instead of after a full kernel boundary (~2-3 us per boundary inside a CUDA graph;
+// an iteration of the 512^2 problem is three kernels of ~3 us of work each).  Every kernel on such a chain starts with
+// kb_pdl_wait() - nothing written by the previous kernel (control block included) is read before it - and releases its
+// own dependents right away.  For a kernel launched without the attribute both calls are no-ops.
+__device__ __forceinline__ void kb_pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void kb_pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ---------------------------------------------------------------------------------------------
 // Generic fused BLAS-1 "tile kernel": one 512-element tile per block, 2 adjacent elements per
 // thread (128-bit accesses), NRED fused canonical dots, scalar epilogue by the last block.
@@ -182,6 +193,8 @@ __device__ __forceinline__ bool kb_arrive_last(unsigned* ticket, unsigned nblock
 // ---------------------------------------------------------------------------------------------
 template <class Op>
 __global__ void __launch_bounds__(KB_THREADS) kb_tile_kernel(Op op) {
+    kb_pdl_wait();
+    kb_pdl_launch_dependents();
     if (op.skip()) return;
     constexpr int NR = Op::NRED > 0 ? Op::NRED : 1;
     __shared__ double sm[NR * 8];
@@ -235,3 +248,24 @@ __device__ __forceinline__ void kb_st2(double* p, double2 v) { *reinterpret_cast
 #endif  // __CUDACC__
 
 static inline int kb_num_tiles(uint64_t n) { return (int)((n + KB_TILE - 1) / KB_TILE); }
+
+#ifdef __CUDACC__
+// launch with (pdl = true) or without the programmatic-dependent-launch attribute
+template <class... KArgs, class... Args>
+static inline cudaError_t kb_launch_ex(bool pdl, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
+// Measured on B200 (CUDA-graph replay): no gain at 512^2 (54.5k -> 53.7k it/s) and a 5 % loss at 256^3 (1835 -> 1747
+// it/s: dependents that become resident early take shared memory and issue slots from the draining kernel), so the
+// attribute is opt-in (KB_PDL=1); the griddepcontrol instructions stay in the kernels and are no-ops without it.
+static inline bool kb_pdl_enabled() {
+    static const bool on = getenv("KB_PDL") && atoi(getenv("KB_PDL")) == 1;
+    return on;
+}
+#endif

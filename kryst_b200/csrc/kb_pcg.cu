@@ -169,6 +169,8 @@ struct PcgXpayOp : KbRedBase {        // K4: p = z + beta p  (pcg.rs:215-217)
 // mailboxes (NVLink peer stores) - the separate 29 us kb_halo_push launch of round 1 is gone, and the transfer
 // overlaps the rest of this kernel and the launch gap before the SpMV that consumes it.
 __global__ void __launch_bounds__(KB_THREADS) kb_pcg_xpay_push(PcgXpayOp op, const KbHaloDev* __restrict__ hp) {
+    kb_pdl_wait();
+    kb_pdl_launch_dependents();
     if (op.skip()) return;
     const int tile = hp->tile_perm[blockIdx.x];            // sending tiles first
     const long long i = (long long)tile * KB_TILE + 2 * threadIdx.x;
@@ -310,7 +312,7 @@ static int pcg_launch_iteration(kb_csr_s* A, const kb_pc_s* pc, KbPcgWs* w) {
     const double* inv = pc ? pc->inv_diag : nullptr;
     {   // K2
         KbSpmvEpi<PcgApFin, true, false> epi; epi.ctl = w->ctl; epi.fin = kb_make_fin(c, PcgApFin{w->ctl}, DIST, w->slots, 1);
-        KB_TRY((kb_launch_spmv<KbSpmvEpi<PcgApFin, true, false>, false>(A, w->p, w->ap, nullptr, w->p, w->partials, w->pstride, epi, DIST ? w->p : nullptr, fused_push != nullptr)));
+        KB_TRY((kb_launch_spmv<KbSpmvEpi<PcgApFin, true, false>, false>(A, w->p, w->ap, nullptr, w->p, w->partials, w->pstride, epi, DIST ? w->p : nullptr, fused_push != nullptr, /*pdl=*/fused_push != nullptr || !DIST)));
         if (DIST) KB_TRY((kb_finish_dist<PcgApFin>(c, PcgApFin{w->ctl}, w->ctl, w->slots, 1)));
     }
     if (pc && pc->kind != KB_PC_JACOBI) {   // K3 with a generic preconditioner
@@ -328,16 +330,14 @@ static int pcg_launch_iteration(kb_csr_s* A, const kb_pc_s* pc, KbPcgWs* w) {
         PcgUpdateOp<PcgUpdateFin> op; op.n = (long long)w->n; op.partials = w->partials; op.pstride = w->pstride; op.ticket = c->ticket;
         op.x = w->x; op.p = w->p; op.r = w->r; op.ap = w->ap; op.inv = inv; op.z = w->z; op.ctl = w->ctl;
         op.fin = kb_make_fin(c, PcgUpdateFin{w->ctl}, DIST, w->slots, 2);
-        { KbLaunch L(c, KB_K_PCG_UPDATE); kb_tile_kernel<<<A->ntiles, KB_THREADS, 0, c->stream>>>(op); }
-        KB_CUDA(cudaGetLastError());
+        { KbLaunch L(c, KB_K_PCG_UPDATE); KB_CUDA(kb_launch_ex(kb_pdl_enabled(), kb_tile_kernel<PcgUpdateOp<PcgUpdateFin>>, dim3(A->ntiles), dim3(KB_THREADS), 0, c->stream, op)); }
         if (DIST) KB_TRY((kb_finish_dist<PcgUpdateFin>(c, PcgUpdateFin{w->ctl}, w->ctl, w->slots, 2)));
     }
     {   // K4
         PcgXpayOp op; op.n = (long long)w->n; op.partials = nullptr; op.pstride = 0; op.ticket = c->ticket;
         op.z = w->z; op.p = w->p; op.ctl = w->ctl;
-        if (fused_push) { KbLaunch L(c, KB_K_XPAY); kb_pcg_xpay_push<<<A->ntiles, KB_THREADS, 0, c->stream>>>(op, fused_push); }
-        else { KbLaunch L(c, KB_K_XPAY); kb_tile_kernel<<<A->ntiles, KB_THREADS, 0, c->stream>>>(op); }
-        KB_CUDA(cudaGetLastError());
+        if (fused_push) { KbLaunch L(c, KB_K_XPAY); KB_CUDA(kb_launch_ex(kb_pdl_enabled(), kb_pcg_xpay_push, dim3(A->ntiles), dim3(KB_THREADS), 0, c->stream, op, fused_push)); }
+        else { KbLaunch L(c, KB_K_XPAY); KB_CUDA(kb_launch_ex(kb_pdl_enabled(), kb_tile_kernel<PcgXpayOp>, dim3(A->ntiles), dim3(KB_THREADS), 0, c->stream, op)); }
     }
     return KB_OK;
 }

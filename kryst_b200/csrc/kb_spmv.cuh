@@ -72,6 +72,8 @@ __device__ __forceinline__ double kb_xload(const KbSpmvArgs& a, const double* xg
 // Epi: struct with static constexpr bool WDOT, YDOT (slot order: <w,y> then <y,y>); __device__ bool skip() const; template <int BAR> __device__ void finish_block(double* ssum) const  (all threads of the last CTA)
 template <class Epi, bool RESID, bool GH = false>
 __global__ void __launch_bounds__(KB_THREADS) kb_spmv_stream(KbSpmvArgs a, Epi epi) {
+    kb_pdl_wait();
+    kb_pdl_launch_dependents();
     if (epi.skip()) return;
     const double* xg = nullptr;
     if (GH) xg = kb_halo_wait(a);
@@ -185,6 +187,8 @@ __global__ void __launch_bounds__(KB_THREADS) kb_spmv_stream(KbSpmvArgs a, Epi e
 // ---------------------------------------------------------------------------------------------
 template <class Epi, bool RESID, int VEC, bool GH = false>
 __global__ void __launch_bounds__(KB_THREADS) kb_spmv_vector(KbSpmvArgs a, Epi epi) {
+    kb_pdl_wait();
+    kb_pdl_launch_dependents();
     if (epi.skip()) return;
     const double* xg = nullptr;
     if (GH) { xg = kb_halo_wait(a); __syncthreads(); }

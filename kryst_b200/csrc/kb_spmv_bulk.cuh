@@ -242,6 +242,8 @@ __device__ __forceinline__ void kb_bulk_init_barriers(KbBulkSmem& S) {
 
 template <class Epi, bool RESID, bool GH = false, bool PROD = false>
 __global__ void __launch_bounds__(KB_BULK_THREADS, 2) kb_spmv_bulk(KbSpmvArgs a, KbChunkTable tb, Epi epi) {
+    kb_pdl_wait();
+    kb_pdl_launch_dependents();
     if (epi.skip()) return;
     const double* xg = nullptr;
     if (GH) xg = kb_halo_wait(a);          // ordered before the gathers by the __syncthreads() below
