@@ -31,6 +31,7 @@ struct KbTileSolve {
     ulonglong2* mail = nullptr;
     unsigned* sync = nullptr;            // [0],[1] epoch of L / U ; [2],[3] finish tickets
     int face_len = 0;                    // packets per tile: by*bz + bx*bz + bx*by
+    int variant = 0;                     // 0 flag hand-off, 1 packets + communication warp (fine-grained), 2 packets at tile granularity
     unsigned long long* trace = nullptr; // diagnostics (KB_TILES_TRACE=1)
 };
 
@@ -424,6 +425,141 @@ __global__ void __launch_bounds__(KB_TL_THREADS) kb_trsv_tiles_ll(KbTileArgs a) 
     }
 }
 
+// ---- packet faces, tile-granular ("kb_trsv_tiles_pk") ------------------------------------------------------------
+// Same tile-level pipeline as kb_trsv_tiles, but the hand-off is made of the data itself: every face row publishes
+// its value as a 16-byte tagged packet the moment it is solved, and a successor tile starts by polling, thread by
+// thread, exactly the packets its own rows read across a face.  Compared with the flag hand-off this removes the
+// release fence after the last step, the flag poll + barrier, the dependent L2 read of the neighbours' values and the
+// per-apply flag memset; the in-tile step stays the lean one (operands that cross a face sit in registers).
+template <bool UPPER, int R>
+__global__ void __launch_bounds__(KB_THREADS, R <= 2 ? 4 : 1) kb_trsv_tiles_pk(KbTileArgs a) {
+    if (kb_skip(a.skip_ctl, a.skip_mask)) return;
+    __shared__ double ytile[KB_TILE_ROWS_MAX];
+    const int tid = threadIdx.x;
+    const int bxy = a.bx * a.by, trows = bxy * a.bz;
+    const int nlevels = a.bx + a.by + a.bz - 2;
+    const int sx = a.nx;
+    const int offB = a.by * a.bz, offC = offB + a.bx * a.bz;
+    const unsigned epoch = *reinterpret_cast<volatile unsigned*>(a.sync + (UPPER ? 1 : 0)) + 1u;
+    const unsigned tag = 2u * epoch + (UPPER ? 1u : 0u);
+    for (int t = blockIdx.x; t < a.ntiles; t += gridDim.x) {
+        const int tile = a.order[t];
+        const int TI = tile % a.tx, TJ = (tile / a.tx) % a.ty, TK = tile / (a.tx * a.ty);
+        const int my_mail = tile * a.face_len;
+        int row[R], lvl[R], di[R][3], ext[R][3], outp[R][3];
+        double rh[R], dg[R], cv[R][3], xv[R][3];
+#pragma unroll
+        for (int m = 0; m < R; ++m) {
+            const int q = m * KB_THREADS + tid;
+            row[m] = -1; lvl[m] = -1; rh[m] = 0.0; dg[m] = 1.0;
+#pragma unroll
+            for (int e = 0; e < 3; ++e) { di[m][e] = -2; cv[m][e] = 0.0; xv[m][e] = 0.0; ext[m][e] = -1; outp[m][e] = -1; }
+            if (q < trows) {
+                const int li = q % a.bx, lj = (q / a.bx) % a.by, lk = q / bxy;
+                const int gi = TI * a.bx + li, gj = TJ * a.by + lj, gk = TK * a.bz + lk;
+                const int r = gi + a.nx * (gj + a.ny * gk);
+                if (gi < a.nx && gj < a.ny && gk < a.nz && r < a.n) {
+                    row[m] = r;
+                    lvl[m] = li + lj + lk;
+                    rh[m] = a.rhs[r];
+                    const int pd = a.dptr[r];
+                    const int p0 = UPPER ? pd + 1 : a.rp[r];
+                    const int p1 = UPPER ? a.rp[r + 1] : pd;
+                    if (UPPER) dg[m] = a.inv_diag[r];
+#pragma unroll
+                    for (int e = 0; e < 3; ++e) {
+                        if (p0 + e < p1) {
+                            const int c = a.col[p0 + e];
+                            cv[m][e] = a.lu[p0 + e];
+                            const int d = UPPER ? c - r : r - c;
+                            int slot = -1;
+                            if (d == 1) { if (UPPER ? li + 1 < a.bx : li >= 1) slot = UPPER ? q + 1 : q - 1; else ext[m][e] = my_mail + (lj + a.by * lk); }
+                            else if (d == sx) { if (UPPER ? lj + 1 < a.by : lj >= 1) slot = UPPER ? q + a.bx : q - a.bx; else ext[m][e] = my_mail + offB + (li + a.bx * lk); }
+                            else { if (UPPER ? lk + 1 < a.bz : lk >= 1) slot = UPPER ? q + bxy : q - bxy; else ext[m][e] = my_mail + offC + (li + a.bx * lj); }
+                            di[m][e] = slot;
+                        }
+                    }
+                    if (!UPPER) {
+                        if (li == a.bx - 1 && gi + 1 < a.nx) outp[m][0] = (tile + 1) * a.face_len + (lj + a.by * lk);
+                        if (lj == a.by - 1 && gj + 1 < a.ny) outp[m][1] = (tile + a.tx) * a.face_len + offB + (li + a.bx * lk);
+                        if (lk == a.bz - 1 && gk + 1 < a.nz) outp[m][2] = (tile + a.tx * a.ty) * a.face_len + offC + (li + a.bx * lj);
+                    } else {
+                        if (li == 0 && gi >= 1) outp[m][0] = (tile - 1) * a.face_len + (lj + a.by * lk);
+                        if (lj == 0 && gj >= 1) outp[m][1] = (tile - a.tx) * a.face_len + offB + (li + a.bx * lk);
+                        if (lk == 0 && gk >= 1) outp[m][2] = (tile - a.tx * a.ty) * a.face_len + offC + (li + a.bx * lj);
+                    }
+                }
+            }
+        }
+        // ---- the hand-off: every thread waits for the packets its own rows read across a face.  All of a thread's
+        //      packets are requested before the first one is looked at (one L2 round trip, not one per packet).
+        {
+            ulonglong2 qv[R][3];
+#pragma unroll
+            for (int m = 0; m < R; ++m)
+#pragma unroll
+                for (int e = 0; e < 3; ++e) { qv[m][e] = make_ulonglong2(0ull, 0ull); if (ext[m][e] >= 0) qv[m][e] = kb_tl_load(a.mail + ext[m][e]); }
+            unsigned spins = 0;
+            bool pending = true;
+            while (pending) {
+                pending = false;
+#pragma unroll
+                for (int m = 0; m < R; ++m)
+#pragma unroll
+                    for (int e = 0; e < 3; ++e)
+                        if (ext[m][e] >= 0 && !kb_tl_ok(qv[m][e], tag)) { qv[m][e] = kb_tl_load(a.mail + ext[m][e]); pending = true; }
+                if (pending) {
+                    if (++spins > 2u) __nanosleep(64);
+                    if ((spins & 1023u) == 0u) {
+                        if (spins > (1u << 22)) atomicExch(a.err, 1u);
+                        if (*reinterpret_cast<volatile unsigned*>(a.err)) break;
+                    }
+                }
+            }
+#pragma unroll
+            for (int m = 0; m < R; ++m)
+#pragma unroll
+                for (int e = 0; e < 3; ++e) if (ext[m][e] >= 0) xv[m][e] = kb_tl_value(qv[m][e]);
+        }
+        __syncthreads();          // (the previous tile's readers of ytile are done as well)
+        // ---- internal wavefront: the step of kb_trsv_tiles plus the face packets
+        for (int s0 = 0; s0 < nlevels; ++s0) {
+            const int step = UPPER ? nlevels - 1 - s0 : s0;
+#pragma unroll
+            for (int m = 0; m < R; ++m) {
+                if (lvl[m] == step) {
+                    double v[3];
+#pragma unroll
+                    for (int e = 0; e < 3; ++e) {
+                        const double y = ytile[max(di[m][e], 0)];
+                        v[e] = di[m][e] >= 0 ? y : xv[m][e];
+                    }
+                    double s = rh[m];
+#pragma unroll
+                    for (int e = 0; e < 3; ++e) s = s - cv[m][e] * v[e];
+                    if (UPPER) s = s * dg[m];
+                    ytile[m * KB_THREADS + tid] = s;
+                    a.out[row[m]] = s;
+                    if ((outp[m][0] & outp[m][1] & outp[m][2]) != -1) {      // a face row (rare): publish
+#pragma unroll
+                        for (int e = 0; e < 3; ++e) if (outp[m][e] >= 0) kb_tl_store(a.mail + outp[m][e], s, tag);
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    }
+    if (tid == 0) {
+        __threadfence();
+        const unsigned tk = atomicAdd(a.sync + 2 + (UPPER ? 1 : 0), 1u);
+        if (tk == gridDim.x - 1u) {
+            a.sync[2 + (UPPER ? 1 : 0)] = 0u;
+            a.sync[UPPER ? 1 : 0] = epoch;
+            __threadfence();
+        }
+    }
+}
+
 // ---- host ------------------------------------------------------------------------------------------------------
 void kb_tiles_grid(const KbTileSolve* t, int* nx, int* ny, int* nz) { *nx = t->nx; *ny = t->ny; *nz = t->nz; }
 void kb_tiles_free(KbTileSolve* t) {
@@ -433,8 +569,9 @@ void kb_tiles_free(KbTileSolve* t) {
 }
 
 template <bool UPPER, int R>
-static int tiles_occupancy(int* occ, bool ll = false) {
-    if (ll) KB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, kb_trsv_tiles_ll<UPPER, R>, KB_TL_THREADS, 0));
+static int tiles_occupancy(int* occ, int variant = 0) {
+    if (variant == 2) KB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, kb_trsv_tiles_pk<UPPER, R>, KB_THREADS, 0));
+    else if (variant == 1) KB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, kb_trsv_tiles_ll<UPPER, R>, KB_TL_THREADS, 0));
     else KB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, kb_trsv_tiles<UPPER, R>, KB_THREADS, 0));
     return KB_OK;
 }
@@ -497,11 +634,16 @@ int kb_tiles_build(kb_pc_s* pc, unsigned* d_err, KbTileSolve** out) {
         if (cudaMemcpyAsync(t->order[1], ord.data(), (size_t)nt * sizeof(int), cudaMemcpyHostToDevice, c->stream) != cudaSuccess) { st = KB_SOLVE_ERROR; break; }
         if (cudaStreamSynchronize(c->stream) != cudaSuccess) { st = KB_SOLVE_ERROR; break; }
         // fine-grained packet variant (3-D grids; KB_TILES_LL=0 keeps the flag hand-off)
-        // Measured on B200 (256^3): flag hand-off 0.71 ms per solve; packet faces 1.92 ms with the polling inside the
-        // compute step (~500 instructions per step), 1.21 ms with the communication warp (its ~200 instructions per
-        // step, not the 8 compute warps, set the step time).  Opt-in (KB_TILES_LL=1) until that warp is table-driven.
-        const bool ll = nz > 1 && getenv("KB_TILES_LL") && atoi(getenv("KB_TILES_LL")) == 1 && t->by + 2 * t->bx <= 32 &&
-                        t->by * t->bz + t->bx * t->bz + t->bx * t->by <= KB_TL_HALO_MAX;
+        // Measured on B200 (256^3, per solve): release/acquire flag hand-off 0.71 ms.  Packet faces (the data is its own
+        // flag): 1.92 ms with the polling inside the compute step (~500 instructions per step), 1.21 ms with a
+        // communication warp (fine-grained: a tile starts as soon as its first rows can), 1.09-1.29 ms with packets at tile
+        // granularity - every variant has ~200 polling threads per waiting tile where the flag kernel has 7, and the
+        // strong loads of ~400 waiting tiles slow the L2 for everybody.  The flag hand-off stays the default
+        // (KB_TILES_LL=1 / 2 select the packet variants; both are bit-identical and covered by the GPU tests).
+        const int ll_env = getenv("KB_TILES_LL") ? atoi(getenv("KB_TILES_LL")) : 0;      // 0 flags, 1 fine-grained (communication warp), 2 packets at tile granularity
+        t->variant = nz > 1 ? ll_env : 0;
+        if (t->variant == 1 && !(t->by + 2 * t->bx <= 32 && t->by * t->bz + t->bx * t->bz + t->bx * t->by <= KB_TL_HALO_MAX)) t->variant = 2;
+        const bool ll = t->variant != 0;
         if (ll) {
             t->face_len = t->by * t->bz + t->bx * t->bz + t->bx * t->by;
             const size_t slots = (size_t)nt * t->face_len;
@@ -515,7 +657,8 @@ int kb_tiles_build(kb_pc_s* pc, unsigned* d_err, KbTileSolve** out) {
         }
         // the whole grid must be co-resident: a tile may wait on a tile owned by any other CTA
         int occ[2] = {1, 1};
-        const bool use_ll = t->mail != nullptr;
+        const int use_ll = t->mail != nullptr ? t->variant : 0;
+        if (!t->mail) t->variant = 0;
         if (t->rows_per_thread == 4) { if ((st = tiles_occupancy<false, 4>(&occ[0], use_ll)) != KB_OK || (st = tiles_occupancy<true, 4>(&occ[1], use_ll)) != KB_OK) break; }
         else if (t->rows_per_thread == 2) { if ((st = tiles_occupancy<false, 2>(&occ[0], use_ll)) != KB_OK || (st = tiles_occupancy<true, 2>(&occ[1], use_ll)) != KB_OK) break; }
         else { if ((st = tiles_occupancy<false, 1>(&occ[0], use_ll)) != KB_OK || (st = tiles_occupancy<true, 1>(&occ[1], use_ll)) != KB_OK) break; }
@@ -539,6 +682,17 @@ int kb_tiles_apply(kb_pc_s* pc, KbTileSolve* t, const double* d_r, double* d_z, 
     a.mail = t->mail; a.sync = t->sync; a.face_len = t->face_len;
     a.lag = getenv("KB_TILES_LAG") ? atoi(getenv("KB_TILES_LAG")) : 3;
     a.trace = t->trace;
+    if (t->mail && t->variant == 2) {       // packets at tile granularity: no flags, no memset
+        for (int u = 0; u < 2; ++u) {
+            a.order = t->order[u]; a.flags = nullptr; a.rhs = u == 0 ? d_r : pc->tmp; a.out = u == 0 ? pc->tmp : d_z;
+            KbLaunch L(c, KB_K_TRSV);
+            if (t->rows_per_thread == 4) { if (u) kb_trsv_tiles_pk<true, 4><<<t->grid[1], KB_THREADS, 0, c->stream>>>(a); else kb_trsv_tiles_pk<false, 4><<<t->grid[0], KB_THREADS, 0, c->stream>>>(a); }
+            else if (t->rows_per_thread == 2) { if (u) kb_trsv_tiles_pk<true, 2><<<t->grid[1], KB_THREADS, 0, c->stream>>>(a); else kb_trsv_tiles_pk<false, 2><<<t->grid[0], KB_THREADS, 0, c->stream>>>(a); }
+            else { if (u) kb_trsv_tiles_pk<true, 1><<<t->grid[1], KB_THREADS, 0, c->stream>>>(a); else kb_trsv_tiles_pk<false, 1><<<t->grid[0], KB_THREADS, 0, c->stream>>>(a); }
+        }
+        KB_CUDA(cudaGetLastError());
+        return KB_OK;
+    }
     if (t->mail) {       // fine-grained packet variant: no flags, no memset
         for (int u = 0; u < 2; ++u) {
             a.order = t->order[u]; a.flags = nullptr; a.rhs = u == 0 ? d_r : pc->tmp; a.out = u == 0 ? pc->tmp : d_z;
