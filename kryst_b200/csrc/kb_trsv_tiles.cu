@@ -142,6 +142,7 @@ __global__ void __launch_bounds__(KB_THREADS) kb_trsv_tiles(KbTileArgs a) {
                 int v;
                 do {
                     asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+                    if (v == 0 && a.lag > 0) __nanosleep(a.lag);   // polite polling (KB_TILES_SLEEP ns): fewer strong loads competing with the working tiles
                     if (v == 0 && (++spins & 1023u) == 0u) {      // bounded: give up (and let everybody give up) instead of hanging
                         if (spins > (1u << 26)) atomicExch(a.err, 1u);
                         if (*reinterpret_cast<volatile unsigned*>(a.err)) break;
@@ -704,6 +705,7 @@ int kb_tiles_apply(kb_pc_s* pc, KbTileSolve* t, const double* d_r, double* d_z, 
         KB_CUDA(cudaGetLastError());
         return KB_OK;
     }
+    a.lag = getenv("KB_TILES_SLEEP") ? atoi(getenv("KB_TILES_SLEEP")) : 0;      // (the flag kernel reuses the field as its poll back-off)
     KB_CUDA(cudaMemsetAsync(t->flags, 0, 2 * (size_t)t->ntiles * sizeof(int), c->stream));
     {
         a.order = t->order[0]; a.flags = t->flags; a.rhs = d_r; a.out = pc->tmp;
