@@ -50,6 +50,8 @@ struct KbMarch {
     unsigned* err = nullptr;         // borrowed: the preconditioner's error word
     unsigned long long* trace = nullptr;   // diagnostics, allocated on demand (KB_MARCH_TRACE=1)
     int grid = 1, warps = KB_MARCH_WARPS;
+    int lean = 1, threads = 0, lag = 8;   // lean kernel (kb_trsv_lean): default; KB_MARCH_LEAN=0 keeps the v2 kernel
+    size_t smem[2] = {0, 0};
 };
 
 // ---- setup: pre-skewed copy of the factor + full-stencil check ---------------------------------------------------
@@ -156,6 +158,8 @@ struct KbMarchArgs {
     const double* __restrict__ coef;   // pre-skewed, interleaved
     const double* __restrict__ rhs; double* out;
     int n, nx, ny, nz, px, py, npencils;
+    int nsteps;                      // local steps of one pencil: nz + LX + LY - 2, rounded up to a multiple of 4
+    int lag;                         // lean kernel: steps a consumer group keeps behind its L2 producers
     int gpx, gpy, ngroups;           // CTA groups of GA x GB pencils
     const int* __restrict__ order;   // group ids by level (ascending)
     ulonglong2* mail;
@@ -200,7 +204,7 @@ __global__ void __launch_bounds__(GA * GB * 32, 1) kb_trsv_march(KbMarchArgs a) 
     const unsigned tag = 2u * epoch + (UPPER ? 1u : 0u);
     const int la = lane % LX, lb = lane / LX, sk = la + lb;
     const long long plane = (long long)a.nx * a.ny;
-    const int nsteps = a.nz + SK;                                   // local steps of one pencil
+    const int nsteps = a.nsteps;                                    // local steps of one pencil
     const int offset = LX * wa + LY * wb;                           // this pencil's delay inside the group
     const int nsteps_cta = nsteps + LX * (GA - 1) + LY * (GB - 1);
 
@@ -382,6 +386,270 @@ __global__ void __launch_bounds__(GA * GB * 32, 1) kb_trsv_march(KbMarchArgs a) 
     }
 }
 
+// ---- lean march ("v3") -------------------------------------------------------------------------------------------
+// Same schedule, same pre-skewed factor copy, same mailbox as kb_trsv_march above, but the step is stripped to the
+// recurrence.  The v2 step above is ~235 SASS instructions on one dependent chain (ring bookkeeping, five cp.async,
+// packet prefetch / validation / hand-over by shuffle, un-skewing output ring): 0.6 us per step with 4 warps, 1.2 us
+// with 16, times nx+ny+nz steps.  Here the CTA is warp-specialised:
+//   * compute warps (one pencil each) execute per step: 4-5 LDS (coefficients, rhs), 2 shuffles, 2 predicated LDS
+//     (incoming face values), the 6-7 FP64 operations of the row, 2 predicated STS (outgoing faces), one predicated
+//     STG (the solution, stored skewed: the 32-byte sectors are completed in L2 by the neighbouring lanes within
+//     LX+LY steps, long before they are evicted), one cp.async (rhs delay line) and the step barrier;
+//   * coefficients arrive through a 4-stage ring of 2 steps each, ONE cp.async.bulk (TMA engine, mbarrier
+//     complete_tx) per stage and warp: consecutive steps of a pencil are contiguous in the pre-skewed copy;
+//   * ALL L2 packet traffic belongs to helper warps: lane f owns one line of the group's outer faces, validates /
+//     prefetches the incoming packets (register ring, PD steps ahead), drops their values into the shared-memory face
+//     slots the compute lanes read like any in-group face, and publishes the outgoing face values one step after they
+//     were computed.  Compute warps contain no global loads on the dependent chain and no packet code at all.
+// Per-row arithmetic and its order are those of kb_trsv_march: same bits.
+#define KM_PD 4                      // packet prefetch distance (steps) = unroll of the step loop
+
+template <bool UPPER, int LX, int LY, int GA, int GB, int RD>
+struct KmShape {
+    static constexpr int NC = UPPER ? 4 : 3;
+    static constexpr int SK = LX + LY - 2;
+    static constexpr int D = RD - SK - 1;            // rhs prefetch distance (slabs)
+    static constexpr int NCW = GA * GB;              // compute warps
+    static constexpr int NA = GB * LY;               // lines of the group's A faces (in and out)
+    static constexpr int NB = LY > 1 ? GA * LX : 0;  // lines of the B faces
+    static constexpr int NHW = (NA + NB + 31) / 32;  // helper warps
+    static constexpr int THREADS = (NCW + NHW) * 32;
+    static constexpr int CSTEPS = 8;                 // coefficient ring: 4 stages x 2 steps
+    static constexpr int WARP_DOUBLES = CSTEPS * NC * 32 + RD * 32;
+    static constexpr int FA = (GA + 1) * GB * LY;    // faceA[par][wa' = 0..GA][wb][lb]: slot 0 = from L2, slot wa+1 = written by pencil (wa,wb)
+    static constexpr int FB = LY > 1 ? (GB + 1) * GA * LX : 0;
+    static constexpr size_t SMEM = ((size_t)NCW * WARP_DOUBLES + 2 * (FA + FB)) * sizeof(double) + (size_t)NCW * 4 * sizeof(unsigned long long);
+    static_assert((RD & (RD - 1)) == 0 && D >= 3, "rhs delay line: power of two, deep enough");
+};
+
+struct KmLane { int c_lo, c_hi, cA_lo, cB_lo; long long rbase, rstep; };
+// march-space windows of lane (la,lb) of pencil (Pa,Pb): rows that exist (c_lo..c_hi) and rows whose a-1 / b-1 neighbour exists
+template <bool UPPER, int LX, int LY>
+__device__ __forceinline__ KmLane km_lane(const KbMarchArgs& a, int Pa, int Pb, int la, int lb) {
+    KmLane g;
+    const long long plane = (long long)a.nx * a.ny;
+    const int ca = Pa * LX + la, cb = Pb * LY + lb;
+    const bool in_ab = Pa >= 0 && Pb >= 0 && Pa < a.px && Pb < a.py && ca < a.nx && cb < a.ny;
+    const int gi = UPPER ? a.nx - 1 - ca : ca, gj = UPPER ? a.ny - 1 - cb : cb;
+    const long long row0 = (long long)gi + (long long)a.nx * gj;
+    auto kcount = [&](long long x) -> int {
+        const long long room = (long long)a.n - row0 - x;
+        if (!in_ab || room <= 0) return 0;
+        const long long k = (room + plane - 1) / plane;
+        return (int)(k > a.nz ? a.nz : k);
+    };
+    if (!UPPER) { g.c_lo = 0; g.c_hi = kcount(0); g.cA_lo = 0; g.cB_lo = 0; }
+    else { g.c_hi = a.nz; g.c_lo = a.nz - kcount(0); g.cA_lo = a.nz - kcount(1); g.cB_lo = a.nz - kcount(a.nx); }
+    g.rstep = UPPER ? -plane : plane;
+    g.rbase = UPPER ? row0 + plane * (a.nz - 1) : row0;
+    return g;
+}
+__device__ __forceinline__ unsigned km_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void km_bulk(void* dst, const void* src, unsigned bytes, unsigned long long* bar, unsigned long long pol) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(km_u32(bar)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(km_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(km_u32(bar)), "l"(pol)
+                 : "memory");
+}
+
+template <bool UPPER, int LX, int LY, int GA, int GB, int RD>
+__global__ void __launch_bounds__(KmShape<UPPER, LX, LY, GA, GB, RD>::THREADS, 1) kb_trsv_lean(KbMarchArgs a) {
+    if (kb_skip(a.skip_ctl, a.skip_mask)) return;
+    typedef KmShape<UPPER, LX, LY, GA, GB, RD> SH;
+    constexpr int NC = SH::NC, SK = SH::SK, D = SH::D, NCW = SH::NCW, NA = SH::NA, NB = SH::NB, FA = SH::FA, FB = SH::FB;
+    constexpr int RM = RD - 1, PD = KM_PD, FACES = LY == 1 ? 1 : LX + LY, THREADS = SH::THREADS;
+    constexpr unsigned STAGE_BYTES = 2u * NC * 32u * sizeof(double);
+    static_assert(LX * LY == 32, "a pencil is one warp");
+    static_assert(LX % 4 == 0 && (LY == 1 || LY % 4 == 0), "pencil delays inside a group must be multiples of the unroll");
+    extern __shared__ __align__(128) double km_smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double* faceA = km_smem + (size_t)NCW * SH::WARP_DOUBLES;        // [2][GA+1][GB][LY]
+    double* faceB = faceA + 2 * FA;                                   // [2][GB+1][GA][LX]
+    unsigned long long* full = reinterpret_cast<unsigned long long*>(faceB + 2 * FB);     // [NCW][4]
+
+    // L and U share the mailbox: their tags never coincide (even / odd), and both advance once per apply
+    const unsigned epoch = *reinterpret_cast<volatile unsigned*>(a.sync + (UPPER ? 1 : 0)) + 1u;
+    const unsigned tag = 2u * epoch + (UPPER ? 1u : 0u);
+    const int nsteps = a.nsteps;                                          // local steps of one pencil (multiple of 4)
+    const int nsteps_cta = nsteps + LX * (GA - 1) + LY * (GB - 1) + 4;   // + one block in which only the helpers work (last outgoing faces)
+    if (threadIdx.x < NCW * 4) kb_mbar_init_cta(full + threadIdx.x, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncthreads();
+    unsigned kc = 0;                  // coefficient stages consumed by this warp so far (slot = kc & 3, phase = (kc >> 2) & 1)
+    unsigned long long pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+
+    for (int gi_ = blockIdx.x; gi_ < a.ngroups; gi_ += gridDim.x) {
+        const int group = a.order[gi_];
+        const int Pa0 = (group % a.gpx) * GA, Pb0 = (group / a.gpx) * GB;
+        for (int i = threadIdx.x; i < 2 * (FA + FB); i += THREADS) faceA[i] = 0.0;
+        __syncthreads();
+        if (warp < NCW) {
+            // ================= compute warp: one pencil =================
+            const int wa = warp % GA, wb = warp / GA;
+            const int Pa = Pa0 + wa, Pb = Pb0 + wb;
+            const bool valid = Pa < a.px && Pb < a.py;
+            const int pencil = Pa + a.px * Pb;
+            const int la = lane % LX, lb = lane / LX, sk = la + lb;
+            const KmLane g = km_lane<UPPER, LX, LY>(a, Pa, Pb, la, lb);
+            const int offset = LX * wa + LY * wb;                      // this pencil's delay inside the group
+            const int t_lo = g.c_lo + sk;
+            const unsigned span = (unsigned)(g.c_hi - g.c_lo);         // rows of this lane
+            double* cring = km_smem + (size_t)warp * SH::WARP_DOUBLES;  // [4 stages][2 steps][NC][32]
+            double* rring = cring + SH::CSTEPS * NC * 32 + lane;        // [RD][32], lane-private column
+            unsigned long long* fullw = full + warp * 4;
+            const double* p_coef = a.coef + (size_t)pencil * nsteps * (NC * 32);
+            const double* fa_in = faceA + (wa * GB + wb) * LY + lb;    // read by la == 0 (+ parity * FA)
+            double* fa_out = faceA + ((wa + 1) * GB + wb) * LY + lb;   // written by la == LX-1
+            const double* fb_in = faceB + (wb * GA + wa) * LX + la;    // read by lb == 0 (+ parity * FB)
+            double* fb_out = faceB + ((wb + 1) * GA + wa) * LX + la;   // written by lb == LY-1
+            if (valid) {
+                if (lane == 0) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        if (2 * j < nsteps) { const unsigned sl = (kc + j) & 3u; km_bulk(cring + sl * (2 * NC * 32), p_coef + (size_t)j * (2 * NC * 32), STAGE_BYTES, fullw + sl, pol); }
+                }
+#pragma unroll
+                for (int c = 0; c < D; ++c) {
+                    if ((unsigned)(c - g.c_lo) < span) kb_cp_async8(rring + (c & RM) * 32, a.rhs + (g.rbase + g.rstep * c));
+                    kb_cp_async_commit();
+                }
+            }
+            long long r_ld = g.rbase + g.rstep * D;       // row of slab tl + D
+            long long r_out = g.rbase - g.rstep * sk;     // row of this lane at step tl: c = tl - sk
+            double s = 0.0;
+            __syncthreads();                              // the helpers' step-0 face values are in place
+            for (int t0 = 0; t0 < nsteps_cta; t0 += 4) {
+                const int tl0 = t0 - offset;
+                const bool in_range = valid && tl0 >= 0 && tl0 < nsteps;      // warp-uniform, same for the 4 steps
+                const unsigned half = (kc >> 1) & 1u, ph = (kc >> 2) & 1u;
+                const double* cb = cring + half * (4 * NC * 32) + lane;
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    if (in_range) {
+                        const int tl = tl0 + u;
+                        if ((u & 1) == 0) kb_mbar_wait_cta(fullw + (half << 1) + (u >> 1), ph);
+                        const double* cp = cb + u * (NC * 32);
+                        const double vA = cp[0], vB = LY > 1 ? cp[32] : 0.0, vC = cp[64], dg = UPPER ? cp[96] : 1.0;
+                        kb_cp_async_wait<D - 1>();
+                        const double rh = rring[((tl - sk) & RM) * 32];
+                        double ya = __shfl_up_sync(0xffffffffu, s, 1);
+                        double yb = LY > 1 ? __shfl_up_sync(0xffffffffu, s, LX) : 0.0;
+                        const int par_r = (u & 1) ^ 1, par_w = u & 1;          // t0 is a multiple of 4
+                        if (la == 0) ya = fa_in[par_r * FA];
+                        if (LY > 1 && lb == 0) yb = fb_in[par_r * FB];
+                        double v;
+                        if (!UPPER) { v = rh - vC * s; if (LY > 1) v = v - vB * yb; v = v - vA * ya; }          // ascending column: c-1, b-1, a-1
+                        else { v = rh - vA * ya; if (LY > 1) v = v - vB * yb; v = v - vC * s; v = v * dg; }      // a+1, b+1, c+1, then 1/u_ii
+                        const bool act = (unsigned)(tl - t_lo) < span;
+                        s = act ? v : 0.0;
+                        if (la == LX - 1) fa_out[par_w * FA] = s;
+                        if (LY > 1 && lb == LY - 1) fb_out[par_w * FB] = s;
+                        if (act) a.out[r_out] = s;
+                        r_out += g.rstep;
+                        // rhs slab tl + D into the delay line
+                        if ((unsigned)(tl + D - g.c_lo) < span) kb_cp_async8(rring + ((tl + D) & RM) * 32, a.rhs + r_ld);
+                        kb_cp_async_commit();
+                        r_ld += g.rstep;
+                        if (u & 1) {      // this stage is consumed: refill its slot with the stage 4 ahead
+                            __syncwarp();
+                            if (lane == 0 && tl + 7 < nsteps) {
+                                const unsigned sl = (half << 1) + (u >> 1);
+                                km_bulk(cring + sl * (2 * NC * 32), p_coef + (size_t)(tl + 7) * (NC * 32), STAGE_BYTES, fullw + sl, pol);
+                            }
+                        }
+                    }
+                    __syncthreads();                      // step barrier: faces written in step t are read in step t + 1
+                }
+                if (in_range) kc += 2u;
+            }
+            kb_cp_async_wait<0>();
+        } else {
+            // ================= helper warp: the group's L2 faces =================
+            const int line = (warp - NCW) * 32 + lane;
+            const bool isA = line < NA, live = line < NA + NB;
+            int wa_c = 0, wb_c = 0, la_c = 0, lb_c = 0, wa_p = 0, wb_p = 0, la_p = 0, lb_p = 0, fidx = 0;
+            if (isA) { wb_c = wb_p = line / LY; lb_c = lb_p = line % LY; wa_p = GA - 1; la_p = LX - 1; fidx = lb_c; }
+            else if (live) { const int q = line - NA; wa_c = wa_p = q / LX; la_c = la_p = q % LX; wb_p = GB - 1; lb_p = LY - 1; fidx = LY + la_c; }
+            const int Pa_c = Pa0 + wa_c, Pb_c = Pb0 + wb_c, Pa_p = Pa0 + wa_p, Pb_p = Pb0 + wb_p;
+            const KmLane gc = km_lane<UPPER, LX, LY>(a, Pa_c, Pb_c, la_c, lb_c);
+            const KmLane gp = km_lane<UPPER, LX, LY>(a, Pa_p, Pb_p, la_p, lb_p);
+            const bool has_in = live && Pa_c < a.px && Pb_c < a.py && (isA ? Pa_c > 0 : Pb_c > 0);
+            const bool has_out = live && Pa_p < a.px && Pb_p < a.py && (isA ? Pa_p + 1 < a.px : Pb_p + 1 < a.py);
+            const int skew_c = isA ? lb_c : la_c;
+            int pk_lo = 0, pk_hi = 0;                      // consumer-local steps at which an incoming packet exists
+            if (has_in) { pk_lo = (isA ? gc.cA_lo : gc.cB_lo) + skew_c; pk_hi = gc.c_hi + skew_c; if (pk_hi < pk_lo) pk_hi = pk_lo; }
+            int tp_lo = 0, tp_hi = 0;                      // producer-local steps at which an outgoing value exists
+            if (has_out) { tp_lo = gp.c_lo + la_p + lb_p; tp_hi = gp.c_hi + la_p + lb_p; if (tp_hi < tp_lo) tp_hi = tp_lo; }
+            const unsigned in_span = (unsigned)(pk_hi - pk_lo), out_span = (unsigned)(tp_hi - tp_lo);
+            const int off_c = LX * wa_c + LY * wb_c, off_p = LX * wa_p + LY * wb_p;
+            const ulonglong2* mail_in = a.mail + (size_t)(Pa_c + a.px * Pb_c) * nsteps * FACES + fidx;                    // + tl * FACES
+            ulonglong2* mail_out = a.mail + ((size_t)(Pa_p + a.px * Pb_p + (isA ? 1 : a.px)) * nsteps) * FACES + fidx;   // + (tlp - depth) * FACES
+            const int depth = isA ? LX - 1 : LY - 1;
+            double* in_slot = isA ? faceA + wb_c * LY + lb_c : faceB + wa_c * LX + la_c;                                   // slot 0 (+ parity * FA/FB)
+            const double* out_slot = isA ? faceA + (GA * GB + wb_p) * LY + lb_p : faceB + (GB * GA + wa_p) * LX + la_p;   // slot GA / GB
+            const int fstride = isA ? FA : FB;
+            // keep the distance: start only when the producer is `lag` steps further than the wavefront needs
+            if (in_span > 0u) {
+                const int tw = min(pk_lo + a.lag, pk_hi - 1);
+                (void)kb_pkt_wait(mail_in + (size_t)tw * FACES, tag, a.err);
+            }
+            // packet of compute step t' lives at consumer-local step t' - off_c; ring slot t' & 3
+            ulonglong2 pk[PD];
+            {
+                double v0 = 0.0;
+                const int tl = 0 - off_c;
+                if ((unsigned)(tl - pk_lo) < in_span) v0 = kb_pkt_value(kb_pkt_wait(mail_in + (size_t)tl * FACES, tag, a.err));
+                if (live) in_slot[1 * fstride] = v0;       // step 0 reads parity (0 - 1) & 1
+#pragma unroll
+                for (int j = 1; j <= PD; ++j) {
+                    const int tj = j - off_c;
+                    pk[j & (PD - 1)] = make_ulonglong2(0ull, 0ull);
+                    if ((unsigned)(tj - pk_lo) < in_span) pk[j & (PD - 1)] = kb_pkt_load(mail_in + (size_t)tj * FACES);
+                }
+            }
+            __syncthreads();                              // pairs with the compute warps' initial barrier
+            for (int t0 = 0; t0 < nsteps_cta; t0 += PD) {
+#pragma unroll
+                for (int u = 0; u < PD; ++u) {
+                    const int t = t0 + u;
+                    // incoming value of compute step t + 1 -> parity t & 1, then request the packet of step t + 1 + PD
+                    {
+                        const int tl = t + 1 - off_c;
+                        double v = 0.0;
+                        if ((unsigned)(tl - pk_lo) < in_span) {
+                            ulonglong2 q = pk[(u + 1) & (PD - 1)];
+                            if (!kb_pkt_ok(q, tag)) q = kb_pkt_wait(mail_in + (size_t)tl * FACES, tag, a.err);
+                            v = kb_pkt_value(q);
+                        }
+                        if (live) in_slot[(u & 1) * fstride] = v;
+                        pk[(u + 1) & (PD - 1)] = make_ulonglong2(0ull, 0ull);
+                        if ((unsigned)(tl + PD - pk_lo) < in_span) pk[(u + 1) & (PD - 1)] = kb_pkt_load(mail_in + (size_t)(tl + PD) * FACES);
+                    }
+                    // outgoing value computed in step t - 1 (parity (t - 1) & 1)
+                    {
+                        const int tlp = t - 1 - off_p;
+                        if ((unsigned)(tlp - tp_lo) < out_span) kb_pkt_store(mail_out + (ptrdiff_t)(tlp - depth) * FACES, out_slot[((u & 1) ^ 1) * fstride], tag);
+                    }
+                    __syncthreads();
+                }
+            }
+        }
+        // (the next group's face clearing is ordered after every read of this group by the barrier above)
+    }
+    // the last CTA to finish publishes the epoch: every CTA has read it by then
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const unsigned t = atomicAdd(a.sync + 2 + (UPPER ? 1 : 0), 1u);
+        if (t == gridDim.x - 1u) {
+            a.sync[2 + (UPPER ? 1 : 0)] = 0u;
+            a.sync[UPPER ? 1 : 0] = epoch;
+            __threadfence();
+        }
+    }
+}
+
 // ---- host ------------------------------------------------------------------------------------------------------
 void kb_march_free(KbMarch* m) {
     if (!m) return;
@@ -408,6 +676,22 @@ static size_t march_smem(bool upper, bool two_d, int g) {
     return ((size_t)warps * KbMarchShape<8, 4>::warp_doubles(upper) + KbMarchShape<8, 4>::face_doubles(warps)) * sizeof(double);
 }
 
+// lean kernel: (ga, gb) group shapes.  3-D: 1x1, 2x2 (rhs ring 32), 2x4, 4x4 (ring 16: shared memory); 2-D: g x 1 (ring 64)
+struct KmKernel { kb_march_fn fn; size_t smem; int threads; };
+template <bool UPPER, int LX, int LY, int GA, int GB, int RD>
+static KmKernel km_make() { typedef KmShape<UPPER, LX, LY, GA, GB, RD> SH; return KmKernel{kb_trsv_lean<UPPER, LX, LY, GA, GB, RD>, SH::SMEM, SH::THREADS}; }
+static KmKernel lean_kernel(bool upper, bool two_d, int ga, int gb) {
+    if (two_d) {
+        if (ga == 1) return upper ? km_make<true, 32, 1, 1, 1, 64>() : km_make<false, 32, 1, 1, 1, 64>();
+        if (ga == 2) return upper ? km_make<true, 32, 1, 2, 1, 64>() : km_make<false, 32, 1, 2, 1, 64>();
+        return upper ? km_make<true, 32, 1, 4, 1, 64>() : km_make<false, 32, 1, 4, 1, 64>();
+    }
+    if (ga == 1) return upper ? km_make<true, 8, 4, 1, 1, 32>() : km_make<false, 8, 4, 1, 1, 32>();
+    if (ga == 2 && gb == 2) return upper ? km_make<true, 8, 4, 2, 2, 32>() : km_make<false, 8, 4, 2, 2, 32>();
+    if (ga == 2) return upper ? km_make<true, 8, 4, 2, 4, 16>() : km_make<false, 8, 4, 2, 4, 16>();
+    return upper ? km_make<true, 8, 4, 4, 4, 16>() : km_make<false, 8, 4, 4, 4, 16>();
+}
+
 // gx, gy, gz: the box grid detected from the factor's pattern (kb_trsv_tiles.cu).  *out stays nullptr (KB_OK) when the
 // pattern is not a full stencil.
 int kb_march_build(kb_pc_s* pc, int gx, int gy, int gz, unsigned* d_err, KbMarch** out) {
@@ -421,7 +705,7 @@ int kb_march_build(kb_pc_s* pc, int gx, int gy, int gz, unsigned* d_err, KbMarch
     if (two_d) { m->nx = gx; m->ny = 1; m->nz = gy; m->lx = 32; m->ly = 1; m->faces = 1; }
     else { m->nx = gx; m->ny = gy; m->nz = gz; m->lx = 8; m->ly = 4; m->faces = 12; }
     m->px = (m->nx + m->lx - 1) / m->lx; m->py = (m->ny + m->ly - 1) / m->ly;
-    m->nsteps = m->nz + m->lx + m->ly - 2;
+    m->nsteps = (m->nz + m->lx + m->ly - 2 + 3) & ~3;      // (padded steps: zero coefficients, no rows)
     const long long np = (long long)m->px * m->py;
     const long long slots = np * m->nsteps * m->faces;
     const long long skewed = np * m->nsteps * 32;
@@ -447,9 +731,12 @@ int kb_march_build(kb_pc_s* pc, int gx, int gy, int gz, unsigned* d_err, KbMarch
         if (cudaMemcpyAsync(&h_bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, c->stream) != cudaSuccess || cudaStreamSynchronize(c->stream) != cudaSuccess) { st = KB_SOLVE_ERROR; break; }
         if (h_bad) { cudaFree(d_bad); kb_march_free(m); return KB_OK; }      // not a full stencil: other kernels take it
         // groups of ga x gb pencils in level order
-        int g = 4;
-        if (getenv("KB_MARCH_GROUP")) { const int e = atoi(getenv("KB_MARCH_GROUP")); if (e == 1 || e == 2 || e == 4) g = e; }
-        m->ga = g; m->gb = two_d ? 1 : g;
+        m->lean = getenv("KB_MARCH_LEAN") ? atoi(getenv("KB_MARCH_LEAN")) : 1;
+        if (getenv("KB_MARCH_LAG")) m->lag = std::max(KM_PD + 1, atoi(getenv("KB_MARCH_LAG")));
+        int g = m->lean && !two_d ? 2 : 4;
+        int g2 = 0;                                   // lean 3-D only: "24" = 2 x 4 pencils
+        if (getenv("KB_MARCH_GROUP")) { const int e = atoi(getenv("KB_MARCH_GROUP")); if (e == 1 || e == 2 || e == 4) g = e; else if (e == 24 && m->lean && !two_d) { g = 2; g2 = 4; } }
+        m->ga = g; m->gb = two_d ? 1 : (g2 ? g2 : g);
         m->gpx = (m->px + m->ga - 1) / m->ga; m->gpy = (m->py + m->gb - 1) / m->gb;
         m->ngroups = m->gpx * m->gpy;
         std::vector<int> ord((size_t)m->ngroups), lev((size_t)m->ngroups);
@@ -468,10 +755,13 @@ int kb_march_build(kb_pc_s* pc, int gx, int gy, int gz, unsigned* d_err, KbMarch
         int cap = 1 << 30;
         for (int u = 0; u < 2 && st == KB_OK; ++u) {
             kb_march_fn f = march_kernel(u == 1, two_d, m->ga);
-            const size_t sh = march_smem(u == 1, two_d, m->ga);
+            size_t sh = march_smem(u == 1, two_d, m->ga);
+            int threads = m->warps * 32;
+            if (m->lean) { const KmKernel k = lean_kernel(u == 1, two_d, m->ga, m->gb); f = k.fn; sh = k.smem; threads = k.threads; }
+            m->smem[u] = sh; m->threads = threads;
             if (cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh) != cudaSuccess) { st = KB_SOLVE_ERROR; break; }
             int occ = 0;
-            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, f, m->warps * 32, sh) != cudaSuccess || occ < 1) { st = KB_SOLVE_ERROR; break; }
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, f, threads, sh) != cudaSuccess || occ < 1) { st = KB_SOLVE_ERROR; break; }
             cap = std::min(cap, occ * c->sm_count);
         }
         if (st != KB_OK) break;
@@ -490,13 +780,14 @@ int kb_march_apply(kb_pc_s* pc, KbMarch* m, const double* d_r, double* d_z, cons
     const bool two_d = m->ly == 1;
     KbMarchArgs a{};
     a.n = m->n; a.nx = m->nx; a.ny = m->ny; a.nz = m->nz; a.px = m->px; a.py = m->py; a.npencils = m->npencils;
-    a.gpx = m->gpx; a.gpy = m->gpy; a.ngroups = m->ngroups;
+    a.gpx = m->gpx; a.gpy = m->gpy; a.ngroups = m->ngroups; a.nsteps = m->nsteps; a.lag = m->lag;
     a.order = m->order; a.mail = m->mail; a.sync = m->sync; a.err = m->err; a.skip_ctl = skip_ctl; a.skip_mask = skip_mask; a.trace = m->trace;
     for (int u = 0; u < 2; ++u) {
         a.coef = m->coef[u];
         a.rhs = u == 0 ? d_r : pc->tmp; a.out = u == 0 ? pc->tmp : d_z;
         KbLaunch L(c, KB_K_TRSV);
-        march_kernel(u == 1, two_d, m->ga)<<<m->grid, m->warps * 32, march_smem(u == 1, two_d, m->ga), c->stream>>>(a);
+        if (m->lean) lean_kernel(u == 1, two_d, m->ga, m->gb).fn<<<m->grid, m->threads, m->smem[u], c->stream>>>(a);
+        else march_kernel(u == 1, two_d, m->ga)<<<m->grid, m->warps * 32, march_smem(u == 1, two_d, m->ga), c->stream>>>(a);
     }
     KB_CUDA(cudaGetLastError());
     return KB_OK;
