@@ -519,9 +519,12 @@ __global__ void __launch_bounds__(KmShape<UPPER, LX, LY, GA, GB, RD>::THREADS, 1
             long long r_out = g.rbase - g.rstep * sk;     // row of this lane at step tl: c = tl - sk
             double s = 0.0;
             __syncthreads();                              // the helpers' step-0 face values are in place
+            unsigned long long tr_entry = 0ull, tr_first = 0ull;
+            if (a.trace) tr_entry = kb_gtime();
             for (int t0 = 0; t0 < nsteps_cta; t0 += 4) {
                 const int tl0 = t0 - offset;
                 const bool in_range = valid && tl0 >= 0 && tl0 < nsteps;      // warp-uniform, same for the 4 steps
+                if (a.trace && tl0 == 0) tr_first = kb_gtime();
                 const unsigned half = (kc >> 1) & 1u, ph = (kc >> 2) & 1u;
                 const double* cb = cring + half * (4 * NC * 32) + lane;
 #pragma unroll
@@ -564,6 +567,10 @@ __global__ void __launch_bounds__(KmShape<UPPER, LX, LY, GA, GB, RD>::THREADS, 1
                 if (in_range) kc += 2u;
             }
             kb_cp_async_wait<0>();
+            if (a.trace && valid && lane == 0) {
+                unsigned long long* q = a.trace + ((size_t)(UPPER ? a.npencils : 0) + pencil) * 4;
+                q[0] = tr_entry; q[1] = tr_first; q[2] = kb_gtime();
+            }
         } else {
             // ================= helper warp: the group's L2 faces =================
             const int line = (warp - NCW) * 32 + lane;
@@ -596,6 +603,7 @@ __global__ void __launch_bounds__(KmShape<UPPER, LX, LY, GA, GB, RD>::THREADS, 1
             }
             // packet of compute step t' lives at consumer-local step t' - off_c; ring slot t' & 3
             ulonglong2 pk[PD];
+            unsigned tr_stalls = 0u;
             {
                 double v0 = 0.0;
                 const int tl = 0 - off_c;
@@ -619,7 +627,7 @@ __global__ void __launch_bounds__(KmShape<UPPER, LX, LY, GA, GB, RD>::THREADS, 1
                         double v = 0.0;
                         if ((unsigned)(tl - pk_lo) < in_span) {
                             ulonglong2 q = pk[(u + 1) & (PD - 1)];
-                            if (!kb_pkt_ok(q, tag)) q = kb_pkt_wait(mail_in + (size_t)tl * FACES, tag, a.err);
+                            if (!kb_pkt_ok(q, tag)) { q = kb_pkt_wait(mail_in + (size_t)tl * FACES, tag, a.err); ++tr_stalls; }
                             v = kb_pkt_value(q);
                         }
                         if (live) in_slot[(u & 1) * fstride] = v;
@@ -633,6 +641,10 @@ __global__ void __launch_bounds__(KmShape<UPPER, LX, LY, GA, GB, RD>::THREADS, 1
                     }
                     __syncthreads();
                 }
+            }
+            if (a.trace) {      // blocking packet waits of this group's helper lanes -> slot 3 of the group's first pencil
+                const unsigned st_all = __reduce_add_sync(0xffffffffu, tr_stalls);
+                if (lane == 0 && Pa0 < a.px && Pb0 < a.py) atomicAdd(a.trace + ((size_t)(UPPER ? a.npencils : 0) + Pa0 + a.px * Pb0) * 4 + 3, (unsigned long long)st_all);
             }
         }
         // (the next group's face clearing is ordered after every read of this group by the barrier above)
@@ -767,6 +779,7 @@ int kb_march_build(kb_pc_s* pc, int gx, int gy, int gz, unsigned* d_err, KbMarch
         if (st != KB_OK) break;
         m->grid = std::max(1, std::min(cap, m->ngroups));
         if (getenv("KB_MARCH_GRID")) m->grid = std::max(1, std::min(m->grid, atoi(getenv("KB_MARCH_GRID"))));
+        if (m->trace) fprintf(stderr, "[kb march] lean=%d group %dx%d threads %d smem %zu/%zu grid %d (cap %d) groups %d nsteps %d lag %d\n", m->lean, m->ga, m->gb, m->threads, m->smem[0], m->smem[1], m->grid, cap, m->ngroups, m->nsteps, m->lag);
         if (cudaStreamSynchronize(c->stream) != cudaSuccess) { st = KB_SOLVE_ERROR; break; }
     } while (0);
     if (d_bad) cudaFree(d_bad);
@@ -782,6 +795,7 @@ int kb_march_apply(kb_pc_s* pc, KbMarch* m, const double* d_r, double* d_z, cons
     a.n = m->n; a.nx = m->nx; a.ny = m->ny; a.nz = m->nz; a.px = m->px; a.py = m->py; a.npencils = m->npencils;
     a.gpx = m->gpx; a.gpy = m->gpy; a.ngroups = m->ngroups; a.nsteps = m->nsteps; a.lag = m->lag;
     a.order = m->order; a.mail = m->mail; a.sync = m->sync; a.err = m->err; a.skip_ctl = skip_ctl; a.skip_mask = skip_mask; a.trace = m->trace;
+    if (m->trace) cudaMemsetAsync(m->trace, 0, (size_t)m->npencils * 8 * sizeof(unsigned long long), c->stream);
     for (int u = 0; u < 2; ++u) {
         a.coef = m->coef[u];
         a.rhs = u == 0 ? d_r : pc->tmp; a.out = u == 0 ? pc->tmp : d_z;

@@ -11,6 +11,7 @@ ctx = kb.default_context(0)
 n, rp, ci, v = stencils.stencil(kind, N)
 A = kb.DeviceCsr.from_csr(n, n, rp, ci, v, ctx)
 os.environ["KB_MARCH_GROUP"] = sys.argv[3] if len(sys.argv) > 3 else "4"
+os.environ["KB_TRSV_MARCH"] = "1"
 pc = kb.Ilu0().setup(A)
 r = torch.randn(n, dtype=torch.float64, device="cuda"); z = torch.zeros_like(r)
 lib = _ffi.lib()
@@ -34,5 +35,10 @@ for u, name in ((0, "L"), (1, "U")):
     P = first.reshape(py.value, px.value)
     print("  first-step time us along a (b=0):", np.round(P[0, :min(8, px.value)] / 1e3, 1))
     print("  first-step time us along b (a=0):", np.round(P[:min(8, py.value), 0] / 1e3, 1))
+    Pe = ent.reshape(py.value, px.value)
+    print("  entry us along diag:", np.round(np.array([Pe[min(i * py.value // 8, py.value - 1), min(i * px.value // 8, px.value - 1)] for i in range(9)]) / 1e3, 1))
+    print("  first us along diag:", np.round(np.array([P[min(i * py.value // 8, py.value - 1), min(i * px.value // 8, px.value - 1)] for i in range(9)]) / 1e3, 1))
     E = end.reshape(py.value, px.value)
+    print("  end   us along diag:", np.round(np.array([E[min(i * py.value // 8, py.value - 1), min(i * px.value // 8, px.value - 1)] for i in range(9)]) / 1e3, 1))
+    print("  total stalls", stalls.sum(), " groups with stalls", (stalls > 0).sum())
     print("  end us corner:", E[-1, -1] / 1e3, " run of pencil 0 us:", run.reshape(py.value, px.value)[0, 0] / 1e3)
