@@ -62,21 +62,42 @@ def test_trsv_schedules_bit_exact(ctx, kind, N, sched, monkeypatch):
         assert np.array_equal(z, o.ilu0_apply(Ao, lu_o, dp_o, iud_o, r))
 
 
-@pytest.mark.parametrize("warps", ["1", "3", "16"])
-def test_trsv_march_more_pencils_than_warps(ctx, warps, monkeypatch):
-    """Pencils are handed to warps in level order; with few warps per CTA and a capped grid every warp marches
-    several pencils one after the other (the C5-shard regime)."""
+@pytest.mark.parametrize("rows", ["1", "2"])
+@pytest.mark.parametrize("group", ["1", "2"])
+@pytest.mark.parametrize("grid", ["3", "0"])
+def test_trsv_march_shapes(ctx, rows, group, grid, monkeypatch):
+    """Pencil shapes (1 or 2 rows per lane), group shapes (1 or 2x2 pencils per CTA) and a capped grid: with few
+    CTAs every CTA marches several groups one after the other, in level order (the C5-shard regime)."""
     import kryst_b200 as kb
-    monkeypatch.setenv("KB_MARCH_GROUP", {"1": "1", "3": "2", "16": "4"}[warps])     # 1, 4, 16 pencils per CTA
-    monkeypatch.setenv("KB_MARCH_GRID", "3")                                          # few CTAs: every CTA marches several groups
+    monkeypatch.setenv("KB_LEAN_ROWS", rows)
+    monkeypatch.setenv("KB_MARCH_GROUP", group)
+    if grid != "0":
+        monkeypatch.setenv("KB_MARCH_GRID", grid)
     monkeypatch.setenv("KB_TRSV_MARCH", "1")
     A, Ao = _mk("convdiff3d", 33, ctx)
     pc = kb.Ilu0().setup(A)
     st, lu_o, dp_o, iud_o, bad = o.ilu0_factor(Ao)
-    r = np.random.default_rng(2).standard_normal(Ao.n)
-    z = np.zeros(Ao.n)
-    pc.apply(r, z)
-    assert np.array_equal(z, o.ilu0_apply(Ao, lu_o, dp_o, iud_o, r))
+    rng = np.random.default_rng(2)
+    for _ in range(3):
+        r = rng.standard_normal(Ao.n)
+        z = np.zeros(Ao.n)
+        pc.apply(r, z)
+        assert np.array_equal(z, o.ilu0_apply(Ao, lu_o, dp_o, iud_o, r))
+
+
+@pytest.mark.parametrize("group", ["1", "2", "4"])
+def test_trsv_march_2d_groups(ctx, group, monkeypatch):
+    import kryst_b200 as kb
+    monkeypatch.setenv("KB_MARCH_GROUP", group)
+    A, Ao = _mk("convdiff2d", 150, ctx)
+    pc = kb.Ilu0().setup(A)
+    st, lu_o, dp_o, iud_o, bad = o.ilu0_factor(Ao)
+    rng = np.random.default_rng(3)
+    for _ in range(2):
+        r = rng.standard_normal(Ao.n)
+        z = np.zeros(Ao.n)
+        pc.apply(r, z)
+        assert np.array_equal(z, o.ilu0_apply(Ao, lu_o, dp_o, iud_o, r))
 
 
 def test_trsv_march_falls_back_without_a_full_stencil(ctx):
