@@ -44,6 +44,7 @@ struct KlArgs {
     double* out;                     // L: the U solve's array (stream 4 receives y); U: row-major solution
     int n, nx, ny, nz, px, py, npencils;
     int nsteps, nsteps_cta, lag;
+    int dbg;                         // timing experiments only (KB_LEAN_DBG bit mask; results are wrong when set)
     int gpx, gpy, ngroups;
     const int* __restrict__ order;   // group ids by level (ascending)
     ulonglong2* mail;
@@ -65,7 +66,7 @@ struct KbLean {
     unsigned* sync = nullptr;        // [0],[1] epoch of L / U ; [2],[3] finish tickets
     unsigned* err = nullptr;         // borrowed: the preconditioner's error word
     unsigned long long* trace = nullptr;
-    int grid = 1, threads = 0, lag = 10;
+    int grid = 1, threads = 0, lag = KL_PD + 6, dbg = 0;
     size_t smem[2] = {0, 0};
     kl_fn fn[2] = {nullptr, nullptr};
 };
@@ -74,6 +75,9 @@ struct KbLean {
 __device__ __forceinline__ unsigned kl_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void kl_cp8(void* smem_dst, const void* gsrc) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(kl_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void kl_cp8s(unsigned smem_dst, const void* gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_dst), "l"(gsrc) : "memory");
 }
 __device__ __forceinline__ void kl_cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
@@ -190,9 +194,10 @@ struct KlShape {
     static constexpr int NA = GB * LYR;                  // lines of the group's A faces (in and out)
     static constexpr int NB = LY > 1 ? GA * LX : 0;      // lines of the B faces
     static constexpr int NHW = (NA + NB + 31) / 32;      // helper warps
-    static constexpr int THREADS = (NCW + NHW + 1) * 32; // + the loader warp
+    static constexpr int THREADS = (NCW + 2 * NHW + 2) * 32; // + the stage warp (TMA, mbarriers) + the mover warp (L: rhs slabs in, U: solution slabs out)
     static constexpr int STEP_DOUBLES = NCW * NS * R * 32;
-    static constexpr int RR_DOUBLES = UPPER ? 0 : NCW * R * RD * 32;
+    static constexpr int OD = SK + 2 <= 16 ? 16 : (SK + 2 <= 32 ? 32 : 64);      // U: output delay line (slabs), power of two >= SK + 2
+    static constexpr int RR_DOUBLES = UPPER ? NCW * R * OD * 32 : NCW * R * RD * 32;
     static constexpr int FA = (GA + 1) * GB * LYR;       // faceA[par][wa' = 0..GA][wb][qb]: slot 0 = from L2, slot wa+1 = written by pencil (wa,wb)
     static constexpr int FB = LY > 1 ? (GB + 1) * GA * LX : 0;
     static constexpr size_t SMEM = ((size_t)KL_STAGES * STEP_DOUBLES + RR_DOUBLES + 2 * (FA + FB)) * sizeof(double) + KL_STAGES * sizeof(unsigned long long);
@@ -281,18 +286,19 @@ __global__ void __launch_bounds__(KlShape<UPPER, LX, LY, R, GA, GB, RD>::THREADS
                     ostep = -(long long)NCW * 5 * R32;                 // c + 1  ->  U step - 1
                     outp[r] = a.out + s0 + 4 * R32 + ostep * (long long)(0 - sk);
                 } else {
-                    ostep = g.rstep;
-                    outp[r] = a.out + g.rbase - g.rstep * sk;
+                    ostep = 0;
+                    outp[r] = nullptr;                                 // U: the mover warp stores the solution (un-skewed, coalesced)
                 }
             }
+            double* oring = rr + ((size_t)warp * R) * (SH::OD * 32) + lane;    // U: [R][OD][32], slot = local step & (OD-1)
             const double* fa_in = faceA + (wa * GB + wb) * LYR + R * lbp;        // read by la == 0 (+ parity * FA)
             double* fa_out = faceA + ((wa + 1) * GB + wb) * LYR + R * lbp;       // written by la == LX-1
             const double* fb_in = faceB + (wb * GA + wa) * LX + la;              // read by lbp == 0, row 0 (+ parity * FB)
             double* fb_out = faceB + ((wb + 1) * GA + wa) * LX + la;             // written by lbp == LY-1, row R-1
             const double* rr_w = rr + ((size_t)warp * R) * (RD * 32) + lane;     // + r * RD*32 + slot*32
-            double s[R];
+            double s[R], vA[R], vB[R], vC[R], dg[R], rh[R];
 #pragma unroll
-            for (int r = 0; r < R; ++r) s[r] = 0.0;
+            for (int r = 0; r < R; ++r) { s[r] = 0.0; vA[r] = vB[r] = vC[r] = rh[r] = 0.0; dg[r] = 1.0; }
             __syncthreads();                              // the helpers' step-0 face values and the loader's first slabs are in place
             unsigned long long tr_entry = 0ull, tr_first = 0ull;
             if (a.trace) tr_entry = kl_gtime();
@@ -302,22 +308,28 @@ __global__ void __launch_bounds__(KlShape<UPPER, LX, LY, R, GA, GB, RD>::THREADS
                 if (a.trace && tl0 == 0) tr_first = kl_gtime();
                 const unsigned gt = gbase + (unsigned)t0;
                 const unsigned quad = (gt >> 2) & (KL_STAGES / 4 - 1), ph = (gt >> KL_STAGE_LOG) & 1u;
-                const double* cb = cst + (size_t)quad * (4 * STEP) + warp * (NS * R32) + lane;
+                (void)ph;
+                const double* cw = cst + warp * (NS * R32) + lane;
+                const double* cb = cw + (size_t)quad * (4 * STEP);
+                const double* cb_next = cw + (size_t)((quad + 1) & (KL_STAGES / 4 - 1)) * (4 * STEP);
+                // operands of local step tl out of the stage at cp / the rhs delay line.  The loader warp has seen the stage's
+                // mbarrier complete (and the slab's cp.async group land) before the previous step barrier.
+                auto load_ops = [&](const double* cp, int tl) {
+#pragma unroll
+                    for (int r = 0; r < R; ++r) {
+                        vA[r] = cp[r * 32]; vB[r] = LY > 1 ? cp[R32 + r * 32] : 0.0; vC[r] = cp[2 * R32 + r * 32];
+                        dg[r] = UPPER ? cp[3 * R32 + r * 32] : 1.0;
+                        if (UPPER) rh[r] = cp[4 * R32 + r * 32];
+                        else rh[r] = rr_w[r * (RD * 32) + ((rr_off[r] + tl) & RM) * 32];
+                    }
+                };
+                if (in_range && tl0 == 0) load_ops(cb, 0);                      // first step of this pencil (one exposed shared-memory latency)
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
                     if (in_range) {
                         const int tl = tl0 + u;
-                        kl_mbar_wait(full + (quad << 2) + u, ph);
-                        const double* cp = cb + u * STEP;
                         const int par_r = (u & 1) ^ 1, par_w = u & 1;          // t0 is a multiple of 4
-                        double vA[R], vB[R], vC[R], dg[R], rh[R], ya[R], yb[R], v[R];
-#pragma unroll
-                        for (int r = 0; r < R; ++r) {
-                            vA[r] = cp[r * 32]; vB[r] = LY > 1 ? cp[R32 + r * 32] : 0.0; vC[r] = cp[2 * R32 + r * 32];
-                            dg[r] = UPPER ? cp[3 * R32 + r * 32] : 1.0;
-                            if (UPPER) rh[r] = cp[4 * R32 + r * 32];
-                            else rh[r] = rr_w[r * (RD * 32) + ((rr_off[r] + tl) & RM) * 32];
-                        }
+                        double ya[R], yb[R], v[R];
 #pragma unroll
                         for (int r = 0; r < R; ++r) ya[r] = __shfl_up_sync(0xffffffffu, s[r], 1);
                         if (LY > 1) {
@@ -325,11 +337,13 @@ __global__ void __launch_bounds__(KlShape<UPPER, LX, LY, R, GA, GB, RD>::THREADS
 #pragma unroll
                             for (int r = 1; r < R; ++r) yb[r] = s[r - 1];
                         }
+                        if (!(a.dbg & 8)) {
                         if (la == 0) {
 #pragma unroll
                             for (int r = 0; r < R; ++r) ya[r] = fa_in[par_r * FA + r];
                         }
                         if (LY > 1 && lbp == 0) yb[0] = fb_in[par_r * FB];
+                        }
 #pragma unroll
                         for (int r = 0; r < R; ++r) {
                             if (!UPPER) { v[r] = rh[r] - vC[r] * s[r]; if (LY > 1) v[r] = v[r] - vB[r] * yb[r]; v[r] = v[r] - vA[r] * ya[r]; }          // ascending column: c-1, b-1, a-1
@@ -339,14 +353,18 @@ __global__ void __launch_bounds__(KlShape<UPPER, LX, LY, R, GA, GB, RD>::THREADS
                         for (int r = 0; r < R; ++r) {
                             const bool act = (unsigned)(tl - t_lo[r]) < span[r];
                             s[r] = act ? v[r] : 0.0;
-                            if (act) *outp[r] = s[r];
-                            outp[r] += ostep;
+                            if (!UPPER) { if (act && !(a.dbg & 1)) *outp[r] = s[r]; outp[r] += ostep; }
+                            else oring[r * (SH::OD * 32) + (tl & (SH::OD - 1)) * 32] = s[r];
                         }
+                        if (!(a.dbg & 8)) {
                         if (la == LX - 1) {
 #pragma unroll
                             for (int r = 0; r < R; ++r) fa_out[par_w * FA + r] = s[r];
                         }
                         if (LY > 1 && lbp == LY - 1) fb_out[par_w * FB] = s[R - 1];
+                        }
+                        // operands of the next step: their latency hides behind the barrier
+                        if (tl + 1 < nsteps) load_ops(u < 3 ? cb + (u + 1) * STEP : cb_next, tl + 1);
                     }
                     __syncthreads();                      // step barrier: faces written in step t are read in step t + 1
                 }
@@ -355,84 +373,103 @@ __global__ void __launch_bounds__(KlShape<UPPER, LX, LY, R, GA, GB, RD>::THREADS
                 unsigned long long* q = a.trace + ((size_t)(UPPER ? a.npencils : 0) + pencil) * 4;
                 q[0] = tr_entry; q[1] = tr_first; q[2] = kl_gtime();
             }
-        } else if (warp < NCW + NHW) {
-            // ================= helper warp: the group's L2 faces =================
-            const int line = (warp - NCW) * 32 + lane;
+        } else if (warp < NCW + 2 * NHW) {
+            // ================= helper warps: the group's L2 faces (first NHW warps: incoming packets, next NHW: outgoing) =================
+            const bool inbound = warp < NCW + NHW;
+            const int line = (warp - NCW - (inbound ? 0 : NHW)) * 32 + lane;
             const bool isA = line < NA, live = line < NA + NB;
             int wa_c = 0, wb_c = 0, la_c = 0, qb_c = 0, wa_p = 0, wb_p = 0, la_p = 0, qb_p = 0, fidx = 0;
             if (isA) { wb_c = wb_p = line / LYR; qb_c = qb_p = line % LYR; wa_p = GA - 1; la_p = LX - 1; fidx = qb_c; }
             else if (live) { const int q = line - NA; wa_c = wa_p = q / LX; la_c = la_p = q % LX; wb_p = GB - 1; qb_p = LYR - 1; fidx = LYR + la_c; }
-            const int Pa_c = Pa0 + wa_c, Pb_c = Pb0 + wb_c, Pa_p = Pa0 + wa_p, Pb_p = Pb0 + wb_p;
-            const KlRow gc = kl_row<UPPER, LX, LYR>(a, Pa_c, Pb_c, la_c, qb_c);
-            const KlRow gp = kl_row<UPPER, LX, LYR>(a, Pa_p, Pb_p, la_p, qb_p);
-            const bool has_in = live && Pa_c < a.px && Pb_c < a.py && (isA ? Pa_c > 0 : Pb_c > 0);
-            const bool has_out = live && Pa_p < a.px && Pb_p < a.py && (isA ? Pa_p + 1 < a.px : Pb_p + 1 < a.py);
-            const int skew_c = isA ? qb_c : la_c;
-            int pk_lo = 0, pk_hi = 0;                      // consumer-local steps at which an incoming packet exists
-            if (has_in) { pk_lo = (isA ? gc.cA_lo : gc.cB_lo) + skew_c; pk_hi = gc.c_hi + skew_c; if (pk_hi < pk_lo) pk_hi = pk_lo; }
-            int tp_lo = 0, tp_hi = 0;                      // producer-local steps at which an outgoing value exists
-            if (has_out) { tp_lo = gp.c_lo + la_p + qb_p; tp_hi = gp.c_hi + la_p + qb_p; if (tp_hi < tp_lo) tp_hi = tp_lo; }
-            const unsigned in_span = (unsigned)(pk_hi - pk_lo), out_span = (unsigned)(tp_hi - tp_lo);
-            const int off_c = LX * wa_c + LYR * wb_c, off_p = LX * wa_p + LYR * wb_p;
-            const ulonglong2* mail_in = a.mail + (size_t)(Pa_c + a.px * Pb_c) * nsteps * FACES + fidx;                    // + tl * FACES
-            ulonglong2* mail_out = a.mail + ((size_t)(Pa_p + a.px * Pb_p + (isA ? 1 : a.px)) * nsteps) * FACES + fidx;   // + (tlp - depth) * FACES
-            const int depth = isA ? LX - 1 : LYR - 1;
-            double* in_slot = isA ? faceA + wb_c * LYR + qb_c : faceB + wa_c * LX + la_c;                                   // slot 0 (+ parity * FA/FB)
-            const double* out_slot = isA ? faceA + (GA * GB + wb_p) * LYR + qb_p : faceB + (GB * GA + wa_p) * LX + la_p;   // slot GA / GB
             const int fstride = isA ? FA : FB;
-            // keep the distance: start only when the packets of the group's step `lag` are there (lines whose first
-            // packet is needed later than that do not hold the group back)
-            {
-                const int tw = a.lag - off_c;
-                if ((unsigned)(tw - pk_lo) < in_span) (void)kl_pkt_wait(mail_in + (ptrdiff_t)tw * FACES, tag, a.err);
-            }
-            // packet of compute step t' lives at consumer-local step t' - off_c; ring slot t' & (PD - 1)
-            ulonglong2 pk[PD];
-            unsigned tr_stalls = 0u;
-            {
-                double v0 = 0.0;
-                const int tl = 0 - off_c;
-                if ((unsigned)(tl - pk_lo) < in_span) v0 = kl_pkt_value(kl_pkt_wait(mail_in + (ptrdiff_t)tl * FACES, tag, a.err));
-                if (live) in_slot[1 * fstride] = v0;       // step 0 reads parity (0 - 1) & 1
-#pragma unroll
-                for (int j = 1; j <= PD; ++j) {
-                    const int tj = j - off_c;
-                    pk[j & (PD - 1)] = make_ulonglong2(0ull, 0ull);
-                    if ((unsigned)(tj - pk_lo) < in_span) pk[j & (PD - 1)] = kl_pkt_load(mail_in + (ptrdiff_t)tj * FACES);
+            if (inbound) {
+                const int Pa_c = Pa0 + wa_c, Pb_c = Pb0 + wb_c;
+                const KlRow gc = kl_row<UPPER, LX, LYR>(a, Pa_c, Pb_c, la_c, qb_c);
+                const bool has_in = live && Pa_c < a.px && Pb_c < a.py && (isA ? Pa_c > 0 : Pb_c > 0);
+                const int skew_c = isA ? qb_c : la_c;
+                int pk_lo = 0, pk_hi = 0;                      // consumer-local steps at which an incoming packet exists
+                if (has_in) { pk_lo = (isA ? gc.cA_lo : gc.cB_lo) + skew_c; pk_hi = gc.c_hi + skew_c; if (pk_hi < pk_lo) pk_hi = pk_lo; }
+                const unsigned in_span = (unsigned)(pk_hi - pk_lo);
+                const int off_c = LX * wa_c + LYR * wb_c;
+                const ulonglong2* mail_in = a.mail + (size_t)(Pa_c + a.px * Pb_c) * nsteps * FACES + fidx;      // + tl * FACES
+                double* in_slot = isA ? faceA + wb_c * LYR + qb_c : faceB + wa_c * LX + la_c;                     // slot 0 (+ parity * FA/FB)
+                // keep the distance: start only when the packets of the group's step `lag` are there (lines whose first
+                // packet is needed later than that do not hold the group back)
+                {
+                    const int tw = a.lag - off_c;
+                    if ((unsigned)(tw - pk_lo) < in_span) (void)kl_pkt_wait(mail_in + (ptrdiff_t)tw * FACES, tag, a.err);
                 }
-            }
-            __syncthreads();                              // pairs with the compute warps' initial barrier
-            for (int t0 = 0; t0 < nsteps_cta; t0 += PD) {
+                // packet of compute step t' lives at consumer-local step t' - off_c; ring slot t' & (PD - 1)
+                ulonglong2 pk[PD];
+                unsigned tr_stalls = 0u;
+                {
+                    double v0 = 0.0;
+                    const int tl = 0 - off_c;
+                    if ((unsigned)(tl - pk_lo) < in_span) v0 = kl_pkt_value(kl_pkt_wait(mail_in + (ptrdiff_t)tl * FACES, tag, a.err));
+                    if (live) in_slot[1 * fstride] = v0;       // step 0 reads parity (0 - 1) & 1
 #pragma unroll
-                for (int u = 0; u < PD; ++u) {
-                    const int t = t0 + u;
-                    // incoming value of compute step t + 1 -> parity t & 1, then request the packet of step t + 1 + PD
-                    {
-                        const int tl = t + 1 - off_c;
+                    for (int j = 1; j <= PD; ++j) {
+                        const int tj = j - off_c;
+                        pk[j & (PD - 1)] = make_ulonglong2(0ull, 0ull);
+                        if ((unsigned)(tj - pk_lo) < in_span) pk[j & (PD - 1)] = kl_pkt_load(mail_in + (ptrdiff_t)tj * FACES);
+                    }
+                }
+                int din = 1 - off_c - pk_lo;                                       // (tl - pk_lo) of the packet of compute step t + 1, at t = 0
+                const ulonglong2* pin = mail_in + (ptrdiff_t)(1 - off_c) * FACES;   // that packet
+                __syncthreads();                              // pairs with the compute warps' initial barrier
+                for (int t0 = 0; t0 < nsteps_cta; t0 += PD) {
+#pragma unroll
+                    for (int u = 0; u < PD; ++u) {
+                        // incoming value of compute step t + 1 -> parity t & 1, then request the packet of step t + 1 + PD
                         double v = 0.0;
-                        if ((unsigned)(tl - pk_lo) < in_span) {
+                        if ((unsigned)din < in_span) {
                             ulonglong2 q = pk[(u + 1) & (PD - 1)];
-                            if (!kl_pkt_ok(q, tag)) { q = kl_pkt_wait(mail_in + (ptrdiff_t)tl * FACES, tag, a.err); ++tr_stalls; }
+                            if (!kl_pkt_ok(q, tag)) {
+                                // the group caught up with its producer: wait, then request the following packets again (the
+                                // copies in the ring were loaded before their packets existed; the wait has restored the distance)
+                                q = kl_pkt_wait(pin, tag, a.err);
+                                ++tr_stalls;
+#pragma unroll
+                                for (int j = 1; j < PD; ++j)
+                                    if ((unsigned)(din + j) < in_span) pk[(u + 1 + j) & (PD - 1)] = kl_pkt_load(pin + j * FACES);
+                            }
                             v = kl_pkt_value(q);
                         }
                         if (live) in_slot[(u & 1) * fstride] = v;
-                        pk[(u + 1) & (PD - 1)] = make_ulonglong2(0ull, 0ull);
-                        if ((unsigned)(tl + PD - pk_lo) < in_span) pk[(u + 1) & (PD - 1)] = kl_pkt_load(mail_in + (ptrdiff_t)(tl + PD) * FACES);
+                        if ((unsigned)(din + PD) < in_span) pk[(u + 1) & (PD - 1)] = kl_pkt_load(pin + PD * FACES);
+                        ++din; pin += FACES;
+                        __syncthreads();
                     }
-                    // outgoing value computed in step t - 1 (parity (t - 1) & 1)
-                    {
-                        const int tlp = t - 1 - off_p;
-                        if ((unsigned)(tlp - tp_lo) < out_span) kl_pkt_store(mail_out + (ptrdiff_t)(tlp - depth) * FACES, out_slot[((u & 1) ^ 1) * fstride], tag);
+                }
+                if (a.trace) {      // blocking packet waits of this group's helper lanes -> slot 3 of the group's first pencil
+                    const unsigned st_all = __reduce_add_sync(0xffffffffu, tr_stalls);
+                    if (lane == 0 && Pa0 < a.px && Pb0 < a.py) atomicAdd(a.trace + ((size_t)(UPPER ? a.npencils : 0) + Pa0 + a.px * Pb0) * 4 + 3, (unsigned long long)st_all);
+                }
+            } else {
+                const int Pa_p = Pa0 + wa_p, Pb_p = Pb0 + wb_p;
+                const KlRow gp = kl_row<UPPER, LX, LYR>(a, Pa_p, Pb_p, la_p, qb_p);
+                const bool has_out = live && Pa_p < a.px && Pb_p < a.py && (isA ? Pa_p + 1 < a.px : Pb_p + 1 < a.py);
+                int tp_lo = 0, tp_hi = 0;                      // producer-local steps at which an outgoing value exists
+                if (has_out) { tp_lo = gp.c_lo + la_p + qb_p; tp_hi = gp.c_hi + la_p + qb_p; if (tp_hi < tp_lo) tp_hi = tp_lo; }
+                const unsigned out_span = (unsigned)(tp_hi - tp_lo);
+                const int off_p = LX * wa_p + LYR * wb_p;
+                const int depth = isA ? LX - 1 : LYR - 1;
+                // the value computed in step t - 1 (producer-local step tlp = t - 1 - off_p) is the consumer's packet of step tlp - depth
+                ulonglong2* pout = a.mail + ((size_t)(Pa_p + a.px * Pb_p + (isA ? 1 : a.px)) * nsteps) * FACES + fidx + (ptrdiff_t)(-1 - off_p - depth) * FACES;
+                const double* out_slot = isA ? faceA + (GA * GB + wb_p) * LYR + qb_p : faceB + (GB * GA + wa_p) * LX + la_p;   // slot GA / GB
+                int dout = -1 - off_p - tp_lo;                 // (tlp - tp_lo) at t = 0
+                __syncthreads();                              // initial barrier
+                for (int t0 = 0; t0 < nsteps_cta; t0 += 2) {
+#pragma unroll
+                    for (int u = 0; u < 2; ++u) {
+                        if ((unsigned)dout < out_span) kl_pkt_store(pout, out_slot[(u ^ 1) * fstride], tag);      // parity (t - 1) & 1
+                        ++dout; pout += FACES;
+                        __syncthreads();
                     }
-                    __syncthreads();
                 }
             }
-            if (a.trace) {      // blocking packet waits of this group's helper lanes -> slot 3 of the group's first pencil
-                const unsigned st_all = __reduce_add_sync(0xffffffffu, tr_stalls);
-                if (lane == 0 && Pa0 < a.px && Pb0 < a.py) atomicAdd(a.trace + ((size_t)(UPPER ? a.npencils : 0) + Pa0 + a.px * Pb0) * 4 + 3, (unsigned long long)st_all);
-            }
-        } else {
-            // ================= loader warp: coefficient stages (TMA) and the L solve's rhs delay line =================
+        } else if (warp == NCW + 2 * NHW) {
+            // ================= stage warp: coefficient stages by TMA, mbarrier waits on behalf of everybody =================
             unsigned long long pol;
             asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
             const double* gsrc = a.coef + (size_t)group * nsteps_cta * STEP;
@@ -442,57 +479,81 @@ __global__ void __launch_bounds__(KlShape<UPPER, LX, LY, R, GA, GB, RD>::THREADS
                     if (j < nsteps_cta) {
                         const unsigned sl = (gbase + (unsigned)j) & (KL_STAGES - 1);
                         kl_mbar_wait(full + sl, ((gbase + (unsigned)j - KL_STAGES) >> KL_STAGE_LOG) & 1u);      // the slot's previous copy has landed (nobody may have waited for it)
-                        kl_bulk(cst + (size_t)sl * STEP, gsrc + (size_t)j * STEP, STEP_BYTES, full + sl, pol); }
-            }
-            // rhs slabs: lane (la,lb') of this warp loads the elements of lane (la,lb') of every pencil, un-skewed
-            const int la = lane % LX, lbp = lane / LX;
-            long long r_ld[UPPER ? 1 : NCW * R]; int c0[UPPER ? 1 : NCW * R]; unsigned cs[UPPER ? 1 : NCW * R]; long long rstep = 0;
-            if (!UPPER) {
-#pragma unroll
-                for (int w = 0; w < NCW; ++w)
-#pragma unroll
-                    for (int r = 0; r < R; ++r) {
-                        const KlRow g = kl_row<UPPER, LX, LYR>(a, Pa0 + w % GA, Pb0 + w / GA, la, R * lbp + r);
-                        const int off_w = LX * (w % GA) + LYR * (w / GA);
-                        // at loader step t this row's slab is c = t - off_w + D
-                        c0[w * R + r] = D - off_w - g.c_lo;                 // c - c_lo at t = 0
-                        cs[w * R + r] = (unsigned)(g.c_hi - g.c_lo);
-                        r_ld[w * R + r] = g.rbase + g.rstep * (long long)(D - off_w);
-                        rstep = g.rstep;
+                        kl_bulk(cst + (size_t)sl * STEP, gsrc + (size_t)j * STEP, STEP_BYTES, full + sl, pol);
                     }
-                // prologue: loader steps -D .. -1
-                for (int t = -D; t < 0; ++t) {
-#pragma unroll
-                    for (int w = 0; w < NCW; ++w)
-#pragma unroll
-                        for (int r = 0; r < R; ++r) {
-                            const int k = w * R + r;
-                            const int c = t + D - (LX * (w % GA) + LYR * (w / GA));
-                            if ((unsigned)(c0[k] + t) < cs[k]) kl_cp8(rr + ((size_t)k * RD + (c & RM)) * 32 + lane, a.rhs + (r_ld[k] + rstep * t));
-                        }
-                    kl_cp_commit();
-                }
-                kl_cp_wait<D - 1 < 0 ? 0 : D - 1>();
             }
+            // the compute warps read a stage one step before they use it and never touch the mbarriers: this warp sees the
+            // stage of step t + 2 complete before it joins the barrier of step t
+            kl_mbar_wait(full + (gbase & (KL_STAGES - 1)), (gbase >> KL_STAGE_LOG) & 1u);
+            kl_mbar_wait(full + ((gbase + 1u) & (KL_STAGES - 1)), ((gbase + 1u) >> KL_STAGE_LOG) & 1u);
             __syncthreads();                              // initial barrier
             for (int t = 0; t < nsteps_cta; ++t) {
                 // the slot of step t - 1 is free: stage step t - 1 + KL_STAGES
-                if (lane == 0 && t >= 1 && t - 1 + KL_STAGES < nsteps_cta) {
-                    const unsigned sl = (gbase + (unsigned)(t - 1)) & (KL_STAGES - 1);
-                    kl_mbar_wait(full + sl, ((gbase + (unsigned)(t - 1)) >> KL_STAGE_LOG) & 1u);
+                if (lane == 0 && t >= 1 && t - 1 + KL_STAGES < nsteps_cta && !(a.dbg & 16)) {
+                    const unsigned sl = (gbase + (unsigned)(t - 1)) & (KL_STAGES - 1);      // (this warp saw its phase complete three steps ago)
                     kl_bulk(cst + (size_t)sl * STEP, gsrc + (size_t)(t - 1 + KL_STAGES) * STEP, STEP_BYTES, full + sl, pol);
                 }
-                if (!UPPER) {
+                if (t + 2 < nsteps_cta && !(a.dbg & 16)) kl_mbar_wait(full + ((gbase + (unsigned)(t + 2)) & (KL_STAGES - 1)), ((gbase + (unsigned)(t + 2)) >> KL_STAGE_LOG) & 1u);
+                __syncthreads();
+            }
+        } else {
+            // ================= mover warp: L - rhs slabs into the delay line; U - finished solution slabs out, both un-skewed =================
+            // lane (la,lb') moves the elements of lane (la,lb') of every pencil: one slab c per pencil and step, 64-byte segments
+            const int la = lane % LX, lbp = lane / LX;
+            constexpr int NK = NCW * R;
+            const double* gp[NK]; int cw[NK]; unsigned cs[NK]; unsigned sbase[NK]; long long rstep = 0;
 #pragma unroll
-                    for (int w = 0; w < NCW; ++w)
+            for (int w = 0; w < NCW; ++w)
 #pragma unroll
-                        for (int r = 0; r < R; ++r) {
-                            const int k = w * R + r;
-                            const int c = t + D - (LX * (w % GA) + LYR * (w / GA));
-                            if ((unsigned)(c0[k] + t) < cs[k]) kl_cp8(rr + ((size_t)k * RD + (c & RM)) * 32 + lane, a.rhs + (r_ld[k] + rstep * t));
-                        }
+                for (int r = 0; r < R; ++r) {
+                    const int k = w * R + r;
+                    const KlRow g = kl_row<UPPER, LX, LYR>(a, Pa0 + w % GA, Pb0 + w / GA, la, R * lbp + r);
+                    const int off_w = LX * (w % GA) + LYR * (w / GA);
+                    // the slab of pencil w handled at step t:  L: c = t - off_w + D (prefetch);  U: c = t - 1 - off_w - SK (complete since step t - 1)
+                    const int cshift = UPPER ? -1 - off_w - SK : D - off_w;
+                    cw[k] = cshift - g.c_lo;                             // c - c_lo at t = 0
+                    cs[k] = (unsigned)(g.c_hi - g.c_lo);
+                    gp[k] = (UPPER ? (const double*)a.out : a.rhs) + (g.rbase + g.rstep * (long long)cshift);
+                    sbase[k] = kl_u32(rr + (size_t)k * ((UPPER ? SH::OD : RD) * 32) + lane);
+                    rstep = g.rstep;
+                }
+            if (!UPPER) {
+                // prologue: steps -D .. -1
+                for (int t = -D; t < 0; ++t) {
+#pragma unroll
+                    for (int k = 0; k < NK; ++k) {
+                        const int c = t + D - (LX * ((k / R) % GA) + LYR * ((k / R) / GA));
+                        if ((unsigned)(cw[k] + t) < cs[k]) kl_cp8s(sbase[k] + (unsigned)(c & RM) * 256u, gp[k] + rstep * t);
+                    }
                     kl_cp_commit();
-                    kl_cp_wait<D - 1 < 0 ? 0 : D - 1>();      // the slabs consumed in step t + 1 have landed
+                }
+                kl_cp_wait<D - 2 < 0 ? 0 : D - 2>();      // the slabs of steps 0 and 1 have landed
+            }
+            __syncthreads();                              // initial barrier
+            for (int t = 0; t < nsteps_cta; ++t) {
+                if (!UPPER) {
+                    if (!(a.dbg & 2)) {
+#pragma unroll
+                        for (int k = 0; k < NK; ++k) {
+                            const int c = t + D - (LX * ((k / R) % GA) + LYR * ((k / R) / GA));
+                            if ((unsigned)(cw[k] + t) < cs[k]) kl_cp8s(sbase[k] + (unsigned)(c & RM) * 256u, gp[k]);
+                            gp[k] += rstep;
+                        }
+                        kl_cp_commit();
+                        kl_cp_wait<D - 2 < 0 ? 0 : D - 2>();      // the slabs consumed in step t + 2 have landed
+                    }
+                } else if (!(a.dbg & 1)) {
+#pragma unroll
+                    for (int k = 0; k < NK; ++k) {
+                        // element of this lane's row in slab c: written at the row's local step c + sk
+                        const int tlw = t - 1 - (LX * ((k / R) % GA) + LYR * ((k / R) / GA)) - SK + la + R * lbp + (k % R);
+                        if ((unsigned)(cw[k] + t) < cs[k]) {
+                            double v;
+                            asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(sbase[k] + (unsigned)(tlw & (SH::OD - 1)) * 256u) : "memory");
+                            *const_cast<double*>(gp[k]) = v;
+                        }
+                        gp[k] += rstep;
+                    }
                 }
                 __syncthreads();
             }
@@ -556,6 +617,7 @@ int kb_lean_build(kb_pc_s* pc, int gx, int gy, int gz, unsigned* d_err, KbLean**
     if (getenv("KB_LEAN_ROWS")) { const int e = atoi(getenv("KB_LEAN_ROWS")); if (!two_d && (e == 1 || e == 2)) r = e; }
     if (getenv("KB_MARCH_GROUP")) { const int e = atoi(getenv("KB_MARCH_GROUP")); if (e == 1 || e == 2 || (e == 4 && two_d)) g = e; }
     if (getenv("KB_MARCH_LAG")) m->lag = std::max(KL_PD + 1, atoi(getenv("KB_MARCH_LAG")));
+    if (getenv("KB_LEAN_DBG")) m->dbg = atoi(getenv("KB_LEAN_DBG"));
     m->r = r;
     if (two_d) { m->nx = gx; m->ny = 1; m->nz = gy; m->lx = 32; m->lyr = 1; m->faces = 1; }
     else { m->nx = gx; m->ny = gy; m->nz = gz; m->lx = 8; m->lyr = 4 * r; m->faces = m->lx + m->lyr; }
@@ -628,7 +690,7 @@ int kb_lean_apply(kb_pc_s* pc, KbLean* m, const double* d_r, double* d_z, const 
     kb_ctx_s* c = pc->a->ctx;
     KlArgs a{};
     a.n = m->n; a.nx = m->nx; a.ny = m->ny; a.nz = m->nz; a.px = m->px; a.py = m->py; a.npencils = m->npencils;
-    a.nsteps = m->nsteps; a.nsteps_cta = m->nsteps_cta; a.lag = m->lag;
+    a.nsteps = m->nsteps; a.nsteps_cta = m->nsteps_cta; a.lag = m->lag; a.dbg = m->dbg;
     a.gpx = m->gpx; a.gpy = m->gpy; a.ngroups = m->ngroups;
     a.order = m->order; a.mail = m->mail; a.sync = m->sync; a.err = m->err; a.skip_ctl = skip_ctl; a.skip_mask = skip_mask; a.trace = m->trace;
     if (m->trace) cudaMemsetAsync(m->trace, 0, (size_t)m->npencils * 8 * sizeof(unsigned long long), c->stream);

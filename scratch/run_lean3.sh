@@ -1,0 +1,23 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests/test_gpu_ilu_gmres.py -x -q -k "march or slab or ilu0_factors" > gpurun_out/lean3_pytest.log 2>&1
+echo "pytest rc=$?" >> gpurun_out/lean3_pytest.log
+tail -4 gpurun_out/lean3_pytest.log
+if grep -q "failed\|rc=124" gpurun_out/lean3_pytest.log; then exit 1; fi
+show() { python - "$1" "$2" <<'P'
+import json,sys
+try:
+    d=json.loads(open(sys.argv[1]).readline())
+    print(sys.argv[2], round(d['value'],1), d['iterations'], d['parity']['ok'], {k:round(v['avg_ms'],3) for k,v in d['per_class_ms'].items()})
+except Exception as e: print(sys.argv[2], 'failed', e)
+P
+}
+for lag in 10 9 14; do
+  KB_MARCH_LAG=$lag timeout 300 python bench_configs.py C4g --reps 2 --no-cpu > gpurun_out/lean3_c4g_l$lag.jsonl 2> gpurun_out/lean3_c4g_l$lag.err
+  show gpurun_out/lean3_c4g_l$lag.jsonl "C4g lag=$lag"
+done
+KB_LEAN_ROWS=1 timeout 300 python bench_configs.py C4g --reps 2 --no-cpu > gpurun_out/lean3_c4g_r1.jsonl 2> gpurun_out/lean3_c4g_r1.err
+show gpurun_out/lean3_c4g_r1.jsonl "C4g rows=1"
+timeout 300 python bench_configs.py C2 --reps 2 --no-cpu > gpurun_out/lean3_c2.jsonl 2> gpurun_out/lean3_c2.err
+show gpurun_out/lean3_c2.jsonl "C2"
+KB_MARCH_TRACE=1 python scratch/march_probe.py poisson3d 256 2 2>&1 | tail -22
