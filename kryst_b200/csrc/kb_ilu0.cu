@@ -342,12 +342,7 @@ int kb_tiles_apply(kb_pc_s* pc, KbTileSolve* t, const double* d_r, double* d_z, 
 void kb_tiles_free(KbTileSolve* t);
 void kb_tiles_grid(const KbTileSolve* t, int* nx, int* ny, int* nz);
 int kb_tiles_trace_get(KbTileSolve* t, unsigned long long* out, int* tx, int* ty, int* tz);
-struct KbMarch;                                      // kb_trsv_march.cu: pencil-marching solves (full-stencil box grids)
-int kb_march_build(kb_pc_s* pc, int gx, int gy, int gz, unsigned* d_err, KbMarch** out);
-int kb_march_apply(kb_pc_s* pc, KbMarch* m, const double* d_r, double* d_z, const KbCtl* skip_ctl, int skip_mask);
-void kb_march_free(KbMarch* m);
-int kb_march_trace_get(KbMarch* m, unsigned long long* out, int* px, int* py);
-struct KbLean;                                       // kb_trsv_lean.cu: warp-specialised pencil march (the default)
+struct KbLean;                                       // kb_trsv_lean.cu: warp-specialised pencil march (full-stencil box grids; the default)
 int kb_lean_build(kb_pc_s* pc, int gx, int gy, int gz, unsigned* d_err, KbLean** out);
 int kb_lean_apply(kb_pc_s* pc, KbLean* m, const double* d_r, double* d_z, const KbCtl* skip_ctl, int skip_mask);
 void kb_lean_free(KbLean* m);
@@ -370,7 +365,6 @@ struct KbIluExtra {
     int gate = 3;
     int kind = 1;            // 1 persistent chunk-ELL solve, 0 ticketed CSR solve
     KbTileSolve* tiles = nullptr;   // non-null: the factor's pattern is a 5-/7-point box grid -> block-wavefront solves
-    KbMarch* march = nullptr;       // non-null: ... and a full stencil -> pencil-marching solves (v2/v3 kernels, KB_MARCH_IMPL=old)
     KbLean* lean = nullptr;         // non-null: ... and a full stencil -> warp-specialised pencil march (preferred)
     int sleep_ns = 0;
 };
@@ -382,7 +376,6 @@ void kb_ilu0_free(kb_pc_s* pc) {
     if (x) {
         if (x->owns_pattern) { KB_FREE(pc->l_rp); KB_FREE(pc->l_col); }
         kb_tiles_free(x->tiles); x->tiles = nullptr;
-        kb_march_free(x->march); x->march = nullptr;
         kb_lean_free(x->lean); x->lean = nullptr;
         KB_FREE(x->level[0]); KB_FREE(x->level[1]); KB_FREE(x->counters); KB_FREE(x->ediag);
         for (int u = 0; u < 2; ++u) { KB_FREE(x->width[u]); KB_FREE(x->off[u]); KB_FREE(x->ecol[u]); KB_FREE(x->eval[u]); KB_FREE(x->spad[u]); KB_FREE(x->chunk_lev[u]); KB_FREE(x->done[u]); }
@@ -554,17 +547,13 @@ int kb_ilu0_build(kb_pc_s* pc) {
     }
     // 5. grid-structured pattern (5-/7-point box stencil, detected from the CSR): block-wavefront solves
     if (!(getenv("KB_TRSV_TILES") && atoi(getenv("KB_TRSV_TILES")) == 0)) KB_TRY(kb_tiles_build(pc, x->counters + 2, &x->tiles));
-    // Pencil-marching warps (kb_trsv_march.cu).  Measured on B200: 2-D 1024^2 0.67 ms per solve against 0.98 ms for the
-    // tiles; 3-D 256^3 0.83-0.88 ms against 0.73 ms (the per-step dependency chain of a warp, ~0.25 us, times the
-    // nx+ny+nz wavefront plus one L2 hand-off per pencil face exceeds 94 tile levels x 7.8 us).  Hence: default for
-    // 2-D grids, opt-in (KB_TRSV_MARCH=1) for 3-D ones, KB_TRSV_MARCH=0 switches it off.
+    // Pencil-marching warps (kb_trsv_lean.cu) when the stencil is full.  Measured on B200, per solve: 3-D 256^3 0.30 ms against
+    // 0.72 ms for the tiles and 1.45 ms level-scheduled; 2-D 1024^2 0.35 ms against 0.98 / 2.3 ms.  KB_TRSV_MARCH=0 switches it off.
     if (x->tiles) {
         int gx = 0, gy = 0, gz = 0;
         kb_tiles_grid(x->tiles, &gx, &gy, &gz);
         const int want = getenv("KB_TRSV_MARCH") ? atoi(getenv("KB_TRSV_MARCH")) : -1;
-        const bool old_impl = getenv("KB_MARCH_IMPL") && !strcmp(getenv("KB_MARCH_IMPL"), "old");
-        if (old_impl) { if (want > 0 || (want < 0 && gz == 1)) KB_TRY(kb_march_build(pc, gx, gy, gz, x->counters + 2, &x->march)); }
-        else if (want != 0) KB_TRY(kb_lean_build(pc, gx, gy, gz, x->counters + 2, &x->lean));
+        if (want != 0) KB_TRY(kb_lean_build(pc, gx, gy, gz, x->counters + 2, &x->lean));
     }
     // 6. level-ordered chunk-ELL copies of L and U for the persistent (general-pattern) solves
     if (getenv("KB_TRSV_KIND")) x->kind = atoi(getenv("KB_TRSV_KIND"));
@@ -610,7 +599,6 @@ int kb_ilu0_apply_dev(kb_pc_s* pc, const double* d_r, double* d_z, const KbCtl* 
     if (A->n == 0) return KB_OK;
     KbIluExtra* x = extra_of(pc);
     if (x->lean) return kb_lean_apply(pc, x->lean, d_r, d_z, skip_ctl, skip_mask);
-    if (x->march) return kb_march_apply(pc, x->march, d_r, d_z, skip_ctl, skip_mask);
     if (x->tiles) return kb_tiles_apply(pc, x->tiles, d_r, d_z, skip_ctl, skip_mask);
     {
         KbLaunch L(c, KB_K_TRSV);
@@ -718,11 +706,10 @@ extern "C" int kb_pc_ilu0_get_levels(kb_pc pc, int upper, uint64_t* nlevels, uin
 // diagnostics for tuning scripts (deliberately not declared in include/kryst_b200.h)
 extern "C" int kb_debug_march_trace(kb_pc pc, unsigned long long* out, int* px, int* py) {
     KbIluExtra* x = pc && pc->kind == KB_PC_ILU0 ? extra_of(pc) : nullptr;
-    if (!x || (!x->march && !x->lean)) return 0;
+    if (!x || !x->lean) return 0;
     cudaSetDevice(pc->ctx->device);
     cudaStreamSynchronize(pc->ctx->stream);
-    if (x->lean) return kb_lean_trace_get(x->lean, out, px, py);
-    return kb_march_trace_get(x->march, out, px, py);
+    return kb_lean_trace_get(x->lean, out, px, py);
 }
 
 extern "C" int kb_debug_tiles_trace(kb_pc pc, unsigned long long* out, int* tx, int* ty, int* tz) {

@@ -36,7 +36,7 @@
 #define KL_STAGE_LOG 4
 #define KL_STAGES (1 << KL_STAGE_LOG) // coefficient ring (steps): the march needs its stage within KL_STAGES-1 steps of the request, i.e.
                                      // step time >= (DRAM + TMA latency) / (KL_STAGES - 1); 8 stages pinned the step at ~0.22 us
-#define KL_PD 8                      // packet prefetch distance (steps) = unroll of the helpers' step loop
+#define KL_PD 4                      // packet prefetch distance (steps) = unroll of the helpers' step loop
 
 struct KlArgs {
     const double* __restrict__ coef; // [group][step][pencil][stream][32]
@@ -66,7 +66,7 @@ struct KbLean {
     unsigned* sync = nullptr;        // [0],[1] epoch of L / U ; [2],[3] finish tickets
     unsigned* err = nullptr;         // borrowed: the preconditioner's error word
     unsigned long long* trace = nullptr;
-    int grid = 1, threads = 0, lag = KL_PD + 6, dbg = 0;
+    int grid = 1, threads = 0, lag = KL_PD + 2, dbg = 0;
     size_t smem[2] = {0, 0};
     kl_fn fn[2] = {nullptr, nullptr};
 };
