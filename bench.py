@@ -222,6 +222,8 @@ def measure_config(name, ctx, stream, world, rank, reps=2, A=None, with_cpu=True
         solver = kb.BiCgStabSolver(TOL, MAX_ITERS, textbook=True)
     else:
         solver = kb.GmresSolver(cfg["restart"], TOL, MAX_ITERS)
+        if os.environ.get("KB_BENCH_BLOCK_ORTH") == "1":     # tuning runs only: the opt-in block-orthogonalisation variant (parity is vs CGS2 goldens)
+            solver.with_block_orthogonalisation()
     best, st = None, None
     for rep in range(reps + 1):
         x.zero_()

@@ -153,6 +153,10 @@ int kb_pc_ilu0_get_levels(kb_pc pc, int upper, uint64_t* nlevels, uint64_t* leve
 #define KB_FLAG_SINGLE_REDUCTION 16u /* PCG: Chronopoulos-Gear recurrences, ONE fused reduction (one all-reduce on
                                         shards) per iteration - what pcg.rs:36-37's flag is named after; SURVEY 8(f3) */
 
+#define KB_FLAG_BLOCK_ORTH 128u   /* GMRES: block orthogonalisation (the idea of src/solver/pca_gmres.rs:172-229): ONE classical
+                                   * Gram-Schmidt pass whose inner products {V^T w, w.w} are reduced together (one all-reduce per
+                                   * Arnoldi step instead of three), h_{j+1,j}^2 = w.w - sum h^2; 2 sweeps over the basis instead
+                                   * of 3.  Opt-in extension: CGS2 (gmres.rs:65-105 semantics) stays the default.                */
 #define KB_FLAG_HISTORY 32u       /* record the per-iteration residuals on the device; fetch with kb_get_history        */
 #define KB_FLAG_MONITOR 64u       /* slow mode: one iteration (GMRES family: one restart cycle) per launch batch,
                                      the observer set with kb_set_monitor runs on the host for every new history entry */

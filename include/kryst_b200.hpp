@@ -228,13 +228,17 @@ class GmresSolver {          // src/solver/gmres.rs:38-402
 public:
     GmresSolver(size_t restart, double tol, size_t max_iters) : restart_(restart), tol_(tol), max_iters_(max_iters) {}
     GmresSolver& with_preconditioning(Preconditioning m) { mode_ = m; return *this; }
+    // extension (block orthogonalisation, the idea of pca_gmres.rs:172-229): one CGS pass, one fused reduction per step
+    GmresSolver& with_block_orthogonalisation(bool on = true) { block_ = on; return *this; }
     SolveStats solve(const DeviceCsr& a, const Preconditioner* pc, const std::vector<double>& b, std::vector<double>& x) {
         kb_stats st{};
-        check(kb_gmres_solve(a.handle(), pc ? pc->handle() : nullptr, b.data(), x.data(), restart_, tol_, max_iters_, static_cast<int>(mode_), 0, &st));
+        check(kb_gmres_solve(a.handle(), pc ? pc->handle() : nullptr, b.data(), x.data(), restart_, tol_, max_iters_, static_cast<int>(mode_),
+                             block_ ? KB_FLAG_BLOCK_ORTH : 0u, &st));
         return to_stats(st);
     }
 private:
     size_t restart_; double tol_; size_t max_iters_; Preconditioning mode_ = Preconditioning::Left;   // gmres.rs:53
+    bool block_ = false;
 };
 class FgmresSolver {         // src/solver/fgmres.rs:30-340: FgmresSolver::new(tol, max_iters, restart).solve_flex(..)
 public:

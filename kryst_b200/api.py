@@ -21,7 +21,7 @@ from . import _ffi
 from ._ffi import KbStats, KbProfile, f64p, u64p
 
 KB_FLAG_DEVICE_PTRS, KB_FLAG_TEXTBOOK, KB_FLAG_PROFILE, KB_FLAG_NO_GRAPH, KB_FLAG_SINGLE_REDUCTION = 1, 2, 4, 8, 16
-KB_FLAG_HISTORY, KB_FLAG_MONITOR = 32, 64
+KB_FLAG_HISTORY, KB_FLAG_MONITOR, KB_FLAG_BLOCK_ORTH = 32, 64, 128
 
 
 # ---- KError (src/error.rs:6-19) ----------------------------------------------------------------
@@ -715,6 +715,14 @@ class GmresSolver(_SolverBase):
         self.preconditioning = Preconditioning(mode)
         return self
 
+    block_orthogonalisation = False
+
+    def with_block_orthogonalisation(self, on=True):
+        """Extension (the idea of src/solver/pca_gmres.rs:172-229): one classical Gram-Schmidt pass, every inner product of
+        the Arnoldi step reduced together (KB_FLAG_BLOCK_ORTH); the default stays CGS2."""
+        self.block_orthogonalisation = bool(on)
+        return self
+
     record_history = False
     monitor = None
 
@@ -727,6 +735,8 @@ class GmresSolver(_SolverBase):
         st = KbStats()
         if self.record_history:
             flags |= KB_FLAG_HISTORY
+        if self.block_orthogonalisation:
+            flags |= KB_FLAG_BLOCK_ORTH
         with _MonitorScope(a, self.monitor) as mflag:
             rc = _ffi.lib().kb_gmres_solve(a.handle, _pc_handle(pc), pb, px, self.restart, self.tol, self.max_iters,
                                            int(self.preconditioning), flags | mflag, C.byref(st))

@@ -25,12 +25,14 @@ struct KbGmresDev {       // device pointers shared by the kernels
     const double* h1src; const double* h2src;   // where the (all-reduced) CGS coefficients live
     int flex;                                   // FGMRES (fgmres.rs): single-pass CGS, z_j = M^-1 v_j kept, literal quirks
     double* Z;                                  // flexible basis (== V when there is no preconditioner)
+    int block;                                  // KB_FLAG_BLOCK_ORTH: one block classical GS pass, ||w'||^2 = w.w - sum h^2, ONE reduction per step
 };
 #define KB_SIDE_FLEX 3
 
 // ---- multi-column dot: partial[c][tile] = canonical tile sum of V_c . w, c = 0..j ----------------------
+// self_col != 0: one more "column" w . w (block orthogonalisation: the norm rides the same reduction)
 __global__ void __launch_bounds__(KB_THREADS) kb_gs_dot(KbGmresDev g, const double* __restrict__ w, long long n, double* partials, size_t pstride,
-                                                        int ncols) {
+                                                        int ncols, int self_col = 0) {
     KbCtl* ctl = g.ctl;
     if (ctl->done || ctl->cycle_break) return;
     __shared__ double sm[(KB_MAX_RESTART + 1) * 8];
@@ -48,6 +50,11 @@ __global__ void __launch_bounds__(KB_THREADS) kb_gs_dot(KbGmresDev g, const doub
         else if (h0) e0 = vc[i] * w0;
         double v = kb_warp_butterfly(e0 + e1);
         if (lane == 0) sm[c * 8 + wp] = v;
+    }
+    if (self_col) {
+        double v = kb_warp_butterfly(w0 * w0 + w1 * w1);
+        if (lane == 0) sm[ncols * 8 + wp] = v;
+        ++ncols;
     }
     __syncthreads();
     for (int c = tid; c < ncols; c += KB_THREADS) {
@@ -260,7 +267,7 @@ __global__ void __launch_bounds__(KB_THREADS) kb_gs_level2(KbCtl* ctl, const dou
 __device__ void kb_arnoldi_fin(const KbGmresDev& g, double ww, int j) {
     KbCtl* c = g.ctl;
     __shared__ double hcol[KB_MAX_RESTART + 2], scs[KB_MAX_RESTART], ssn[KB_MAX_RESTART];
-    if (g.flex) { for (int k = threadIdx.x; k <= j; k += blockDim.x) hcol[k] = g.h1src[k]; }      // one classical GS pass (fgmres.rs:219-228)
+    if (g.flex || g.block) { for (int k = threadIdx.x; k <= j; k += blockDim.x) hcol[k] = g.h1src[k]; }      // one classical GS pass (fgmres.rs:219-228)
     else { for (int k = threadIdx.x; k <= j; k += blockDim.x) hcol[k] = g.h1src[k] + g.h2src[k]; }
     for (int k = threadIdx.x; k < j; k += blockDim.x) { scs[k] = c->cs[k]; ssn[k] = c->sn[k]; }
     __syncthreads();
@@ -306,6 +313,16 @@ __global__ void kb_arnoldi_fin_kernel(KbGmresDev g, const double* sums, int j) {
     if (g.ctl->done || g.ctl->cycle_break) return;
     kb_arnoldi_fin(g, sums[0], j);
 }
+// Block orthogonalisation (the idea of pca_gmres.rs:172-229: every inner product of the step is gathered into one
+// array and reduced ONCE): sums = {V_0.w, ..., V_j.w, w.w}; ||w - V h||^2 = w.w - sum_k h_k^2 for an orthonormal V,
+// evaluated sequentially in k (mul, then sub) and clamped at 0; then the usual H column / Givens / stop test.
+__global__ void kb_block_fin_kernel(KbGmresDev g, const double* sums, int j) {
+    if (g.ctl->done || g.ctl->cycle_break) return;
+    double hn2 = sums[j + 1];
+    for (int k = 0; k <= j; ++k) hn2 = hn2 - sums[k] * sums[k];
+    if (hn2 < 0.0) hn2 = 0.0;
+    kb_arnoldi_fin(g, hn2, j);
+}
 
 // w -= V h (sequential in c: t = t - V[c][i]*h[c]); NORM: fused ||w||^2 and the Arnoldi epilogue
 template <bool NORM>
@@ -336,6 +353,31 @@ struct GsUpdateOp : KbRedBase {
         else if (slots) { if (threadIdx.x == 0) slots[0] = sums[0]; }
         else kb_arnoldi_fin(g, sums[0], ncols - 1);
     }
+};
+
+// block orthogonalisation: v_{j+1} = (w - V h) / h_{j+1,j} in one pass (the epilogue ran before this sweep)
+struct GsUpdateScaleOp : KbRedBase {
+    static constexpr int NRED = 0;
+    KbGmresDev g; const double* w; const double* hsrc; double* dst; int ncols;
+    __device__ bool skip() const { return g.ctl->done != 0 || g.ctl->cycle_break != 0; }
+    __device__ void pair(long long i, bool has1, double*) const {
+        const double d = g.ctl->hnorm;
+        if (has1) {
+            double2 t = kb_ld2(w + i);
+#pragma unroll 4
+            for (int c = 0; c < ncols; ++c) {
+                const double2 v = kb_ld2(g.V + (size_t)c * g.ld + i);
+                const double h = hsrc[c];
+                t.x = t.x - v.x * h; t.y = t.y - v.y * h;
+            }
+            kb_st2(dst + i, make_double2(t.x / d, t.y / d));
+        } else {
+            double t = w[i];
+            for (int c = 0; c < ncols; ++c) t = t - g.V[(size_t)c * g.ld + i] * hsrc[c];
+            dst[i] = t / d;
+        }
+    }
+    __device__ void finish_block(double*) const {}
 };
 
 // dst = src / *div  (v_{j+1} = w / h_{j+1,j}: gmres.rs:102-103 ; v_0 = r / beta)
@@ -603,6 +645,16 @@ static int gm_inner_iteration(GmPlan& P, int j) {
     } else {                                 // w = A v_j   (gmres.rs:80-81)
         KB_TRY((kb_launch_spmv<Epi, false>(A, vj, w->w, nullptr, nullptr, nullptr, 0, epi, P.dist ? vj : nullptr)));
     }
+    if (P.g.block) {   // {h, w.w} in ONE sweep and ONE reduction, epilogue, then v_{j+1} = (w - V h) / h_{j+1,j}: 2 sweeps over V per step
+        { KbLaunch L(c, KB_K_GS_DOT); kb_gs_dot<<<A->ntiles, KB_THREADS, 0, c->stream>>>(P.g, w->w, (long long)A->n, w->partials, w->pstride, ncols, 1); }
+        double* dst = P.dist ? w->slots : &ctl->h1[0];
+        { KbLaunch L(c, KB_K_SMALL); kb_gs_level2<<<ncols + 1, KB_THREADS, 0, c->stream>>>(ctl, w->partials, w->pstride, A->ntiles, dst); }
+        if (P.dist) KB_TRY(kb_allreduce_slots(c, w->slots, ncols + 1));
+        { KbLaunch L(c, KB_K_SMALL); kb_block_fin_kernel<<<1, KB_THREADS, 0, c->stream>>>(P.g, P.g.h1src, j); }
+        KB_CUDA(cudaGetLastError());
+        GsUpdateScaleOp op; op.partials = nullptr; op.pstride = 0; op.g = P.g; op.w = w->w; op.hsrc = P.g.h1src; op.dst = w->V + (size_t)(j + 1) * w->ld; op.ncols = ncols;
+        return gm_tile(A, op, KB_K_GS_UPDATE);
+    }
     {   // h1 = V^T w ; w -= V h1
         { KbLaunch L(c, KB_K_GS_DOT); kb_gs_dot<<<A->ntiles, KB_THREADS, 0, c->stream>>>(P.g, w->w, (long long)A->n, w->partials, w->pstride, ncols); }
         double* dst = P.dist ? w->slots : &ctl->h1[0];
@@ -739,6 +791,9 @@ static int gmres_solve_impl(kb_csr A, kb_pc pc, const double* b, double* x, uint
     P.g.h1src = dist ? w->slots : &w->ctl->h1[0];
     P.g.h2src = dist ? w->slots + (KB_MAX_RESTART + 8) : &w->ctl->h2[0];
     P.g.flex = flex ? 1 : 0; P.g.Z = (flex && pc) ? w->Z : w->V;
+    const bool block = (flags & KB_FLAG_BLOCK_ORTH) != 0;
+    if (block && flex) { kb_set_error("KB_FLAG_BLOCK_ORTH applies to kb_gmres_solve (FGMRES already makes a single pass)"); return KB_UNSUPPORTED; }
+    P.g.block = block ? 1 : 0;
     const bool profile = (flags & KB_FLAG_PROFILE) != 0;
     const bool use_graph = !(flags & (KB_FLAG_NO_GRAPH | KB_FLAG_PROFILE));
     const bool was_prof = c->profiling;
@@ -759,7 +814,7 @@ static int gmres_solve_impl(kb_csr A, kb_pc pc, const double* b, double* x, uint
             }
         }
         if ((st = gm_start_vector(P)) != KB_OK) break;
-        const uint64_t key = ((kb_pc_serial(pc) + 1) * 4 + (uint64_t)side) * 256 + restart;
+        const uint64_t key = (((kb_pc_serial(pc) + 1) * 4 + (uint64_t)side) * 256 + restart) * 2 + (block ? 1 : 0);
         st = kb_run_iterations(c, &w->gc, key, 1, (uint64_t)h->n_outer, use_graph, w->ctl, h, [&]() { return gm_cycle(P); }, &mon);
         if (st != KB_OK) break;
         if (cudaMemcpyAsync(h, w->ctl, offsetof(KbCtl, h), cudaMemcpyDeviceToHost, c->stream) != cudaSuccess ||

@@ -645,6 +645,10 @@ int ko_pcg_sr(const ko_csr* A, const ko_pc* pc, const double* b, double* x, doub
 //   variant 1 (CGS2, Tier T): textbook None/Left/Right with classical Gram-Schmidt
 //       + reorthogonalisation as a block GEMV — what the GPU runs.
 //   variant 2 (MGS2, Tier T): same textbook formulation with the literal's MGS+2nd pass.
+//   variant 3 (BLOCK, extension): textbook formulation, ONE classical GS pass with all inner products of the step
+//       (V^T w and w.w) reduced together; h_{j+1,j} = sqrt(max(w.w - sum h^2, 0)) - the block-orthogonalisation
+//       idea of src/solver/pca_gmres.rs:172-229 (which cannot run for block sizes > 1: it multiplies basis
+//       vectors that do not exist yet, :175); what the GPU runs under KB_FLAG_BLOCK_ORTH.
 //   mode: 0 None, 1 Left, 2 Right (gmres.rs:28-32); pc==NULL forces None (gmres.rs:262).
 // Shared pieces: Givens (:154-176), back-substitution (:180-192), eps = 1e-14 (:233),
 // Convergence::check inner stop (:349), true-residual test per cycle, strict < (:394-395).
@@ -740,7 +744,18 @@ int ko_gmres(const ko_csr* A, const ko_pc* pc, const double* b, double* x, u64 r
             } else {
                 ko_spmv(A, V[j].data(), w.data());     // gmres.rs:80-81
             }
-            if (variant == 1) {                        // CGS2 block GEMV
+            double hn_block = 0.0;
+            if (variant == 3) {                        // block orthogonalisation (pca_gmres.rs:172-229 idea): one CGS pass, one fused reduction
+                std::vector<double> h1(j + 1);
+                for (u64 c = 0; c <= j; ++c) h1[c] = DOT((*basis)[c].data(), w.data());
+                double hn2 = DOT(w.data(), w.data());
+                for (u64 c = 0; c <= j; ++c) hn2 = hn2 - h1[c] * h1[c];
+                if (hn2 < 0.0) hn2 = 0.0;
+                hn_block = std::sqrt(hn2);
+#pragma omp parallel for schedule(static)
+                for (i64 i = 0; i < (i64)n; ++i) { double t = w[i]; for (u64 c = 0; c <= j; ++c) t = t - (*basis)[c][i] * h1[c]; w[i] = t; }
+                for (u64 c = 0; c <= j; ++c) h[c][j] = h1[c];
+            } else if (variant == 1) {                 // CGS2 block GEMV
                 std::vector<double> h1(j + 1), h2(j + 1);
                 for (u64 c = 0; c <= j; ++c) h1[c] = DOT((*basis)[c].data(), w.data());
 #pragma omp parallel for schedule(static)
@@ -763,7 +778,7 @@ int ko_gmres(const ko_csr* A, const ko_pc* pc, const double* b, double* x, u64 r
                     for (i64 i = 0; i < (i64)n; ++i) w[i] = w[i] - t * vc[i];
                 }
             }
-            h[j + 1][j] = NRM(w.data());
+            h[j + 1][j] = variant == 3 ? hn_block : NRM(w.data());
             if (std::fabs(h[j + 1][j]) < eps) {
                 happy = true;
                 if (variant == 0 && mode != 0) break;  // gmres.rs:299-302,330-333: break BEFORE Givens/check

@@ -361,7 +361,7 @@ def pcg_sr(A, pc, b, x0, tol, max_iters, norm_type=1, nshards=1, hist_cap=0):
     return rc, x, st, hist[:min(int(hl.value), hist_cap)]
 
 
-GMRES_LITERAL, GMRES_CGS2, GMRES_MGS2 = 0, 1, 2
+GMRES_LITERAL, GMRES_CGS2, GMRES_MGS2, GMRES_BLOCK = 0, 1, 2, 3
 MODE_NONE, MODE_LEFT, MODE_RIGHT = 0, 1, 2
 
 
