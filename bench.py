@@ -346,8 +346,8 @@ def main():
     ap.add_argument("--workload", default="C4", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--configs", default="auto", help="comma list of other BASELINE configs to append (auto: N=1 -> C4g,C1,C2,C3; N=8 -> C5; none)")
-    ap.add_argument("--pcg-variant", default="literal", choices=["literal", "fused"],
-                    help="literal = pcg.rs recurrences (the headline); fused = single-reduction extension (SURVEY 8(f3))")
+    ap.add_argument("--pcg-variant", default="literal", choices=["literal", "fused", "pipelined"],
+                    help="literal = pcg.rs recurrences (the headline); fused = single-reduction extension, pipelined = Ghysels-Vanroose (SURVEY 8(f3))")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -399,9 +399,11 @@ def main():
 
     solver_obj = kb.PcgSolver(TOL, MAX_ITERS)
     solver_obj.record_history = False
-    fused = args.pcg_variant == "fused"
-    if fused:
+    fused = args.pcg_variant != "literal"
+    if args.pcg_variant == "fused":
         solver_obj.with_fused_reduction(True)
+    elif args.pcg_variant == "pipelined":
+        solver_obj.with_pipelined(True)
 
     def barrier():
         if world > 1:
@@ -478,7 +480,7 @@ def main():
         except Exception:
             traffic = None
     total_ms = sum(v["ms"] for v in prof.values())
-    iter_bytes = b_spmv + (96 if fused else 88) * nloc   # PCG+Jacobi per iteration (fused variant: DESIGN §4)
+    iter_bytes = b_spmv + {"literal": 88, "fused": 96, "pipelined": 168}[args.pcg_variant] * nloc   # PCG+Jacobi per iteration (fused variant: DESIGN §4)
     roofline = {"bound": "hbm", "kernel": "kb_spmv_bulk<PcgAp> (bulk-async staged CSR SpMV fused with p.Ap)", "achieved": achieved, "peak": peak,
                 "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": b_spmv, "avg_launch_ms": spmv_ms,

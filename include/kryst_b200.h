@@ -157,6 +157,9 @@ int kb_pc_ilu0_get_levels(kb_pc pc, int upper, uint64_t* nlevels, uint64_t* leve
                                    * Gram-Schmidt pass whose inner products {V^T w, w.w} are reduced together (one all-reduce per
                                    * Arnoldi step instead of three), h_{j+1,j}^2 = w.w - sum h^2; 2 sweeps over the basis instead
                                    * of 3.  Opt-in extension: CGS2 (gmres.rs:65-105 semantics) stays the default.                */
+#define KB_FLAG_PIPELINED 256u    /* PCG: pipelined recurrences (Ghysels-Vanroose): u = M^-1 r and w = A u are carried by recurrences, so the
+                                   * ONE reduction of an iteration {r.u, w.u, norm} is sent before the iteration's SpMV and received after
+                                   * it (the all-reduce overlaps the SpMV on shards).  Jacobi / no preconditioner.  Opt-in extension.     */
 #define KB_FLAG_HISTORY 32u       /* record the per-iteration residuals on the device; fetch with kb_get_history        */
 #define KB_FLAG_MONITOR 64u       /* slow mode: one iteration (GMRES family: one restart cycle) per launch batch,
                                      the observer set with kb_set_monitor runs on the host for every new history entry */

@@ -206,6 +206,8 @@ public:
     PcgSolver& with_single_reduction(bool f) { single_reduction_ = f; return *this; }
     // extension: true single-reduction (Chronopoulos-Gear) recurrences, KB_FLAG_SINGLE_REDUCTION
     PcgSolver& with_fused_reduction(bool f = true) { fused_ = f; return *this; }
+    // extension: pipelined (Ghysels-Vanroose) recurrences, KB_FLAG_PIPELINED
+    PcgSolver& with_pipelined(bool f = true) { pipelined_ = f; return *this; }
     PcgSolver& with_radius(double r) { radius_ = r; has_radius_ = true; return *this; }
     PcgSolver& with_obj_target(double t) { obj_target_ = t; has_obj_target_ = true; return *this; }
     std::vector<double> residual_history;
@@ -213,7 +215,7 @@ public:
         std::vector<double> hist(max_iters_ + 1 < (1u << 20) ? max_iters_ + 1 : (1u << 20));
         uint64_t hl = 0;
         kb_stats st{};
-        int rc = kb_pcg_solve(a.handle(), pc ? pc->handle() : nullptr, b.data(), x.data(), tol_, max_iters_, static_cast<int>(norm_), fused_ ? KB_FLAG_SINGLE_REDUCTION : 0u,
+        int rc = kb_pcg_solve(a.handle(), pc ? pc->handle() : nullptr, b.data(), x.data(), tol_, max_iters_, static_cast<int>(norm_), (fused_ ? KB_FLAG_SINGLE_REDUCTION : 0u) | (pipelined_ ? KB_FLAG_PIPELINED : 0u),
                               hist.data(), hist.size(), &hl, &st);
         residual_history.insert(residual_history.end(), hist.begin(), hist.begin() + (hl < hist.size() ? hl : hist.size()));
         check(rc);
@@ -221,7 +223,7 @@ public:
     }
 private:
     double tol_; size_t max_iters_; CgNormType norm_ = CgNormType::Unpreconditioned;
-    bool single_reduction_ = false, fused_ = false, has_radius_ = false, has_obj_target_ = false;
+    bool single_reduction_ = false, fused_ = false, pipelined_ = false, has_radius_ = false, has_obj_target_ = false;
     double radius_ = 0.0, obj_target_ = 0.0;
 };
 class GmresSolver {          // src/solver/gmres.rs:38-402

@@ -21,7 +21,7 @@ from . import _ffi
 from ._ffi import KbStats, KbProfile, f64p, u64p
 
 KB_FLAG_DEVICE_PTRS, KB_FLAG_TEXTBOOK, KB_FLAG_PROFILE, KB_FLAG_NO_GRAPH, KB_FLAG_SINGLE_REDUCTION = 1, 2, 4, 8, 16
-KB_FLAG_HISTORY, KB_FLAG_MONITOR, KB_FLAG_BLOCK_ORTH = 32, 64, 128
+KB_FLAG_HISTORY, KB_FLAG_MONITOR, KB_FLAG_BLOCK_ORTH, KB_FLAG_PIPELINED = 32, 64, 128, 256
 
 
 # ---- KError (src/error.rs:6-19) ----------------------------------------------------------------
@@ -637,6 +637,7 @@ class PcgSolver(_SolverBase):
         self.norm_type = CgNormType.Unpreconditioned
         self.single_reduction = False
         self.fused_reduction = False
+        self.pipelined = False
         self.radius = None
         self.obj_target = None
         self.residual_history = []
@@ -661,6 +662,13 @@ class PcgSolver(_SolverBase):
         self.fused_reduction = bool(flag)
         return self
 
+    def with_pipelined(self, flag=True):
+        """Extension: pipelined (Ghysels-Vanroose) recurrences - the one reduction of an iteration is sent
+        before that iteration's SpMV and received after it (KB_FLAG_PIPELINED; Jacobi / no pc only).  Parity is checked
+        against the oracle's restatement of this variant."""
+        self.pipelined = bool(flag)
+        return self
+
     def with_radius(self, radius):
         # pcg.rs:72-75 stores the value; solve (pcg.rs:114-222) never reads it - same here
         self.radius = float(radius)
@@ -682,6 +690,8 @@ class PcgSolver(_SolverBase):
         pb, px, flags, keep = self._solve_args(a, b, x)
         if self.fused_reduction:
             flags |= KB_FLAG_SINGLE_REDUCTION
+        if self.pipelined:
+            flags |= KB_FLAG_PIPELINED
         cap = 0
         hist = None
         if self.record_history or self.monitor:

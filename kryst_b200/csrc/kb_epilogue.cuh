@@ -34,6 +34,7 @@ struct KbFinish {
     double* slots = nullptr;
     int nred = 0;
     const KbP2PDev* p2p = nullptr;
+    int recv_only = 0;       // pipelined PCG: ssum[1..nred) were SENT by the previous kernel (kb_p2p_allreduce_send); only receive here
     template <int BAR>
     __device__ void coop(double* ssum) const {
         if constexpr (kb_has_pre<Fin>::value) {
@@ -41,7 +42,8 @@ struct KbFinish {
             kb_sync<BAR>();
         }
         if (p2p) {
-            kb_p2p_allreduce_block<BAR>(*p2p, ssum, nred);
+            if (recv_only) kb_p2p_allreduce_recv<BAR>(*p2p, ssum + 1, nred - 1);
+            else kb_p2p_allreduce_block<BAR>(*p2p, ssum, nred);
             if (threadIdx.x == 0) fin(ssum);
         } else if (threadIdx.x == 0) {
             if (slots) { for (int r = 0; r < nred; ++r) slots[r] = ssum[r]; }

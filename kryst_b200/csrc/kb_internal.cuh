@@ -60,7 +60,7 @@ struct KbCtl {
     double* hist;              // device residual history (residual_history pushes)
     // --- PCG (pcg.rs:114-222)
     double rz, pAp, alpha, beta, rz_new;
-    double sr_loc[2];          // single-reduction PCG: this rank's r.u and norm sums, folded into the SpMV's all-reduce
+    double sr_loc[3];          // single-reduction / pipelined PCG: this rank's sums of the update kernel, folded into the SpMV's all-reduce
     int norm_type;
     // --- BiCGStab (bicgstab.rs:69-293)
     double rho, rho_prev, omega, omega_prev, alpha_den, thr, rnorm, vv;

@@ -98,6 +98,46 @@ __device__ __forceinline__ void kb_p2p_allreduce_block(const KbP2PDev& p, double
     kb_sync<BAR>();
 }
 
+// The two halves of kb_p2p_allreduce_block as separate calls (pipelined PCG): the kernel that produced the sums SENDS
+// them, the last CTA of the following SpMV RECEIVES - the NVLink flight time passes while the SpMV runs.
+// No other reduction may start between the two (the receive reads the sequence number the send advanced).
+template <int BAR = 0>
+__device__ __forceinline__ void kb_p2p_allreduce_send(const KbP2PDev& p, const double* in, int count) {
+    __shared__ unsigned long long s_seq_s;
+    const int tid = threadIdx.x;
+    if (tid == 0) { s_seq_s = *p.seq + 1ull; *p.seq = s_seq_s; }
+    kb_sync<BAR>();
+    const unsigned long long seq = s_seq_s;
+    const unsigned tag = (unsigned)seq;
+    const size_t par = (size_t)(seq & 1ull);
+    for (int idx = tid; idx < p.size * count; idx += KB_THREADS) {
+        const int q = idx / count, r = idx - q * count;
+        kb_ll_store(reinterpret_cast<ulonglong2*>(p.vals[q]) + (par * p.size + p.rank) * KB_AR_MAX + r, in[r], tag);
+    }
+    kb_sync<BAR>();
+}
+template <int BAR = 0>
+__device__ __forceinline__ void kb_p2p_allreduce_recv(const KbP2PDev& p, double* out, int count) {
+    const int tid = threadIdx.x;
+    const unsigned long long seq = *reinterpret_cast<const volatile unsigned long long*>(p.seq);      // advanced by the send (an earlier kernel)
+    const unsigned tag = (unsigned)seq;
+    const size_t par = (size_t)(seq & 1ull);
+    for (int r = tid; r < count; r += KB_THREADS) {
+        const ulonglong2* v = reinterpret_cast<const ulonglong2*>(p.vals[p.rank]) + (par * p.size) * KB_AR_MAX + r;
+        double s = 0.0;
+        for (int q = 0; q < p.size; ++q) {                 // rank order: the oracle's sharded reduction
+            double x;
+            unsigned spins = 0;
+            while (!kb_ll_load(v + (size_t)q * KB_AR_MAX, tag, &x)) {
+                if (++spins > KB_SPIN_LIMIT) { atomicExch(p.err, 1u); break; }
+            }
+            s = q == 0 ? x : s + x;
+        }
+        out[r] = s;
+    }
+    kb_sync<BAR>();
+}
+
 __global__ void __launch_bounds__(KB_THREADS) kb_p2p_allreduce_kernel(KbP2PDev p, double* vals, int count);
 
 // Halo push fused into the kernel that produces the SpMV operand: called by all 256 threads of the CTA that owns

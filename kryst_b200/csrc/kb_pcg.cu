@@ -260,6 +260,98 @@ struct PcgSrOp : KbRedBase {          // S1 (INIT: u = D^-1 r ; p = s = 0 and th
     __device__ void finish_block(double* sm) const { fin.template coop<0>(sm); }
 };
 
+// ---- pipelined variant (Ghysels-Vanroose) --------------------------------------------------
+// One iteration = two kernels; its ONE reduction is SENT by the first and RECEIVED by the second:
+//   P1  z = n + beta z ; q = m + beta q ; s = w + beta s ; p = u + beta p ; x += alpha p ; r -= alpha s ;
+//       u -= alpha q ; w -= alpha z ; m = D^-1 w ; sums of r.u, w.u and the norm; on shards its last CTA stores the
+//       three sums into every peer's mailbox (kb_p2p_allreduce_send) and returns
+//   P2  n = A m ; its last CTA receives the sums (they crossed NVLink while the SpMV ran), then history push,
+//       Convergence::check and the Chronopoulos-Gear scalars (beta = g'/g, p.Ap = delta - beta g'/alpha, alpha)
+// Bytes per iteration: B_spmv + 168 n (literal path: B_spmv + 88 n): more vector traffic for a hidden all-reduce.
+struct PcgPipeFin {      // P2 epilogue; s = {m.n (unused), r.u, w.u, norm sum} (global)
+    KbCtl* ctl;
+    __device__ void pre(double* s) const { s[1] = ctl->sr_loc[0]; s[2] = ctl->sr_loc[1]; s[3] = ctl->sr_loc[2]; }
+    __device__ void operator()(const double* s) const {
+        KbCtl* c = ctl;
+        const double g_new = s[1], delta = s[2];
+        const double res = (c->norm_type == KB_NORM_PRECONDITIONED || c->norm_type == KB_NORM_UNPRECONDITIONED) ? sqrt(s[3])
+                           : (c->norm_type == KB_NORM_NATURAL ? sqrt(fabs(g_new)) : 0.0);
+        if (c->hist_len < c->hist_cap) c->hist[c->hist_len] = res;
+        c->hist_len += 1;
+        c->res = res;
+        const unsigned long long it = c->iter + 1;
+        c->iter = it;
+        const double rel = res / c->res0;                       // Convergence::check (convergence.rs:18-34)
+        if (rel <= c->tol || it >= c->max_iters) { c->converged = 1; c->done = 1; return; }
+        const double beta = g_new / c->rz;
+        if (beta < 0.0) { c->status = KB_INDEFINITE_PC; c->converged = 0; c->done = 1; return; }
+        const double pAp = delta - beta * g_new / c->alpha;
+        if (pAp <= 0.0) { c->status = KB_INDEFINITE_MATRIX; c->iter = it + 1; c->converged = 0; c->done = 1; return; }
+        c->pAp = pAp; c->beta = beta; c->alpha = g_new / pAp; c->rz = g_new;
+    }
+};
+struct PcgPipeInitOp : KbRedBase {     // m = D^-1 w ; z = q = 0   (after the single-reduction set-up: u, w, p = s = 0 and the scalars exist)
+    static constexpr int NRED = 0;
+    const double* w; const double* inv; double* m; double* z; double* q;
+    __device__ bool skip() const { return false; }
+    __device__ void pair(long long i, bool has1, double*) const {
+        if (has1) {
+            double2 ww = kb_ld2(w + i);
+            if (inv) { const double2 d = kb_ld2(inv + i); ww = make_double2(d.x * ww.x, d.y * ww.y); }
+            kb_st2(m + i, ww); kb_st2(z + i, make_double2(0.0, 0.0)); kb_st2(q + i, make_double2(0.0, 0.0));
+        } else { m[i] = inv ? inv[i] * w[i] : w[i]; z[i] = 0.0; q[i] = 0.0; }
+    }
+    __device__ void finish_block(double*) const {}
+};
+struct PcgPipeOp : KbRedBase {         // P1
+    static constexpr int NRED = 3;
+    double *x, *r, *u, *w, *m, *z, *q, *s, *p; const double* nn; const double* inv; KbCtl* ctl; const KbP2PDev* p2p;
+    __device__ bool skip() const { return ctl->done != 0; }
+    __device__ void pair(long long i, bool has1, double* red) const {
+        const int nt = ctl->norm_type;
+        const double alpha = ctl->alpha, beta = ctl->beta;
+        if (has1) {
+            double2 zz = kb_ld2(z + i), qq = kb_ld2(q + i), ss = kb_ld2(s + i), pp = kb_ld2(p + i);
+            const double2 n2 = kb_ld2(nn + i), m2 = kb_ld2(m + i);
+            double2 ww = kb_ld2(w + i), uu = kb_ld2(u + i), xx = kb_ld2(x + i), rr = kb_ld2(r + i);
+            zz.x = n2.x + beta * zz.x; zz.y = n2.y + beta * zz.y;
+            qq.x = m2.x + beta * qq.x; qq.y = m2.y + beta * qq.y;
+            ss.x = ww.x + beta * ss.x; ss.y = ww.y + beta * ss.y;
+            pp.x = uu.x + beta * pp.x; pp.y = uu.y + beta * pp.y;
+            xx.x = xx.x + alpha * pp.x; xx.y = xx.y + alpha * pp.y;
+            rr.x = rr.x - alpha * ss.x; rr.y = rr.y - alpha * ss.y;
+            uu.x = uu.x - alpha * qq.x; uu.y = uu.y - alpha * qq.y;
+            ww.x = ww.x - alpha * zz.x; ww.y = ww.y - alpha * zz.y;
+            kb_st2(z + i, zz); kb_st2(q + i, qq); kb_st2(s + i, ss); kb_st2(p + i, pp);
+            kb_st2(x + i, xx); kb_st2(r + i, rr); kb_st2(u + i, uu); kb_st2(w + i, ww);
+            double2 mm = ww;
+            if (inv) { const double2 d = kb_ld2(inv + i); mm = make_double2(d.x * ww.x, d.y * ww.y); }
+            kb_st2(m + i, mm);
+            red[0] = rr.x * uu.x + rr.y * uu.y;
+            red[1] = ww.x * uu.x + ww.y * uu.y;
+            red[2] = nt == KB_NORM_PRECONDITIONED ? (uu.x * uu.x + uu.y * uu.y) : nt == KB_NORM_UNPRECONDITIONED ? (rr.x * rr.x + rr.y * rr.y) : 0.0;
+        } else {
+            const double zz = nn[i] + beta * z[i];
+            const double qq = m[i] + beta * q[i];
+            const double ss = w[i] + beta * s[i];
+            const double pp = u[i] + beta * p[i];
+            const double xx = x[i] + alpha * pp;
+            const double rr = r[i] - alpha * ss;
+            const double uu = u[i] - alpha * qq;
+            const double ww = w[i] - alpha * zz;
+            z[i] = zz; q[i] = qq; s[i] = ss; p[i] = pp; x[i] = xx; r[i] = rr; u[i] = uu; w[i] = ww;
+            m[i] = inv ? inv[i] * ww : ww;
+            red[0] = rr * uu + 0.0;
+            red[1] = ww * uu + 0.0;
+            red[2] = nt == KB_NORM_PRECONDITIONED ? (uu * uu + 0.0) : nt == KB_NORM_UNPRECONDITIONED ? (rr * rr + 0.0) : 0.0;
+        }
+    }
+    __device__ void finish_block(double* sm) const {      // called by all threads of the last CTA
+        if (p2p) kb_p2p_allreduce_send<0>(*p2p, sm, 3);
+        else if (threadIdx.x == 0) { ctl->sr_loc[0] = sm[0]; ctl->sr_loc[1] = sm[1]; ctl->sr_loc[2] = sm[2]; }
+    }
+};
+
 // ---- workspace ----------------------------------------------------------------------------------
 struct KbPcgWs {
     uint64_t n = 0, nx = 0;
@@ -271,12 +363,13 @@ struct KbPcgWs {
     KbGraphCache gc;
     unsigned* mega_bar = nullptr;     // grid-barrier words of the persistent kernel
     double *u_sr = nullptr, *s_sr = nullptr;   // single-reduction variant: u (SpMV operand, with ghost tail) and s = A p
+    double *m_pp = nullptr, *n_pp = nullptr, *q_pp = nullptr;   // pipelined variant: m = M^-1 w (SpMV operand, with ghost tail), n = A m, q
 };
 void kb_pcg_ws_free(KbPcgWs* w) {
     if (!w) return;
     w->gc.reset();
     KB_FREE(w->x); KB_FREE(w->r); KB_FREE(w->z); KB_FREE(w->p); KB_FREE(w->ap); KB_FREE(w->b);
-    KB_FREE(w->partials); KB_FREE(w->slots); KB_FREE(w->ctl); KB_FREE(w->hist); KB_FREE(w->mega_bar); KB_FREE(w->u_sr); KB_FREE(w->s_sr);
+    KB_FREE(w->partials); KB_FREE(w->slots); KB_FREE(w->ctl); KB_FREE(w->hist); KB_FREE(w->mega_bar); KB_FREE(w->u_sr); KB_FREE(w->s_sr); KB_FREE(w->m_pp); KB_FREE(w->n_pp); KB_FREE(w->q_pp);
     if (w->h_ctl) cudaFreeHost(w->h_ctl);
     delete w;
 }
@@ -290,7 +383,7 @@ static int pcg_ws_get(kb_csr_s* A, uint64_t hist_cap, KbPcgWs** out) {
         KB_TRY(kb_alloc(&w->r, w->n + 2)); KB_TRY(kb_alloc(&w->z, w->n + 2));
         KB_TRY(kb_alloc(&w->ap, w->n + 2)); KB_TRY(kb_alloc(&w->b, w->n + 2));
         w->pstride = (size_t)A->ntiles + 1;
-        KB_TRY(kb_alloc(&w->partials, 2 * w->pstride));
+        KB_TRY(kb_alloc(&w->partials, 3 * w->pstride));      // up to three fused sums per kernel (pipelined variant)
         KB_TRY(kb_alloc(&w->slots, 64));
         KB_TRY(kb_alloc(&w->ctl, 1));
         KB_CUDA(cudaMallocHost((void**)&w->h_ctl, sizeof(KbCtl)));
@@ -365,6 +458,41 @@ static int pcg_sr_iteration(kb_csr_s* A, const kb_pc_s* pc, KbPcgWs* w) {
     return A->dist && A->ctx->size > 1 ? pcg_sr_launch<true, false>(A, pc, w) : pcg_sr_launch<false, false>(A, pc, w);
 }
 
+// pipelined variant: set-up (after the single-reduction set-up) and one iteration
+template <bool DIST>
+static int pcg_pipe_init(kb_csr_s* A, const kb_pc_s* pc, KbPcgWs* w) {
+    kb_ctx_s* c = A->ctx;
+    PcgPipeInitOp op; op.n = (long long)w->n; op.partials = nullptr; op.pstride = 0; op.ticket = c->ticket;
+    op.w = w->ap; op.inv = pc ? pc->inv_diag : nullptr; op.m = w->m_pp; op.z = w->z; op.q = w->q_pp;
+    { KbLaunch L(c, KB_K_INIT); kb_tile_kernel<<<std::max(A->ntiles, 1), KB_THREADS, 0, c->stream>>>(op); }
+    KB_CUDA(cudaGetLastError());
+    KbEpiNone epi;
+    return kb_launch_spmv<KbEpiNone, false>(A, w->m_pp, w->n_pp, nullptr, nullptr, nullptr, 0, epi, DIST ? w->m_pp : nullptr);
+}
+template <bool DIST>
+static int pcg_pipe_launch(kb_csr_s* A, const kb_pc_s* pc, KbPcgWs* w) {
+    kb_ctx_s* c = A->ctx;
+    const KbP2PDev* p2p = DIST ? kb_p2p_dev_ptr(c) : nullptr;
+    {
+        PcgPipeOp op; op.n = (long long)w->n; op.partials = w->partials; op.pstride = w->pstride; op.ticket = c->ticket;
+        op.x = w->x; op.r = w->r; op.u = w->u_sr; op.w = w->ap; op.m = w->m_pp; op.z = w->z; op.q = w->q_pp; op.s = w->s_sr; op.p = w->p;
+        op.nn = w->n_pp; op.inv = pc ? pc->inv_diag : nullptr; op.ctl = w->ctl; op.p2p = p2p;
+        { KbLaunch L(c, KB_K_PCG_UPDATE); kb_tile_kernel<<<std::max(A->ntiles, 1), KB_THREADS, 0, c->stream>>>(op); }
+        KB_CUDA(cudaGetLastError());
+    }
+    {
+        typedef KbSpmvEpi<PcgPipeFin, true, false> Epi;
+        Epi epi; epi.ctl = w->ctl; epi.fin = kb_make_fin(c, PcgPipeFin{w->ctl}, DIST, w->slots, 4);
+        epi.fin.recv_only = p2p ? 1 : 0;
+        KB_TRY((kb_launch_spmv<Epi, false>(A, w->m_pp, w->n_pp, nullptr, w->m_pp, w->partials, w->pstride, epi, DIST ? w->m_pp : nullptr)));
+        if (DIST) KB_TRY((kb_finish_dist<PcgPipeFin>(c, PcgPipeFin{w->ctl}, w->ctl, w->slots, 4)));
+    }
+    return KB_OK;
+}
+static int pcg_pipe_iteration(kb_csr_s* A, const kb_pc_s* pc, KbPcgWs* w) {
+    return A->dist && A->ctx->size > 1 ? pcg_pipe_launch<true>(A, pc, w) : pcg_pipe_launch<false>(A, pc, w);
+}
+
 // whole solve in one cooperative launch (single GPU, bulk SpMV, Jacobi or no preconditioner)
 static int pcg_persistent(kb_csr_s* A, const kb_pc_s* pc, KbPcgWs* w) {
     kb_ctx_s* c = A->ctx;
@@ -414,9 +542,11 @@ extern "C" int kb_pcg_solve(kb_csr A, kb_pc pc, const double* b, double* x, doub
     if (hist_len) *hist_len = 0;
     if (A->n == 0 && !dist) { stats->converged = 0; return KB_OK; }
     const bool jacobi_like = !pc || pc->kind == KB_PC_JACOBI;
-    const bool single_red = (flags & KB_FLAG_SINGLE_REDUCTION) != 0;
-    if (single_red && !jacobi_like) { kb_set_error("single-reduction PCG supports Jacobi or no preconditioner"); return KB_UNSUPPORTED; }
+    const bool pipelined = (flags & KB_FLAG_PIPELINED) != 0;
+    const bool single_red = (flags & KB_FLAG_SINGLE_REDUCTION) != 0 || pipelined;      // the pipelined variant shares the single-reduction set-up
+    if (single_red && !jacobi_like) { kb_set_error("single-reduction / pipelined PCG supports Jacobi or no preconditioner"); return KB_UNSUPPORTED; }
     if (single_red && !w->u_sr) { KB_TRY(kb_alloc(&w->u_sr, w->nx + 2)); KB_TRY(kb_alloc(&w->s_sr, w->n + 2)); }
+    if (pipelined && !w->m_pp) { KB_TRY(kb_alloc(&w->m_pp, w->nx + 2)); KB_TRY(kb_alloc(&w->n_pp, w->n + 2)); KB_TRY(kb_alloc(&w->q_pp, w->n + 2)); }
 
     KB_TRY(kb_upload_or_alias(c, b, w->b, w->n, dev));
     KB_TRY(kb_upload_or_alias(c, x, w->x, w->n, dev));
@@ -445,6 +575,7 @@ extern "C" int kb_pcg_solve(kb_csr A, kb_pc pc, const double* b, double* x, doub
         if (single_red) {     // u = D^-1 r ; w = A u ; gamma, delta, res0, first history entry
             st = dist ? pcg_sr_launch<true, true>(A, pc, w) : pcg_sr_launch<false, true>(A, pc, w);
             if (st != KB_OK) break;
+            if (pipelined && (st = dist ? pcg_pipe_init<true>(A, pc, w) : pcg_pipe_init<false>(A, pc, w)) != KB_OK) break;   // m = M^-1 w ; n = A m ; z = q = 0
         } else if (!jacobi_like) {   // z = M^-1 r ; p = z ; rz ; norm
             if ((st = kb_pc_apply_dev(pc, w->r, w->z, nullptr, 0)) != KB_OK) break;
             PcgRzOp<PcgInitFin, true> op; op.n = (long long)w->n; op.partials = w->partials; op.pstride = w->pstride; op.ticket = c->ticket;
@@ -478,8 +609,8 @@ extern "C" int kb_pcg_solve(kb_csr A, kb_pc pc, const double* b, double* x, doub
         // iterations per graph replay: ~2 ms of work, so the per-replay host poll is amortised
         const int B = kb_batch_size(12.0 * (double)A->nnz + 108.0 * (double)A->n, 3);
         // graph key: the captured launches differ between the two variants
-        st = kb_run_iterations(c, &w->gc, (kb_pc_serial(pc) + 1) ^ (single_red ? 0x5352ull << 48 : 0ull), B, max_iters, use_graph, w->ctl, h,
-                               [&]() { return single_red ? pcg_sr_iteration(A, pc, w) : pcg_iteration(A, pc, w); }, &mon);
+        st = kb_run_iterations(c, &w->gc, (kb_pc_serial(pc) + 1) ^ (pipelined ? 0x5049ull << 48 : single_red ? 0x5352ull << 48 : 0ull), B, max_iters, use_graph, w->ctl, h,
+                               [&]() { return pipelined ? pcg_pipe_iteration(A, pc, w) : single_red ? pcg_sr_iteration(A, pc, w) : pcg_iteration(A, pc, w); }, &mon);
         }
         if (st != KB_OK) break;
         if (cudaMemcpyAsync(h, w->ctl, offsetof(KbCtl, h), cudaMemcpyDeviceToHost, c->stream) != cudaSuccess ||

@@ -638,6 +638,72 @@ int ko_pcg_sr(const ko_csr* A, const ko_pc* pc, const double* b, double* x, doub
     return finish(KO_OK);
 }
 
+// Pipelined PCG (Ghysels & Vanroose 2014, Alg. 4): the Chronopoulos-Gear scalars of ko_pcg_sr, but u = M^-1 r
+// and w = A u are carried by recurrences (u -= alpha q, w -= alpha z with q = m + beta q, z = n + beta z, m = M^-1 w,
+// n = A m), so the one reduction of an iteration {r.u, w.u, norm} does not depend on that iteration's SpMV and can
+// overlap it.  Same conventions as ko_pcg / ko_pcg_sr (first history entry, res0 = sqrt|r0.u0|, Convergence::check,
+// IndefiniteMatrix / IndefinitePreconditioner exits, x written only on Ok).
+int ko_pcg_pipe(const ko_csr* A, const ko_pc* pc, const double* b, double* x, double tol, u64 max_iters,
+                int norm_type, u64 nshards, double* history, u64 hist_cap, u64* hist_len, ko_stats* stats) {
+    const u64 n = A->n;
+    std::vector<double> xv(x, x + n), r(n), u(n), w(n), m(n), nn(n), p(n, 0.0), sv(n, 0.0), z(n, 0.0), q(n, 0.0);
+    u64 hl = 0;
+    auto push = [&](double v) { if (history && hl < hist_cap) history[hl] = v; ++hl; };
+    auto DOT = [&](const std::vector<double>& a, const std::vector<double>& c) { return ko_dot_sharded(n, a.data(), c.data(), nshards); };
+    ko_spmv(A, xv.data(), w.data());
+#pragma omp parallel for schedule(static)
+    for (i64 i = 0; i < (i64)n; ++i) r[i] = b[i] - w[i];
+    pc_apply(pc, r.data(), u.data(), n);
+    double gamma = DOT(r, u);
+    auto NORM = [&](double g) -> double {
+        switch (norm_type) {
+        case 0: return std::sqrt(DOT(u, u));
+        case 1: return std::sqrt(DOT(r, r));
+        case 2: return std::sqrt(std::fabs(g));
+        default: return 0.0;
+        }
+    };
+    double res = NORM(gamma);
+    ko_spmv(A, u.data(), w.data());
+    double delta = DOT(u, w);
+    const double res0 = std::sqrt(std::fabs(gamma));
+    stats->iterations = 0; stats->final_residual = res0; stats->converged = 0; stats->breakdown = 0;
+    push(res);
+    auto finish = [&](int rc) { if (rc == KO_OK) std::memcpy(x, xv.data(), sizeof(double) * n); if (hist_len) *hist_len = hl; return rc; };
+    if (max_iters == 0) return finish(KO_OK);
+    if (delta <= 0.0) { stats->iterations = 1; stats->final_residual = res; return finish(KO_INDEFINITE_MATRIX); }
+    double alpha = gamma / delta, beta = 0.0;
+    pc_apply(pc, w.data(), m.data(), n);
+    ko_spmv(A, m.data(), nn.data());
+    for (u64 i = 0; i < max_iters; ++i) {
+#pragma omp parallel for schedule(static)
+        for (i64 k = 0; k < (i64)n; ++k) {
+            z[k] = nn[k] + beta * z[k];
+            q[k] = m[k] + beta * q[k];
+            sv[k] = w[k] + beta * sv[k];
+            p[k] = u[k] + beta * p[k];
+            xv[k] = xv[k] + alpha * p[k];
+            r[k] = r[k] - alpha * sv[k];
+            u[k] = u[k] - alpha * q[k];
+            w[k] = w[k] - alpha * z[k];
+        }
+        pc_apply(pc, w.data(), m.data(), n);
+        const double gamma_new = DOT(r, u);
+        delta = DOT(w, u);
+        res = NORM(gamma_new);
+        ko_spmv(A, m.data(), nn.data());
+        push(res);
+        if (conv_check(res, res0, i + 1, tol, max_iters, stats)) return finish(KO_OK);
+        beta = gamma_new / gamma;
+        if (beta < 0.0) { stats->iterations = i + 1; stats->final_residual = res; stats->converged = 0; return finish(KO_INDEFINITE_PC); }
+        const double pAp = delta - beta * gamma_new / alpha;
+        if (pAp <= 0.0) { stats->iterations = i + 2; stats->final_residual = res; stats->converged = 0; return finish(KO_INDEFINITE_MATRIX); }
+        alpha = gamma_new / pAp;
+        gamma = gamma_new;
+    }
+    return finish(KO_OK);
+}
+
 // ----------------------------------------------------------------------------
 // GMRES
 //   variant 0 (LITERAL): src/solver/gmres.rs:216-402 exactly, incl. the inconsistent

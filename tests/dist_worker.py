@@ -127,6 +127,24 @@ def main():
         assert st.final_residual == so.final_residual, "dist single-reduction pcg residual"
         if rc == 0:
             assert np.array_equal(x, xo[lo:hi]), "dist single-reduction pcg"
+        # pipelined PCG: the iteration's one reduction is sent by the update kernel and received at the end of
+        # the SpMV; same status / bits as the oracle's restatement
+        x = np.zeros(hi - lo)
+        rc, xo, so, _ = o.pcg_pipe(Ao, o.OPc.jacobi(Ao), bg, np.zeros(n), 1e-8, 3000, nshards=world)
+        pp = kb.PcgSolver(1e-8, 3000).with_pipelined()
+        try:
+            st = pp.solve(A, kb.Jacobi().setup(A), b, x)
+            assert rc == 0, ("pipelined: oracle failed, device did not", kind, rc)
+        except kb.IndefiniteMatrix:
+            assert rc == 3 and not x.any(), ("pipelined: device raised IndefiniteMatrix", kind, rc)
+            st = pp.last_stats
+        except kb.IndefinitePreconditioner:
+            assert rc == 4 and not x.any(), ("pipelined: device raised IndefinitePreconditioner", kind, rc)
+            st = pp.last_stats
+        assert (st.iterations, st.converged) == (so.iterations, bool(so.converged)), ("pipelined", kind, st.iterations, so.iterations)
+        assert st.final_residual == so.final_residual, "dist pipelined pcg residual"
+        if rc == 0:
+            assert np.array_equal(x, xo[lo:hi]), "dist pipelined pcg"
         # BiCGStab (textbook) + Jacobi
         x = np.zeros(hi - lo)
         st = kb.BiCgStabSolver(1e-8, 3000, textbook=True).solve(A, kb.Jacobi().setup(A), b, x)
@@ -142,6 +160,12 @@ def main():
                                  mode=mode, variant=o.GMRES_CGS2, nshards=world)
             assert (st.iterations, st.converged) == (so.iterations, bool(so.converged)), ("dist gmres", kind, mode, st.iterations, so.iterations)
             assert st.final_residual == so.final_residual and np.array_equal(x, xo[lo:hi]), "dist gmres"
+        # GMRES with block orthogonalisation: ONE all-reduce of j+2 sums per Arnoldi step
+        x = np.zeros(hi - lo)
+        st = kb.GmresSolver(10, 1e-8, 3000).with_block_orthogonalisation().solve(A, kb.Ilu0().setup(A), b, x)
+        rc, xo, so = o.gmres(Ao, o.OPc.ilu0(Ao, nblocks=world), bg, np.zeros(n), 10, 1e-8, 3000, mode=1, variant=o.GMRES_BLOCK, nshards=world)
+        assert (st.iterations, st.converged) == (so.iterations, bool(so.converged)), ("dist block-orth gmres", kind, st.iterations, so.iterations)
+        assert st.final_residual == so.final_residual and np.array_equal(x, xo[lo:hi]), "dist block-orth gmres"
         # FGMRES (flexible, block-Jacobi ILU(0) as the fixed preconditioner)
         x = np.zeros(hi - lo)
         st = kb.FgmresSolver(1e-8, 3000, 10).solve_flex(A, kb.Ilu0().setup(A), b, x)

@@ -82,6 +82,9 @@ def lib():
         L.ko_pcg.restype = C.c_int
         L.ko_pcg.argtypes = [C.POINTER(KoCsr), C.c_void_p, f64p, f64p, C.c_double, C.c_uint64, C.c_int,
                              C.c_uint64, f64p, C.c_uint64, u64p, C.POINTER(KoStats)]
+        L.ko_pcg_pipe.restype = C.c_int
+        L.ko_pcg_pipe.argtypes = [C.POINTER(KoCsr), C.c_void_p, f64p, f64p, C.c_double, C.c_uint64, C.c_int,
+                                  C.c_uint64, f64p, C.c_uint64, C.POINTER(C.c_uint64), C.POINTER(KoStats)]
         L.ko_pcg_sr.restype = C.c_int
         L.ko_pcg_sr.argtypes = [C.POINTER(KoCsr), C.c_void_p, f64p, f64p, C.c_double, C.c_uint64, C.c_int,
                              C.c_uint64, f64p, C.c_uint64, u64p, C.POINTER(KoStats)]
@@ -358,6 +361,18 @@ def pcg_sr(A, pc, b, x0, tol, max_iters, norm_type=1, nshards=1, hist_cap=0):
     hl = C.c_uint64(0)
     rc = lib().ko_pcg_sr(A.ptr(), _h(pc), _f(b), _f(x), tol, max_iters, norm_type, nshards,
                          _f(hist), hist_cap, C.byref(hl), C.byref(st))
+    return rc, x, st, hist[:min(int(hl.value), hist_cap)]
+
+
+def pcg_pipe(A, pc, b, x0, tol, max_iters, norm_type=1, nshards=1, hist_cap=0):
+    """Pipelined (Ghysels-Vanroose) PCG, SURVEY 8(f3)."""
+    b = _vec(b)
+    x = _vec(x0).copy()
+    st = KoStats()
+    hist = np.zeros(max(hist_cap, 1))
+    hl = C.c_uint64(0)
+    rc = lib().ko_pcg_pipe(A.ptr(), _h(pc), _f(b), _f(x), tol, max_iters, norm_type, nshards,
+                           _f(hist), hist_cap, C.byref(hl), C.byref(st))
     return rc, x, st, hist[:min(int(hl.value), hist_cap)]
 
 

@@ -93,6 +93,54 @@ def test_pcg_fused_single_reduction_bit_exact(ctx, kind, N, use_pc, norm):
         assert abs(int(sl.iterations) - int(st.iterations)) <= max(1, int(0.02 * sl.iterations))
 
 
+@pytest.mark.parametrize("kind,N", [("poisson2d", 16), ("poisson2d", 100), ("poisson3d", 24), ("varcoef27", 12)])
+@pytest.mark.parametrize("use_pc", [True, False])
+@pytest.mark.parametrize("norm", [0, 1, 2, 3])
+def test_pcg_pipelined_bit_exact(ctx, kind, N, use_pc, norm):
+    """pipelined (Ghysels-Vanroose) PCG vs the oracle's restatement: iterations, history and x bit for bit."""
+    import kryst_b200 as kb
+    A, Ao = _mk(kind, N, ctx)
+    b = o.spmv(Ao, np.ones(Ao.n))
+    pc = kb.Jacobi().setup(A) if use_pc else None
+    x = np.zeros(Ao.n)
+    s = kb.PcgSolver(1e-8, 300).with_norm(norm).with_pipelined()
+    st = s.solve(A, pc, b, x)
+    rc, xo, so, ho = o.pcg_pipe(Ao, o.OPc.jacobi(Ao) if use_pc else None, b, np.zeros(Ao.n), 1e-8, 300, norm_type=norm, hist_cap=301)
+    assert rc == 0
+    assert st.iterations == so.iterations and st.converged == bool(so.converged)
+    assert st.final_residual == so.final_residual
+    assert np.array_equal(x, xo)
+    assert np.array_equal(np.array(s.residual_history), ho)
+    if norm == 1 and so.iterations < 300:
+        rc, _, sl, _ = o.pcg(Ao, o.OPc.jacobi(Ao) if use_pc else None, b, np.zeros(Ao.n), 1e-8, 300)
+        assert abs(int(sl.iterations) - int(st.iterations)) <= max(1, int(0.02 * sl.iterations))
+
+
+def test_pcg_pipelined_edges(ctx):
+    import kryst_b200 as kb
+    A, Ao = _mk("poisson2d", 20, ctx)
+    b = o.spmv(Ao, np.ones(Ao.n))
+    x = np.full(Ao.n, 0.25)
+    st = kb.PcgSolver(1e-8, 0).with_pipelined().solve(A, None, b, x)
+    rc, xo, so, _ = o.pcg_pipe(Ao, None, b, np.full(Ao.n, 0.25), 1e-8, 0)
+    assert (st.iterations, st.converged, st.final_residual) == (0, False, so.final_residual) and np.array_equal(x, xo)
+    x = np.zeros(Ao.n)
+    st = kb.PcgSolver(1e-30, 7).with_pipelined().solve(A, None, b, x)
+    rc, xo, so, _ = o.pcg_pipe(Ao, None, b, np.zeros(Ao.n), 1e-30, 7)
+    assert (st.iterations, st.converged) == (7, True) == (so.iterations, bool(so.converged)) and np.array_equal(x, xo)
+    n, rp, ci, v = Ao.n, Ao.row_ptr, Ao.col_idx, -Ao.vals
+    An = kb.DeviceCsr.from_csr(n, n, rp, ci, v, ctx)
+    x = np.full(n, 3.0)
+    with pytest.raises(kb.IndefiniteMatrix):
+        kb.PcgSolver(1e-8, 50).with_pipelined().solve(An, None, b, x)
+    assert np.all(x == 3.0)
+    # solving again with the literal and the single-reduction recurrences on the same operator (separate graph caches)
+    x1, x2 = np.zeros(Ao.n), np.zeros(Ao.n)
+    kb.PcgSolver(1e-8, 300).solve(A, None, b, x1)
+    kb.PcgSolver(1e-8, 300).with_pipelined().solve(A, None, b, x2)
+    assert np.abs(x1 - x2).max() < 1e-6
+
+
 def test_pcg_fused_single_reduction_edges(ctx):
     import kryst_b200 as kb
     A, Ao = _mk("poisson2d", 20, ctx)
