@@ -379,7 +379,7 @@ void kb_csr_unref(kb_csr_s* A) {
     kb_gmres_ws_free(A->gmres_ws);
     kb_halo_free(A->halo);
     KB_FREE(A->row_ptr); KB_FREE(A->col); KB_FREE(A->vals); KB_FREE(A->ghosts);
-    KB_FREE(A->tile_chunk); KB_FREE(A->chunk_row); KB_FREE(A->chunk_nz); KB_FREE(A->tiles_interior); KB_FREE(A->tiles_boundary);
+    KB_FREE(A->tile_chunk); KB_FREE(A->chunk_row); KB_FREE(A->chunk_nz); KB_FREE(A->tiles_interior); KB_FREE(A->tiles_boundary); KB_FREE(A->tiles_order);
     KB_FREE(A->x_tmp); KB_FREE(A->y_tmp); KB_FREE(A->hist_buf);
     kb_ctx_s* c = A->ctx;
     delete A;

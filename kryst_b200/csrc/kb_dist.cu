@@ -594,6 +594,10 @@ int kb_csr_build_dist(kb_csr_s* A) {
             KB_TRY(kb_alloc(&A->tiles_interior, ti.size() + 1)); KB_TRY(kb_alloc(&A->tiles_boundary, tb.size() + 1));
             if (!ti.empty()) KB_CUDA(cudaMemcpyAsync(A->tiles_interior, ti.data(), ti.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
             if (!tb.empty()) KB_CUDA(cudaMemcpyAsync(A->tiles_boundary, tb.data(), tb.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+            std::vector<int> ord(ti);
+            ord.insert(ord.end(), tb.begin(), tb.end());
+            KB_TRY(kb_alloc(&A->tiles_order, ord.size() + 1));
+            KB_CUDA(cudaMemcpyAsync(A->tiles_order, ord.data(), ord.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
             KB_CUDA(cudaStreamSynchronize(c->stream));
         }
     }

@@ -35,6 +35,7 @@ struct kb_csr_s {
     int* tiles_interior = nullptr;   // tiles without ghost columns / with ghost columns (device lists)
     int* tiles_boundary = nullptr;
     int n_interior = 0, n_boundary = 0;
+    int* tiles_order = nullptr;      // interior tiles, then boundary tiles: the single-launch SpMV walks it so that only a CTA's LAST tiles wait for the halo
     // scratch for host-slice matvec
     double* x_tmp = nullptr;
     double* y_tmp = nullptr;

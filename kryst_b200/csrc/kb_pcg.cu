@@ -508,6 +508,7 @@ static int pcg_persistent(kb_csr_s* A, const kb_pc_s* pc, KbPcgWs* w) {
     if (!w->mega_bar) { KB_TRY(kb_alloc(&w->mega_bar, 4)); }
     KB_CUDA(cudaMemsetAsync(w->mega_bar, 0, 4 * sizeof(unsigned), c->stream));
     KbSpmvArgs a{};
+    a.lazy_from = -1;
     a.row_ptr = A->row_ptr; a.col = A->col; a.vals = A->vals; a.x = w->p; a.y = w->ap; a.b = nullptr; a.w = w->p;
     a.n = (int)A->n; a.tile0 = 0; a.ntiles_launch = A->ntiles; a.ntiles_total = A->ntiles; a.tile_list = nullptr; a.finalize = 0;
     a.partials = w->partials; a.pstride = w->pstride; a.ticket = c->ticket;

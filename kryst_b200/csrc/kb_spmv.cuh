@@ -45,15 +45,18 @@ struct KbSpmvArgs {
     const unsigned long long* hflags;   // flags[2][hsize]
     int hsize; unsigned hsrc_mask;
     unsigned* herr;
+    int lazy_from;                      // bulk kernel: >= 0 -> positions [lazy_from, ntiles_launch) of tile_list are the tiles with ghost columns;
+                                        // a CTA waits for the halo only when it reaches the first of them (interior rows hide the NVLink flight)
 };
 
 // Wait until every source rank has published exchange #seq; returns the ghost pointer biased by -n_loc, so
 // that xg[c] is the value of local column c >= n_loc.  All threads call it; the caller synchronises after.
+template <bool WAIT = true>
 __device__ __forceinline__ const double* kb_halo_wait(const KbSpmvArgs& a) {
     const unsigned long long seq = *reinterpret_cast<const volatile unsigned long long*>(a.hseq);
     const size_t par = (size_t)(seq & 1ull);
     const int tid = threadIdx.x;
-    if (tid < a.hsize && ((a.hsrc_mask >> tid) & 1u)) {
+    if (WAIT && tid < a.hsize && ((a.hsrc_mask >> tid) & 1u)) {
         const volatile unsigned long long* f = a.hflags + par * a.hsize + tid;
         unsigned spins = 0;
         while (*f < seq) { if (++spins > (1u << 25)) { atomicExch(a.herr, 1u); break; } }

@@ -147,8 +147,16 @@ __device__ __forceinline__ void kb_bulk_consume(const KbSpmvArgs& a, KbBulkSmem&
     constexpr int YS = WD ? 1 : 0;                      // slot of <y,y>
     const int tid = threadIdx.x;
     const int ntl = a.ntiles_launch;
+    bool halo_ready = !GH || a.lazy_from < 0;
     for (int ti = blockIdx.x; ti < ntl; ti += gridDim.x) {
         int tile = 0, last = 0;
+        if (GH) {
+            if (!halo_ready && ti >= a.lazy_from) {      // CTA-uniform: the first tile with ghost columns of this CTA
+                (void)kb_halo_wait<true>(a);
+                kb_bar_consumers();
+                halo_ready = true;
+            }
+        }
         do {
             const int s = it % KB_BULK_STAGES;
             const unsigned ph = (unsigned)(it / KB_BULK_STAGES) & 1u;
@@ -246,7 +254,7 @@ __global__ void __launch_bounds__(KB_BULK_THREADS, 2) kb_spmv_bulk(KbSpmvArgs a,
     kb_pdl_launch_dependents();
     if (epi.skip()) return;
     const double* xg = nullptr;
-    if (GH) xg = kb_halo_wait(a);          // ordered before the gathers by the __syncthreads() below
+    if (GH) xg = a.lazy_from >= 0 ? kb_halo_wait<false>(a) : kb_halo_wait<true>(a);      // ordered before the gathers by the __syncthreads() below; lazy: see kb_bulk_consume
     constexpr bool WD = Epi::WDOT, YD = Epi::YDOT;      // fused <w,y> and/or <y,y>
     constexpr int NDOT = (WD ? 1 : 0) + (YD ? 1 : 0);
     constexpr int ND = NDOT > 0 ? NDOT : 1;
