@@ -63,7 +63,7 @@ def test_trsv_schedules_bit_exact(ctx, kind, N, sched, monkeypatch):
 
 
 @pytest.mark.parametrize("rows", ["1", "2"])
-@pytest.mark.parametrize("group", ["1", "2"])
+@pytest.mark.parametrize("group", ["1", "2", "24"])
 @pytest.mark.parametrize("grid", ["3", "0"])
 def test_trsv_march_shapes(ctx, rows, group, grid, monkeypatch):
     """Pencil shapes (1 or 2 rows per lane), group shapes (1 or 2x2 pencils per CTA) and a capped grid: with few
