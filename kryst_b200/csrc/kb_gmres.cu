@@ -64,56 +64,9 @@ __global__ void __launch_bounds__(KB_THREADS) kb_gs_dot(KbGmresDev g, const doub
         partials[(size_t)c * pstride + blockIdx.x] = s;
     }
 }
-// Fused CGS sweep: w -= V h1 and, in the same pass over the basis tile (kept in registers), the partial sums
-// of h2 = V^T w_new.  Saves one full read of V per Arnoldi step (3 sweeps instead of 4); the arithmetic and
-// the reduction tree are exactly those of kb_gs_dot / GsUpdateOp, so results are unchanged bit for bit.
-template <int MAXC>
-__global__ void __launch_bounds__(KB_THREADS, 1) kb_gs_update_dot(KbGmresDev g, double* __restrict__ w, const double* __restrict__ hsrc, long long n,
-                                                                  double* partials, size_t pstride, int ncols) {
-    KbCtl* ctl = g.ctl;
-    if (ctl->done || ctl->cycle_break) return;
-    __shared__ double sm[MAXC * 8];
-    const int tid = threadIdx.x, lane = tid & 31, wp = tid >> 5;
-    const long long i = (long long)blockIdx.x * KB_TILE + 2 * tid;
-    const bool h0 = i < n, h1 = i + 1 < n;
-    double t0 = 0.0, t1 = 0.0;
-    if (h1) { double2 t = kb_ld2(w + i); t0 = t.x; t1 = t.y; }
-    else if (h0) t0 = w[i];
-    double2 v[MAXC];
-#pragma unroll
-    for (int c = 0; c < MAXC; ++c) {
-        v[c] = make_double2(0.0, 0.0);
-        if (c < ncols) {
-            const double* vc = g.V + (size_t)c * g.ld;
-            if (h1) v[c] = kb_ld2(vc + i);
-            else if (h0) v[c].x = vc[i];
-        }
-    }
-#pragma unroll
-    for (int c = 0; c < MAXC; ++c)
-        if (c < ncols) { const double h = hsrc[c]; t0 = t0 - v[c].x * h; t1 = t1 - v[c].y * h; }
-    if (h1) kb_st2(w + i, make_double2(t0, t1));
-    else if (h0) w[i] = t0;
-#pragma unroll
-    for (int c = 0; c < MAXC; ++c)
-        if (c < ncols) {
-            double e0 = 0.0, e1 = 0.0;
-            if (h1) { e0 = v[c].x * t0; e1 = v[c].y * t1; }
-            else if (h0) e0 = v[c].x * t0;
-            double r = kb_warp_butterfly(e0 + e1);
-            if (lane == 0) sm[c * 8 + wp] = r;
-        }
-    __syncthreads();
-    for (int c = tid; c < ncols; c += KB_THREADS) {
-        double s = sm[c * 8];
-#pragma unroll
-        for (int k = 1; k < 8; ++k) s = s + sm[c * 8 + k];
-        partials[(size_t)c * pstride + blockIdx.x] = s;
-    }
-}
 // ---- CGS2 sweep 2 as ONE pass over the basis: w -= V h1 and the tile sums of h2 = V^T w_new ----------------------
-// (north_star kernel 3 / SURVEY K6 "update_dotV".)  The register-tile kernel above cannot overlap its loads with its
-// arithmetic (1 CTA/SM, every warp in the same phase); a first shared-memory version staged half tiles with one bulk copy
+// (north_star kernel 3 / SURVEY K6 "update_dotV".)  A register-tile version could not overlap its loads with its
+// arithmetic (1 CTA/SM, every warp in the same phase; removed); a first shared-memory version staged half tiles with one bulk copy
 // per 2-KB column slice and paid more for ~32 bulk-copy issues per stage than for the stage's HBM time (0.89 ms per
 // sweep against 0.34 + 0.37 ms for the two plain sweeps).  This version stages with cp.async instead:
 //   * thread l of a 128-thread team owns rows 2l, 2l+1 of a HALF tile (256 rows = canonical lanes) and copies exactly
@@ -603,14 +556,10 @@ static int gm_inner_iteration(GmPlan& P, int j) {
     KbCtl* ctl = w->ctl;
     double* vj = w->V + (size_t)j * w->ld;
     const int ncols = j + 1;
-    // 3-sweep variant (update fused with the next dot) is opt-in: with the basis tile in registers it runs at
-    // 1 CTA/SM and measured slower on B200 than the two separate bandwidth-bound sweeps (C4g: 191 vs 207 it/s)
-    static const bool fuse_env = getenv("KB_GS_FUSE") && atoi(getenv("KB_GS_FUSE")) == 1;
-    const bool fuse = fuse_env && ncols <= 32;      // the basis tile must fit in registers
     // default: the shared-memory-staged 3-sweep CGS2 (kb_gs_fused, cp.async ring): measured on B200 (C4g) one fused sweep
     // costs 0.58 ms against 0.34 + 0.37 ms for the separate dot and update sweeps it replaces (291 -> 309 it/s).
-    // KB_GS_FUSE=0 selects the 4-sweep form, KB_GS_FUSE=1 the register-tile variant.
-    static const bool fuse_smem_env = !getenv("KB_GS_FUSE") || atoi(getenv("KB_GS_FUSE")) == 2;
+    // KB_GS_FUSE=0 selects the 4-sweep form.
+    static const bool fuse_smem_env = !getenv("KB_GS_FUSE") || atoi(getenv("KB_GS_FUSE")) != 0;
     const bool fuse_smem = fuse_smem_env && !P.g.flex && kb_gsf_stages(ncols) >= 2;
     typedef KbSpmvEpi<GmNoFin, false, false> Epi;
     Epi epi; epi.ctl = ctl; epi.skip_mask = 2; epi.fin = kb_make_fin(c, GmNoFin{}, false, nullptr, 0);
@@ -672,17 +621,13 @@ static int gm_inner_iteration(GmPlan& P, int j) {
             const int per_sm = sh <= 110 * 1024 ? 2 : 1;
             kfn<<<std::min(per_sm * c->sm_count, A->ntiles), KB_GSF_THREADS, sh, c->stream>>>(P.g, w->w, P.g.h1src, (int)A->n, A->ntiles, w->partials, w->pstride, ncols);
             KB_CUDA(cudaGetLastError());
-        } else if (fuse) {   // w -= V h1 fused with the partial sums of h2 = V^T w (basis tile in registers)
-            KbLaunch L(c, KB_K_GS_UPDATE);
-            kb_gs_update_dot<32><<<A->ntiles, KB_THREADS, 0, c->stream>>>(P.g, w->w, P.g.h1src, (long long)A->n, w->partials, w->pstride, ncols);
-            KB_CUDA(cudaGetLastError());
         } else {
             GsUpdateOp<false> op; op.partials = nullptr; op.pstride = 0; op.g = P.g; op.w = w->w; op.hsrc = P.g.h1src; op.slots = nullptr; op.ncols = ncols; op.p2p = nullptr;
             KB_TRY(gm_tile(A, op, KB_K_GS_UPDATE));
         }
     }
     {   // h2 = V^T w ; w -= V h2 fused with ||w||^2 ; Arnoldi epilogue (H column, Givens, stop test)
-        if (!fuse && !fuse_smem) { KbLaunch L(c, KB_K_GS_DOT); kb_gs_dot<<<A->ntiles, KB_THREADS, 0, c->stream>>>(P.g, w->w, (long long)A->n, w->partials, w->pstride, ncols); }
+        if (!fuse_smem) { KbLaunch L(c, KB_K_GS_DOT); kb_gs_dot<<<A->ntiles, KB_THREADS, 0, c->stream>>>(P.g, w->w, (long long)A->n, w->partials, w->pstride, ncols); }
         double* s2 = w->slots + (KB_MAX_RESTART + 8);
         double* dst = P.dist ? s2 : &ctl->h2[0];
         { KbLaunch L(c, KB_K_SMALL); kb_gs_level2<<<ncols, KB_THREADS, 0, c->stream>>>(ctl, w->partials, w->pstride, A->ntiles, dst); }

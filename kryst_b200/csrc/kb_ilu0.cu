@@ -341,7 +341,6 @@ int kb_tiles_build(kb_pc_s* pc, unsigned* d_err, KbTileSolve** out);
 int kb_tiles_apply(kb_pc_s* pc, KbTileSolve* t, const double* d_r, double* d_z, const KbCtl* skip_ctl, int skip_mask);
 void kb_tiles_free(KbTileSolve* t);
 void kb_tiles_grid(const KbTileSolve* t, int* nx, int* ny, int* nz);
-int kb_tiles_trace_get(KbTileSolve* t, unsigned long long* out, int* tx, int* ty, int* tz);
 struct KbLean;                                       // kb_trsv_lean.cu: warp-specialised pencil march (full-stencil box grids; the default)
 int kb_lean_build(kb_pc_s* pc, int gx, int gy, int gz, unsigned* d_err, KbLean** out);
 int kb_lean_apply(kb_pc_s* pc, KbLean* m, const double* d_r, double* d_z, const KbCtl* skip_ctl, int skip_mask);
@@ -712,10 +711,3 @@ extern "C" int kb_debug_march_trace(kb_pc pc, unsigned long long* out, int* px, 
     return kb_lean_trace_get(x->lean, out, px, py);
 }
 
-extern "C" int kb_debug_tiles_trace(kb_pc pc, unsigned long long* out, int* tx, int* ty, int* tz) {
-    KbIluExtra* x = pc && pc->kind == KB_PC_ILU0 ? extra_of(pc) : nullptr;
-    if (!x || !x->tiles) return 0;
-    cudaSetDevice(pc->ctx->device);
-    cudaStreamSynchronize(pc->ctx->stream);
-    return kb_tiles_trace_get(x->tiles, out, tx, ty, tz);
-}

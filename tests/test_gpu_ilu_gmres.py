@@ -38,7 +38,7 @@ def test_ilu0_factors_levels_apply_bit_exact(ctx, kind, N):
     assert np.array_equal(z, o.ilu0_apply(Ao, lu_o, dp_o, iud_o, r))
 
 
-@pytest.mark.parametrize("sched", ["levels", "tiles", "tiles_packets", "tiles_commwarp", "march"])
+@pytest.mark.parametrize("sched", ["levels", "tiles", "march"])
 @pytest.mark.parametrize("kind,N", [("convdiff2d", 70), ("poisson2d", 130), ("poisson3d", 20), ("convdiff3d", 17), ("varcoef27", 10),
                                     ("poisson3d", 41), ("convdiff2d", 201)])
 def test_trsv_schedules_bit_exact(ctx, kind, N, sched, monkeypatch):
@@ -49,8 +49,6 @@ def test_trsv_schedules_bit_exact(ctx, kind, N, sched, monkeypatch):
     import kryst_b200 as kb
     A, Ao = _mk(kind, N, ctx)
     monkeypatch.setenv("KB_TRSV_TILES", "0" if sched == "levels" else "1")
-    # 3-D hand-off between tiles: release-acquire flags (default) / tagged packets at tile granularity / packets + communication warp
-    monkeypatch.setenv("KB_TILES_LL", {"tiles_packets": "2", "tiles_commwarp": "1"}.get(sched, "0"))
     monkeypatch.setenv("KB_TRSV_MARCH", "1" if sched == "march" else "0")      # 1 forces the march on 3-D grids too
     pc = kb.Ilu0().setup(A)
     st, lu_o, dp_o, iud_o, bad = o.ilu0_factor(Ao)
