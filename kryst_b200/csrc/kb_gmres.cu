@@ -193,6 +193,9 @@ static int kb_gsf_stages(int ncols) {
     const size_t stage = (size_t)(ncols + 1) * KB_GSF_ROWS * sizeof(double);
     if (ncols > KB_GSF_MAXC) return 0;
     const size_t half_sm = 110 * 1024, full_sm = 225 * 1024;
+    // the kernel is issue-latency bound at 4 warps per CTA: prefer MORE resident CTAs (two stages each) over deeper rings
+    static const int occ_env = getenv("KB_GSF_OCC") ? atoi(getenv("KB_GSF_OCC")) : 1;
+    if (occ_env && 3 * (2 * stage + head + 1024) <= full_sm + 2048) return 2;
     if (2 * stage + head <= half_sm) { const size_t k = (half_sm - head) / stage; return (int)(k > 4 ? 4 : k); }
     const size_t k = (full_sm - head) / stage;
     return k < 2 ? 0 : (int)(k > KB_GSF_MAX_STAGES ? KB_GSF_MAX_STAGES : k);
@@ -618,7 +621,7 @@ static int gm_inner_iteration(GmPlan& P, int j) {
             }
             KbLaunch L(c, KB_K_GS_UPDATE);
             const size_t sh = kb_gsf_smem(ncols, nst);
-            const int per_sm = sh <= 110 * 1024 ? 2 : 1;
+            const int per_sm = std::max(1, std::min(6, (int)((227 * 1024) / (sh + 1024))));
             kfn<<<std::min(per_sm * c->sm_count, A->ntiles), KB_GSF_THREADS, sh, c->stream>>>(P.g, w->w, P.g.h1src, (int)A->n, A->ntiles, w->partials, w->pstride, ncols);
             KB_CUDA(cudaGetLastError());
         } else {
