@@ -97,6 +97,49 @@ __device__ __forceinline__ void kb_gsf_cp16(void* smem_dst, const void* gsrc) {
 template <int N>
 __device__ __forceinline__ void kb_gsf_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
+// Products of W consecutive basis columns with this thread's two updated rows, reduced over the warp: returns, in lane l, the
+// warp sum of column g0 + (l & (W-1)).  log2(32/W) plain xor-butterfly rounds over all W columns, then the transposed rounds
+// (a lane keeps half of its columns and trades the other half with its xor partner): every addition pairs the same two lanes'
+// values as the canonical 16-8-4-2-1 butterfly, so the sums are bit-identical to kb_gs_dot's whatever W is.  W is chosen from
+// the number of columns left, so that short bases do not pay for 32 columns.
+template <int W>
+__device__ __forceinline__ double kb_gsf_group(const double* st, int g0, int ncols, bool h0, bool h1, double t0, double t1, int lane) {
+    double x[W];
+    if (h1) {                 // both rows exist (every thread but the tail of the last tile)
+#pragma unroll
+        for (int k = 0; k < W; ++k) {
+            x[k] = 0.0;
+            if (g0 + k < ncols) {         // warp-uniform
+                const double2 v = *reinterpret_cast<const double2*>(st + (size_t)(g0 + k + 1) * KB_GSF_ROWS);
+                x[k] = v.x * t0 + v.y * t1;
+            }
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < W; ++k) {
+            double e0 = 0.0;
+            if (g0 + k < ncols && h0) e0 = st[(size_t)(g0 + k + 1) * KB_GSF_ROWS] * t0;
+            x[k] = e0 + 0.0;
+        }
+    }
+#pragma unroll
+    for (int off = 16; off >= W; off >>= 1) {
+#pragma unroll
+        for (int k = 0; k < W; ++k) x[k] = x[k] + __shfl_xor_sync(0xffffffffu, x[k], off);
+    }
+#pragma unroll
+    for (int off = W / 2; off >= 1; off >>= 1) {
+        const bool hi = (lane & off) != 0;
+#pragma unroll
+        for (int k = 0; k < off; ++k) {
+            const double send = hi ? x[k] : x[k + off];
+            const double keep = hi ? x[k + off] : x[k];
+            x[k] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+        }
+    }
+    return x[0];
+}
+
 template <int NST>
 __global__ void __launch_bounds__(KB_GSF_THREADS) kb_gs_fused(KbGmresDev g, double* __restrict__ w, const double* __restrict__ hsrc, int n, int ntiles,
                                                                 double* partials, size_t pstride, int ncols) {
@@ -146,30 +189,22 @@ __global__ void __launch_bounds__(KB_GSF_THREADS) kb_gs_fused(KbGmresDev g, doub
         }
         if (h1) kb_st2(w + i, make_double2(t0, t1));
         else if (h0) w[i] = t0;
-        // phase 2: products for every column, transposed butterfly per group of 32 columns
-        for (int g0 = 0; g0 < ncols; g0 += 32) {
-            double x[32];
-#pragma unroll
-            for (int k = 0; k < 32; ++k) {
-                double e0 = 0.0, e1 = 0.0;
-                if (g0 + k < ncols && h0) {
-                    const double2 v = *reinterpret_cast<const double2*>(st + (size_t)(g0 + k + 1) * KB_GSF_ROWS);
-                    if (h1) { e0 = v.x * t0; e1 = v.y * t1; }
-                    else e0 = v.x * t0;
-                }
-                x[k] = e0 + e1;
+        // phase 2: products for every column, transposed butterfly per group of 32 / 16 / 8 columns
+        for (int g0 = 0; g0 < ncols;) {
+            const int rem = ncols - g0;
+            if (rem > 24) {
+                const double v = kb_gsf_group<32>(st, g0, ncols, h0, h1, t0, t1, lane);
+                if (g0 + lane < ncols) H.wsum[team][(g0 + lane) * 8 + half * 4 + wp] = v;
+                g0 += 32;
+            } else if (rem > 8) {
+                const double v = kb_gsf_group<16>(st, g0, ncols, h0, h1, t0, t1, lane);
+                if (lane < 16 && g0 + lane < ncols) H.wsum[team][(g0 + lane) * 8 + half * 4 + wp] = v;
+                g0 += 16;
+            } else {
+                const double v = kb_gsf_group<8>(st, g0, ncols, h0, h1, t0, t1, lane);
+                if (lane < 8 && g0 + lane < ncols) H.wsum[team][(g0 + lane) * 8 + half * 4 + wp] = v;
+                g0 += 8;
             }
-#pragma unroll
-            for (int off = 16; off >= 1; off >>= 1) {
-                const bool hi = (lane & off) != 0;
-#pragma unroll
-                for (int k = 0; k < off; ++k) {
-                    const double send = hi ? x[k] : x[k + off];
-                    const double keep = hi ? x[k + off] : x[k];
-                    x[k] = keep + __shfl_xor_sync(0xffffffffu, send, off);
-                }
-            }
-            if (g0 + lane < ncols) H.wsum[team][(g0 + lane) * 8 + half * 4 + wp] = x[0];
         }
         if (half == 1) {
             asm volatile("bar.sync %0, %1;" ::"r"(1 + team), "n"(KB_GSF_TEAM) : "memory");
