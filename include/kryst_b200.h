@@ -110,6 +110,7 @@ int kb_csr_matvec_device(kb_csr a, const double* d_x, double* d_y); /* device po
 uint64_t kb_csr_num_ghosts(kb_csr a);
 int kb_csr_get_ghosts(kb_csr a, uint64_t* ghosts_global);
 int kb_csr_spmv_kernel_kind(kb_csr a);                 /* 0 = CSR-stream (thread/row from smem), 1 = vector-per-row, 2 = bulk-async staged */
+int kb_csr_spmv_x_staged(kb_csr a);                    /* kind 2 only: non-zero when x tiles are staged in shared memory too (stage geometry + 1) */
 /* SubmatrixExtract::submatrix(&self, indices) (src/core/traits.rs; impl src/matrix/sparse.rs:72-93), the call
  * AdditiveSchwarz::setup makes per subdomain (src/preconditioner/asm.rs:58-65): out[i][j] = a[indices[i]][indices[j]]
  * for any index order (repeats allowed), stored zeros dropped, built on the device.  Single-GPU operators only.   */

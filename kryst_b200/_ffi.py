@@ -67,6 +67,7 @@ SIGNATURES = {
     "kb_csr_num_ghosts": (C.c_uint64, [C.c_void_p]),
     "kb_csr_get_ghosts": (C.c_int, [C.c_void_p, u64p]),
     "kb_csr_spmv_kernel_kind": (C.c_int, [C.c_void_p]),
+    "kb_csr_spmv_x_staged": (C.c_int, [C.c_void_p]),
     "kb_csr_submatrix": (C.c_int, [C.c_void_p, u64p, C.c_uint64, C.POINTER(C.c_void_p)]),
     "kb_csr_download": (C.c_int, [C.c_void_p, u64p, u64p, f64p]),
     "kb_dot": (C.c_int, [C.c_void_p, C.c_uint64, f64p, f64p, f64p]),

@@ -313,6 +313,10 @@ class DeviceCsr:
     def spmv_kernel_kind(self):
         return int(_ffi.lib().kb_csr_spmv_kernel_kind(self._h))
 
+    def spmv_x_staged(self):
+        """Non-zero when the SpMV stages the x tiles of every chunk in shared memory (kb_spmv_xtile.cuh)."""
+        return int(_ffi.lib().kb_csr_spmv_x_staged(self._h))
+
     def ghosts(self):
         n = int(_ffi.lib().kb_csr_num_ghosts(self._h))
         g = np.zeros(n, dtype=np.uint64)

@@ -247,6 +247,64 @@ static int build_chunk_table(kb_csr_s* A) {
     return KB_OK;
 }
 
+// x-staging tables of kb_spmv_xtile (kb_spmv_xtile.cuh): a second chunk table, the x intervals of every chunk and the
+// chunk-local 16-bit column ids.  All or nothing: if one chunk does not fit, the operator keeps kb_spmv_bulk.
+// KB_SPMV_XTILE = 0 never, 1 whenever the chunks fit, 2 (default) only for long rows (the product-phase operators,
+// where the gather is the limiter); KB_XT_CFG = 0 | 1 selects the stage geometry.
+static void free_xt_table(kb_csr_s* A) {
+    A->xt = 0; A->xt_nchunks = 0;
+    KB_FREE(A->xt_tile_chunk); KB_FREE(A->xt_chunk_row); KB_FREE(A->xt_chunk_nz);
+    KB_FREE(A->xt_lo); KB_FREE(A->xt_len); KB_FREE(A->xt_tail); KB_FREE(A->xt_lcol);
+}
+static int build_xt_table(kb_csr_s* A) {
+    kb_ctx_s* c = A->ctx;
+    const int mode = getenv("KB_SPMV_XTILE") ? atoi(getenv("KB_SPMV_XTILE")) : KB_XT_DEFAULT_MODE;
+    if (mode <= 0 || A->kind != 2 || A->dist || A->n == 0 || A->nnz == 0) return KB_OK;
+    if (mode >= 2 && !A->prod) return KB_OK;
+    const int cfg = getenv("KB_XT_CFG") ? (atoi(getenv("KB_XT_CFG")) != 0 ? 1 : 0) : KB_XT_DEFAULT_CFG;
+    const int cap = cfg ? KbXtCfg<1>::CAP : KbXtCfg<0>::CAP;
+    const int xcap = cfg ? KbXtCfg<1>::XCAP : KbXtCfg<0>::XCAP;
+    const int maxrows = cfg ? KbXtCfg<1>::MAXROWS : KbXtCfg<0>::MAXROWS;
+    if (A->max_row_len > (uint64_t)cap) return KB_OK;
+    const int nt = A->ntiles;
+    int st = KB_OK;
+    int* d_fail = nullptr;
+    do {
+        if ((st = kb_alloc(&A->xt_tile_chunk, (size_t)nt + 1)) != KB_OK) break;
+        { KbLaunch L(c, KB_K_OTHER); kb_xt_chunk_build<<<(nt + 127) / 128, 128, 0, c->stream>>>(A->row_ptr, (int)A->n, nt, cap, maxrows, A->xt_tile_chunk, nullptr, nullptr, 0); }
+        std::vector<int> cnt((size_t)nt + 1, 0);
+        if (cudaMemcpyAsync(cnt.data(), A->xt_tile_chunk, nt * sizeof(int), cudaMemcpyDeviceToHost, c->stream) != cudaSuccess ||
+            cudaStreamSynchronize(c->stream) != cudaSuccess) { kb_set_error("x-tile chunk count failed: %s", cudaGetErrorString(cudaGetLastError())); st = KB_SOLVE_ERROR; break; }
+        int acc = 0;
+        for (int t = 0; t < nt; ++t) { int k = cnt[t]; cnt[t] = acc; acc += k; }
+        cnt[nt] = acc;
+        A->xt_nchunks = acc;
+        if (cudaMemcpyAsync(A->xt_tile_chunk, cnt.data(), ((size_t)nt + 1) * sizeof(int), cudaMemcpyHostToDevice, c->stream) != cudaSuccess) { st = KB_SOLVE_ERROR; break; }
+        if ((st = kb_alloc(&A->xt_chunk_row, (size_t)acc + 1)) != KB_OK) break;
+        if ((st = kb_alloc(&A->xt_chunk_nz, (size_t)acc + 1)) != KB_OK) break;
+        if ((st = kb_alloc(&A->xt_lo, (size_t)acc * KB_XT_KMAX)) != KB_OK) break;
+        if ((st = kb_alloc(&A->xt_len, (size_t)acc * KB_XT_KMAX)) != KB_OK) break;
+        if ((st = kb_alloc(&A->xt_tail, (size_t)acc)) != KB_OK) break;
+        if ((st = kb_alloc(&A->xt_lcol, (size_t)A->nnz + 16)) != KB_OK) break;
+        if ((st = kb_alloc(&d_fail, 1)) != KB_OK) break;
+        cudaMemsetAsync(d_fail, 0, sizeof(int), c->stream);
+        cudaMemsetAsync(A->xt_lcol + A->nnz, 0, 16 * sizeof(unsigned short), c->stream);
+        { KbLaunch L(c, KB_K_OTHER); kb_xt_chunk_build<<<(nt + 127) / 128, 128, 0, c->stream>>>(A->row_ptr, (int)A->n, nt, cap, maxrows, A->xt_tile_chunk, A->xt_chunk_row, A->xt_chunk_nz, 1); }
+        {
+            KbLaunch L(c, KB_K_OTHER);
+            if (cfg) kb_xt_build<KbXtCfg<1>::CAP><<<acc, KB_THREADS, 0, c->stream>>>(A->col, A->xt_chunk_nz, (int)A->ncols_local, xcap, A->xt_lo, A->xt_len, A->xt_tail, A->xt_lcol, d_fail);
+            else kb_xt_build<KbXtCfg<0>::CAP><<<acc, KB_THREADS, 0, c->stream>>>(A->col, A->xt_chunk_nz, (int)A->ncols_local, xcap, A->xt_lo, A->xt_len, A->xt_tail, A->xt_lcol, d_fail);
+        }
+        int fail = 0;
+        if (cudaMemcpyAsync(&fail, d_fail, sizeof(int), cudaMemcpyDeviceToHost, c->stream) != cudaSuccess ||
+            cudaStreamSynchronize(c->stream) != cudaSuccess) { kb_set_error("x-tile table build failed: %s", cudaGetErrorString(cudaGetLastError())); st = KB_SOLVE_ERROR; break; }
+        if (!fail) { A->xt = cfg + 1; }
+    } while (0);
+    if (d_fail) cudaFree(d_fail);
+    if (st != KB_OK || !A->xt) free_xt_table(A);
+    return st;
+}
+
 // allocate the device arrays of an operator (padded tails zeroed); the caller fills row_ptr / col / vals
 int kb_csr_alloc(kb_ctx c, uint64_t nrows, uint64_t ncols_global, uint64_t nnz, kb_csr_s** out) {
     *out = nullptr;
@@ -314,6 +372,7 @@ int kb_csr_finalize(kb_csr_s* A, const int* d_err) {
         }
         if (A->dist && (st = kb_csr_build_dist(A)) != KB_OK) break;
         if (A->kind == 0 && nrows && (st = build_chunk_table(A)) != KB_OK) break;
+        if (A->kind == 2 && (st = build_xt_table(A)) != KB_OK) break;
     } while (0);
     if (d_stats) cudaFree(d_stats);
     return st;
@@ -379,6 +438,7 @@ void kb_csr_unref(kb_csr_s* A) {
     kb_gmres_ws_free(A->gmres_ws);
     kb_halo_free(A->halo);
     KB_FREE(A->row_ptr); KB_FREE(A->col); KB_FREE(A->vals); KB_FREE(A->ghosts);
+    free_xt_table(A);
     KB_FREE(A->tile_chunk); KB_FREE(A->chunk_row); KB_FREE(A->chunk_nz); KB_FREE(A->tiles_interior); KB_FREE(A->tiles_boundary); KB_FREE(A->tiles_order);
     KB_FREE(A->x_tmp); KB_FREE(A->y_tmp); KB_FREE(A->hist_buf);
     kb_ctx_s* c = A->ctx;
@@ -389,6 +449,7 @@ extern "C" uint64_t kb_csr_nrows(kb_csr A) { return A->n; }
 extern "C" uint64_t kb_csr_ncols(kb_csr A) { return A->ncols_global; }
 extern "C" uint64_t kb_csr_nnz(kb_csr A) { return A->nnz; }
 extern "C" int kb_csr_spmv_kernel_kind(kb_csr A) { return A->kind; }
+extern "C" int kb_csr_spmv_x_staged(kb_csr A) { return A->xt; }
 extern "C" uint64_t kb_csr_num_ghosts(kb_csr A) { return A->nghost; }
 extern "C" int kb_csr_get_ghosts(kb_csr A, uint64_t* out) {
     if (A->nghost == 0) return KB_OK;

@@ -11,6 +11,7 @@
 #include "kb_objects.h"
 #include "kb_spmv.cuh"
 #include "kb_spmv_bulk.cuh"
+#include "kb_spmv_xtile.cuh"
 #include "kb_p2p.cuh"
 
 struct KbSpmvArgs;
@@ -91,12 +92,36 @@ static int kb_finish_dist(kb_ctx_s* c, Fin fin, KbCtl* ctl, double* slots, int n
     return KB_OK;
 }
 
+template <class Epi, bool RESID, int CFG>
+static int kb_launch_spmv_xtile(kb_csr_s* A, const KbSpmvArgs& a, Epi epi, int count, bool pdl) {
+    kb_ctx_s* c = A->ctx;
+    using S = KbXtSmem<KbXtCfg<CFG>>;
+    static_assert(sizeof(S) <= 112 * 1024, "two CTAs per SM");
+    auto kfn = A->prod ? kb_spmv_xtile<Epi, RESID, true, CFG> : kb_spmv_xtile<Epi, RESID, false, CFG>;
+    if (!c->configured.count((const void*)kfn)) {
+        KB_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(S)));
+        c->configured.insert((const void*)kfn);
+    }
+    KbXtTable tb{A->xt_tile_chunk, A->xt_chunk_row, A->xt_chunk_nz, A->xt_lo, A->xt_len, A->xt_tail, A->xt_lcol, (int)A->ncols_local - 1};
+    const int grid = std::min(2 * c->sm_count, count);
+    KbLaunch L(c, KB_K_SPMV);
+    KB_CUDA(kb_launch_ex(pdl && kb_pdl_enabled(), kfn, dim3(grid), dim3(KB_BULK_THREADS), sizeof(S), c->stream, a, tb, epi));
+    return KB_OK;
+}
+
 // one launch over a set of canonical tiles (all tiles when list == nullptr); dispatches on the kernel kind
 template <class Epi, bool RESID, bool GH>
 static int kb_launch_spmv_tiles(kb_csr_s* A, KbSpmvArgs a, Epi epi, const int* list, int count, int finalize, bool pdl = false) {
     if (count <= 0) return KB_OK;
     kb_ctx_s* c = A->ctx;
     a.tile_list = list; a.tile0 = 0; a.ntiles_launch = count; a.finalize = finalize;
+    if constexpr (!GH) {
+        // x staged in shared memory (operators whose chunks fit, 16-byte aligned operand; no ghost columns)
+        if (A->kind == 2 && A->xt && (reinterpret_cast<uintptr_t>(a.x) & 15u) == 0) {
+            if (A->xt == 1) return kb_launch_spmv_xtile<Epi, RESID, 0>(A, a, epi, count, pdl);
+            return kb_launch_spmv_xtile<Epi, RESID, 1>(A, a, epi, count, pdl);
+        }
+    }
     if (A->kind == 2) {
         auto kfn = A->prod ? kb_spmv_bulk<Epi, RESID, GH, true> : kb_spmv_bulk<Epi, RESID, GH, false>;
         if (!c->configured.count((const void*)kfn)) {

@@ -24,6 +24,16 @@ struct kb_csr_s {
     int* chunk_nz = nullptr;
     int nchunks = 0;
     bool prod = false;           // kind 2: per-nonzero product phase (long rows) instead of per-row gathers
+    // kind 2 with the x operand staged in shared memory (kb_spmv_xtile.cuh): 0 = off, else configuration + 1
+    int xt = 0;
+    int* xt_tile_chunk = nullptr;
+    int* xt_chunk_row = nullptr;
+    int* xt_chunk_nz = nullptr;
+    int* xt_lo = nullptr;        // [xt_nchunks * 16] x intervals of each chunk
+    int* xt_len = nullptr;
+    int* xt_tail = nullptr;
+    unsigned short* xt_lcol = nullptr;   // [nnz + 16] chunk-local 16-bit column ids
+    int xt_nchunks = 0;
     int vec = 8;                 // sub-warp width of the vector kernel
     uint64_t max_row_len = 0;
     uint64_t hist[6] = {0, 0, 0, 0, 0, 0};   // row-length histogram: <=8,<=16,<=32,<=64,<=128,>128
