@@ -261,10 +261,12 @@ static int build_xt_table(kb_csr_s* A) {
     const int mode = getenv("KB_SPMV_XTILE") ? atoi(getenv("KB_SPMV_XTILE")) : KB_XT_DEFAULT_MODE;
     if (mode <= 0 || A->kind != 2 || A->dist || A->n == 0 || A->nnz == 0) return KB_OK;
     if (mode >= 2 && !A->prod) return KB_OK;
-    const int cfg = getenv("KB_XT_CFG") ? (atoi(getenv("KB_XT_CFG")) != 0 ? 1 : 0) : KB_XT_DEFAULT_CFG;
-    const int cap = cfg ? KbXtCfg<1>::CAP : KbXtCfg<0>::CAP;
-    const int xcap = cfg ? KbXtCfg<1>::XCAP : KbXtCfg<0>::XCAP;
-    const int maxrows = cfg ? KbXtCfg<1>::MAXROWS : KbXtCfg<0>::MAXROWS;
+    int cfg = getenv("KB_XT_CFG") ? atoi(getenv("KB_XT_CFG")) : KB_XT_DEFAULT_CFG;
+    if (cfg < 0 || cfg >= KB_XT_NCFG) cfg = KB_XT_DEFAULT_CFG;
+    static const int caps[KB_XT_NCFG] = {KbXtCfg<0>::CAP, KbXtCfg<1>::CAP, KbXtCfg<2>::CAP, KbXtCfg<3>::CAP};
+    static const int xcaps[KB_XT_NCFG] = {KbXtCfg<0>::XCAP, KbXtCfg<1>::XCAP, KbXtCfg<2>::XCAP, KbXtCfg<3>::XCAP};
+    static const int mrows[KB_XT_NCFG] = {KbXtCfg<0>::MAXROWS, KbXtCfg<1>::MAXROWS, KbXtCfg<2>::MAXROWS, KbXtCfg<3>::MAXROWS};
+    const int cap = caps[cfg], xcap = xcaps[cfg], maxrows = mrows[cfg];
     if (A->max_row_len > (uint64_t)cap) return KB_OK;
     const int nt = A->ntiles;
     int st = KB_OK;
@@ -292,8 +294,9 @@ static int build_xt_table(kb_csr_s* A) {
         { KbLaunch L(c, KB_K_OTHER); kb_xt_chunk_build<<<(nt + 127) / 128, 128, 0, c->stream>>>(A->row_ptr, (int)A->n, nt, cap, maxrows, A->xt_tile_chunk, A->xt_chunk_row, A->xt_chunk_nz, 1); }
         {
             KbLaunch L(c, KB_K_OTHER);
-            if (cfg) kb_xt_build<KbXtCfg<1>::CAP><<<acc, KB_THREADS, 0, c->stream>>>(A->col, A->xt_chunk_nz, (int)A->ncols_local, xcap, A->xt_lo, A->xt_len, A->xt_tail, A->xt_lcol, d_fail);
-            else kb_xt_build<KbXtCfg<0>::CAP><<<acc, KB_THREADS, 0, c->stream>>>(A->col, A->xt_chunk_nz, (int)A->ncols_local, xcap, A->xt_lo, A->xt_len, A->xt_tail, A->xt_lcol, d_fail);
+            if (cap == 2048) kb_xt_build<2048><<<acc, KB_THREADS, 0, c->stream>>>(A->col, A->xt_chunk_nz, (int)A->ncols_local, xcap, A->xt_lo, A->xt_len, A->xt_tail, A->xt_lcol, d_fail);
+            else if (cap == 3072) kb_xt_build<3072><<<acc, KB_THREADS, 0, c->stream>>>(A->col, A->xt_chunk_nz, (int)A->ncols_local, xcap, A->xt_lo, A->xt_len, A->xt_tail, A->xt_lcol, d_fail);
+            else kb_xt_build<3584><<<acc, KB_THREADS, 0, c->stream>>>(A->col, A->xt_chunk_nz, (int)A->ncols_local, xcap, A->xt_lo, A->xt_len, A->xt_tail, A->xt_lcol, d_fail);
         }
         int fail = 0;
         if (cudaMemcpyAsync(&fail, d_fail, sizeof(int), cudaMemcpyDeviceToHost, c->stream) != cudaSuccess ||

@@ -17,16 +17,19 @@
 
 #define KB_XT_KMAX 16          // x intervals per chunk
 #ifndef KB_XT_DEFAULT_MODE
-#define KB_XT_DEFAULT_MODE 0   // KB_SPMV_XTILE when the environment does not say (0 off, 1 whenever it fits, 2 long rows only)
+#define KB_XT_DEFAULT_MODE 2   // KB_SPMV_XTILE when the environment does not say (0 off, 1 whenever it fits, 2 long rows only)
 #endif
 #ifndef KB_XT_DEFAULT_CFG
-#define KB_XT_DEFAULT_CFG 1
+#define KB_XT_DEFAULT_CFG 0
 #endif
 #define KB_XT_GAP 4            // merge intervals whose gap is <= 4 aligned pairs (8 columns)
 
 template <int CFG> struct KbXtCfg;
-template <> struct KbXtCfg<0> { static constexpr int CAP = 3072, XCAP = 2048, STAGES = 2, MAXROWS = 512; };
-template <> struct KbXtCfg<1> { static constexpr int CAP = 2048, XCAP = 1536, STAGES = 3, MAXROWS = 256; };
+template <> struct KbXtCfg<0> { static constexpr int CAP = 3072, XCAP = 2048, STAGES = 2, MAXROWS = 512, CTAS = 2; };
+template <> struct KbXtCfg<1> { static constexpr int CAP = 2048, XCAP = 1536, STAGES = 3, MAXROWS = 256, CTAS = 2; };
+template <> struct KbXtCfg<2> { static constexpr int CAP = 3584, XCAP = 1280, STAGES = 2, MAXROWS = 256, CTAS = 2; };
+template <> struct KbXtCfg<3> { static constexpr int CAP = 3072, XCAP = 1024, STAGES = 5, MAXROWS = 256, CTAS = 1; };
+#define KB_XT_NCFG 4
 
 template <class C>
 struct KbXtStage {
@@ -212,7 +215,7 @@ __device__ __forceinline__ void kb_xt_consume(const KbSpmvArgs& a, KbXtSmem<C>& 
 }
 
 template <class Epi, bool RESID, bool PROD, int CFG>
-__global__ void __launch_bounds__(KB_BULK_THREADS, 2) kb_spmv_xtile(KbSpmvArgs a, KbXtTable tb, Epi epi) {
+__global__ void __launch_bounds__(KB_BULK_THREADS, KbXtCfg<CFG>::CTAS) kb_spmv_xtile(KbSpmvArgs a, KbXtTable tb, Epi epi) {
     using C = KbXtCfg<CFG>;
     kb_pdl_wait();
     kb_pdl_launch_dependents();

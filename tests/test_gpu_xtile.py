@@ -111,7 +111,7 @@ def test_xtile_pcg_jacobi_bit_exact(ctx, cfg, monkeypatch):
     b = o.spmv(Ao, np.ones(Ao.n))
     x = np.zeros(Ao.n)
     st = kb.PcgSolver(1e-8, 1000).solve(A, kb.Jacobi().setup(A), b, x)
-    rc, xo, so = o.pcg(Ao, o.OPc.jacobi(Ao), b, np.zeros(Ao.n), 1e-8, 1000)
+    rc, xo, so, _ = o.pcg(Ao, o.OPc.jacobi(Ao), b, np.zeros(Ao.n), 1e-8, 1000)
     assert (st.iterations, st.converged) == (so.iterations, bool(so.converged))
     assert st.final_residual == so.final_residual and np.array_equal(x, xo)
 
