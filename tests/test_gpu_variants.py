@@ -90,8 +90,9 @@ def test_vector_per_row_kernel_for_long_rows(ctx):
     _check_spmv(ctx, n, n, rp, ci, v, exact=False, kind=1)     # different summation tree: 1e-12 instead of bit-exact
 
 
-def test_product_phase_variant_27pt(ctx):
+def test_product_phase_variant_27pt(ctx, monkeypatch):
     from kryst_b200 import stencils
+    monkeypatch.setenv("KB_SPMV_XTILE", "0")          # kb_spmv_bulk's own product phase (the default for long rows stages x: test_gpu_xtile.py)
     n, rp, ci, v = stencils.stencil("varcoef27", 14)
     _check_spmv(ctx, n, n, rp, ci, v, exact=True, kind=2)
 

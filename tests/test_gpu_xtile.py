@@ -34,7 +34,7 @@ def _banded(n, m, seed, maxlen=12, last_col=True):
     return np.array(rp, dtype=np.uint64), np.array(ci, dtype=np.uint64), np.array(v)
 
 
-@pytest.mark.parametrize("cfg", [0, 1])
+@pytest.mark.parametrize("cfg", [0, 1, 2, 3])
 @pytest.mark.parametrize("kind,N", [("varcoef27", 14), ("varcoef27", 31), ("poisson3d", 17), ("convdiff3d", 24), ("poisson2d", 33),
                                     ("convdiff2d", 130)])
 def test_xtile_spmv_stencils_bit_exact(ctx, kind, N, cfg, monkeypatch):
@@ -49,7 +49,7 @@ def test_xtile_spmv_stencils_bit_exact(ctx, kind, N, cfg, monkeypatch):
         assert np.array_equal(y, o.spmv(Ao, x))
 
 
-@pytest.mark.parametrize("cfg", [0, 1])
+@pytest.mark.parametrize("cfg", [0, 1, 2, 3])
 @pytest.mark.parametrize("n,m", [(1, 1), (5, 5), (513, 513), (700, 707), (1500, 1501), (4099, 4099)])
 def test_xtile_ragged_odd_rectangular(ctx, n, m, cfg, monkeypatch):
     import kryst_b200 as kb
@@ -87,6 +87,32 @@ def test_xtile_auto_mode_only_long_rows(ctx, monkeypatch):
     assert A7.spmv_x_staged() == 0 and A27.spmv_x_staged() == 2
 
 
+def test_xtile_is_the_default_for_long_rows_only(ctx, monkeypatch):
+    monkeypatch.delenv("KB_SPMV_XTILE", raising=False)
+    monkeypatch.delenv("KB_XT_CFG", raising=False)
+    A7, _ = _mk("poisson3d", 12, ctx)
+    A27, Ao = _mk("varcoef27", 12, ctx)
+    assert A7.spmv_x_staged() == 0 and A27.spmv_x_staged() != 0
+    x = np.random.default_rng(1).standard_normal(Ao.n)
+    y = np.zeros(Ao.n)
+    A27.matvec(x, y)
+    assert np.array_equal(y, o.spmv(Ao, x))
+
+
+@pytest.mark.parametrize("prod", ["0", "1"])
+def test_xtile_row_wise_and_product_phase(ctx, prod, monkeypatch):
+    """Both consumer forms of the staged-x kernel (thread per row / per-nonzero product phase) on short and long rows."""
+    _env(monkeypatch, 0)
+    monkeypatch.setenv("KB_SPMV_PROD", prod)
+    for kind, N in (("varcoef27", 18), ("poisson3d", 21)):
+        A, Ao = _mk(kind, N, ctx)
+        assert A.spmv_x_staged() == 1
+        x = np.random.default_rng(N).standard_normal(Ao.n)
+        y = np.zeros(Ao.n)
+        A.matvec(x, y)
+        assert np.array_equal(y, o.spmv(Ao, x))
+
+
 def test_xtile_unaligned_device_operand_falls_back(ctx, monkeypatch):
     import torch
     _env(monkeypatch, 1)
@@ -116,7 +142,7 @@ def test_xtile_pcg_jacobi_bit_exact(ctx, cfg, monkeypatch):
     assert st.final_residual == so.final_residual and np.array_equal(x, xo)
 
 
-@pytest.mark.parametrize("cfg", [0, 1])
+@pytest.mark.parametrize("cfg", [0, 1, 2, 3])
 @pytest.mark.parametrize("kind,N", [("varcoef27", 20), ("convdiff3d", 16)])
 def test_xtile_bicgstab_jacobi_bit_exact(ctx, kind, N, cfg, monkeypatch):
     import kryst_b200 as kb
