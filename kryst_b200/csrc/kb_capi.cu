@@ -250,23 +250,18 @@ static int build_chunk_table(kb_csr_s* A) {
 // x-staging tables of kb_spmv_xtile (kb_spmv_xtile.cuh): a second chunk table, the x intervals of every chunk and the
 // chunk-local 16-bit column ids.  All or nothing: if one chunk does not fit, the operator keeps kb_spmv_bulk.
 // KB_SPMV_XTILE = 0 never, 1 whenever the chunks fit, 2 (default) only for long rows (the product-phase operators,
-// where the gather is the limiter); KB_XT_CFG = 0 | 1 selects the stage geometry.
+// where the gather is the limiter); KB_XT_CFG = 0 | 1 forces one stage geometry (default: 1, then 0).
 static void free_xt_table(kb_csr_s* A) {
     A->xt = 0; A->xt_nchunks = 0;
     KB_FREE(A->xt_tile_chunk); KB_FREE(A->xt_chunk_row); KB_FREE(A->xt_chunk_nz);
     KB_FREE(A->xt_lo); KB_FREE(A->xt_len); KB_FREE(A->xt_tail); KB_FREE(A->xt_lcol);
 }
-static int build_xt_table(kb_csr_s* A) {
+// one geometry: A->xt = cfg + 1 when every chunk fits, tables freed otherwise
+static int try_xt_table(kb_csr_s* A, int cfg) {
     kb_ctx_s* c = A->ctx;
-    const int mode = getenv("KB_SPMV_XTILE") ? atoi(getenv("KB_SPMV_XTILE")) : KB_XT_DEFAULT_MODE;
-    if (mode <= 0 || A->kind != 2 || A->dist || A->n == 0 || A->nnz == 0) return KB_OK;
-    if (mode >= 2 && !A->prod) return KB_OK;
-    int cfg = getenv("KB_XT_CFG") ? atoi(getenv("KB_XT_CFG")) : KB_XT_DEFAULT_CFG;
-    if (cfg < 0 || cfg >= KB_XT_NCFG) cfg = KB_XT_DEFAULT_CFG;
-    static const int caps[KB_XT_NCFG] = {KbXtCfg<0>::CAP, KbXtCfg<1>::CAP, KbXtCfg<2>::CAP, KbXtCfg<3>::CAP};
-    static const int xcaps[KB_XT_NCFG] = {KbXtCfg<0>::XCAP, KbXtCfg<1>::XCAP, KbXtCfg<2>::XCAP, KbXtCfg<3>::XCAP};
-    static const int mrows[KB_XT_NCFG] = {KbXtCfg<0>::MAXROWS, KbXtCfg<1>::MAXROWS, KbXtCfg<2>::MAXROWS, KbXtCfg<3>::MAXROWS};
-    const int cap = caps[cfg], xcap = xcaps[cfg], maxrows = mrows[cfg];
+    const int cap = cfg ? KbXtCfg<1>::CAP : KbXtCfg<0>::CAP;
+    const int xcap = cfg ? KbXtCfg<1>::XCAP : KbXtCfg<0>::XCAP;
+    const int maxrows = cfg ? KbXtCfg<1>::MAXROWS : KbXtCfg<0>::MAXROWS;
     if (A->max_row_len > (uint64_t)cap) return KB_OK;
     const int nt = A->ntiles;
     int st = KB_OK;
@@ -294,18 +289,29 @@ static int build_xt_table(kb_csr_s* A) {
         { KbLaunch L(c, KB_K_OTHER); kb_xt_chunk_build<<<(nt + 127) / 128, 128, 0, c->stream>>>(A->row_ptr, (int)A->n, nt, cap, maxrows, A->xt_tile_chunk, A->xt_chunk_row, A->xt_chunk_nz, 1); }
         {
             KbLaunch L(c, KB_K_OTHER);
-            if (cap == 2048) kb_xt_build<2048><<<acc, KB_THREADS, 0, c->stream>>>(A->col, A->xt_chunk_nz, (int)A->ncols_local, xcap, A->xt_lo, A->xt_len, A->xt_tail, A->xt_lcol, d_fail);
-            else if (cap == 3072) kb_xt_build<3072><<<acc, KB_THREADS, 0, c->stream>>>(A->col, A->xt_chunk_nz, (int)A->ncols_local, xcap, A->xt_lo, A->xt_len, A->xt_tail, A->xt_lcol, d_fail);
-            else kb_xt_build<3584><<<acc, KB_THREADS, 0, c->stream>>>(A->col, A->xt_chunk_nz, (int)A->ncols_local, xcap, A->xt_lo, A->xt_len, A->xt_tail, A->xt_lcol, d_fail);
+            if (cfg) kb_xt_build<KbXtCfg<1>::CAP><<<acc, KB_THREADS, 0, c->stream>>>(A->col, A->xt_chunk_nz, (int)A->ncols_local, xcap, A->xt_lo, A->xt_len, A->xt_tail, A->xt_lcol, d_fail);
+            else kb_xt_build<KbXtCfg<0>::CAP><<<acc, KB_THREADS, 0, c->stream>>>(A->col, A->xt_chunk_nz, (int)A->ncols_local, xcap, A->xt_lo, A->xt_len, A->xt_tail, A->xt_lcol, d_fail);
         }
         int fail = 0;
         if (cudaMemcpyAsync(&fail, d_fail, sizeof(int), cudaMemcpyDeviceToHost, c->stream) != cudaSuccess ||
             cudaStreamSynchronize(c->stream) != cudaSuccess) { kb_set_error("x-tile table build failed: %s", cudaGetErrorString(cudaGetLastError())); st = KB_SOLVE_ERROR; break; }
-        if (!fail) { A->xt = cfg + 1; }
+        if (!fail) A->xt = cfg + 1;
     } while (0);
     if (d_fail) cudaFree(d_fail);
     if (st != KB_OK || !A->xt) free_xt_table(A);
     return st;
+}
+static int build_xt_table(kb_csr_s* A) {
+    const int mode = getenv("KB_SPMV_XTILE") ? atoi(getenv("KB_SPMV_XTILE")) : KB_XT_DEFAULT_MODE;
+    if (mode <= 0 || A->kind != 2 || A->dist || A->n == 0 || A->nnz == 0) return KB_OK;
+    if (mode >= 2 && !A->prod) return KB_OK;
+    // thread per row out of shared memory up to 32 entries per row on average, per-nonzero product phase beyond
+    A->xt_prod = (double)A->nnz / (double)A->n > 32.0;
+    if (getenv("KB_SPMV_PROD")) A->xt_prod = atoi(getenv("KB_SPMV_PROD")) != 0;
+    if (getenv("KB_XT_CFG")) return try_xt_table(A, atoi(getenv("KB_XT_CFG")) != 0 ? 1 : 0);     // tuning: this geometry or none
+    KB_TRY(try_xt_table(A, KB_XT_DEFAULT_CFG));
+    if (!A->xt) KB_TRY(try_xt_table(A, 1 - KB_XT_DEFAULT_CFG));
+    return KB_OK;
 }
 
 // allocate the device arrays of an operator (padded tails zeroed); the caller fills row_ptr / col / vals

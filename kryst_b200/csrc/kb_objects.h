@@ -26,6 +26,7 @@ struct kb_csr_s {
     bool prod = false;           // kind 2: per-nonzero product phase (long rows) instead of per-row gathers
     // kind 2 with the x operand staged in shared memory (kb_spmv_xtile.cuh): 0 = off, else configuration + 1
     int xt = 0;
+    bool xt_prod = false;        // staged x: per-nonzero product phase (rows longer than 32 on average) instead of a thread per row
     int* xt_tile_chunk = nullptr;
     int* xt_chunk_row = nullptr;
     int* xt_chunk_nz = nullptr;

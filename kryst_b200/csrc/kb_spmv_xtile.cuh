@@ -10,7 +10,9 @@
 // `cp.async.bulk` per x interval (lane k copies interval k); the consumers read x from shared memory only.
 // Per-row operation sequence (product rounded, ascending adds) is the one of kb_spmv_bulk and the oracle: same bits.
 // Operators whose chunks do not fit (more than 16 intervals, or more x than a stage holds), shards with ghost
-// columns and operands that are not 16-byte aligned keep kb_spmv_bulk.
+// columns and operands that are not 16-byte aligned keep kb_spmv_bulk.  Default for long-row operators (more than 12
+// entries per row on average: C3 2 333 -> 3 695 it/s, DRAM traffic per SpMV 711 -> 603 MB); 7-point operators keep
+// kb_spmv_bulk, whose L1-served gather already runs at 0.92 of the HBM peak (staged x measured 0.38 vs 0.29 ms on C4).
 #pragma once
 #include <cub/block/block_radix_sort.cuh>
 #include "kb_spmv_bulk.cuh"
@@ -20,16 +22,18 @@
 #define KB_XT_DEFAULT_MODE 2   // KB_SPMV_XTILE when the environment does not say (0 off, 1 whenever it fits, 2 long rows only)
 #endif
 #ifndef KB_XT_DEFAULT_CFG
-#define KB_XT_DEFAULT_CFG 0
+#define KB_XT_DEFAULT_CFG 1
 #endif
 #define KB_XT_GAP 4            // merge intervals whose gap is <= 4 aligned pairs (8 columns)
 
 template <int CFG> struct KbXtCfg;
-template <> struct KbXtCfg<0> { static constexpr int CAP = 3072, XCAP = 2048, STAGES = 2, MAXROWS = 512, CTAS = 2; };
-template <> struct KbXtCfg<1> { static constexpr int CAP = 2048, XCAP = 1536, STAGES = 3, MAXROWS = 256, CTAS = 2; };
-template <> struct KbXtCfg<2> { static constexpr int CAP = 3584, XCAP = 1280, STAGES = 2, MAXROWS = 256, CTAS = 2; };
-template <> struct KbXtCfg<3> { static constexpr int CAP = 3072, XCAP = 1024, STAGES = 5, MAXROWS = 256, CTAS = 1; };
-#define KB_XT_NCFG 4
+// Stage geometries (two CTAs per SM, two stages each).  Measured on B200 with the 27-point 128^3 operator (C3), SpMV
+// with two fused dots: kb_spmv_bulk 0.175 ms; geometry 1 thread-per-row 0.103 ms, product phase 0.157 ms; geometry 0
+// 0.128 / 0.132 ms; 3 stages of 2048 entries 0.150 ms; one CTA per SM with 5 stages 0.19-0.20 ms (the consumers, not the
+// bytes in flight, are the limiter).  Geometry 1 is tried first, geometry 0 (more room for x) when a chunk does not fit.
+template <> struct KbXtCfg<0> { static constexpr int CAP = 3072, XCAP = 2048, STAGES = 2, MAXROWS = 512; };
+template <> struct KbXtCfg<1> { static constexpr int CAP = 3584, XCAP = 1280, STAGES = 2, MAXROWS = 256; };
+#define KB_XT_NCFG 2
 
 template <class C>
 struct KbXtStage {
@@ -215,7 +219,7 @@ __device__ __forceinline__ void kb_xt_consume(const KbSpmvArgs& a, KbXtSmem<C>& 
 }
 
 template <class Epi, bool RESID, bool PROD, int CFG>
-__global__ void __launch_bounds__(KB_BULK_THREADS, KbXtCfg<CFG>::CTAS) kb_spmv_xtile(KbSpmvArgs a, KbXtTable tb, Epi epi) {
+__global__ void __launch_bounds__(KB_BULK_THREADS, 2) kb_spmv_xtile(KbSpmvArgs a, KbXtTable tb, Epi epi) {
     using C = KbXtCfg<CFG>;
     kb_pdl_wait();
     kb_pdl_launch_dependents();

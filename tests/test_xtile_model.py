@@ -10,7 +10,7 @@ import pytest
 from kryst_b200 import stencils
 
 KB_TILE, KMAX, GAP = 512, 16, 4
-CFGS = {0: dict(cap=3072, xcap=2048, maxrows=512), 1: dict(cap=2048, xcap=1536, maxrows=256)}
+CFGS = {0: dict(cap=3072, xcap=2048, maxrows=512), 1: dict(cap=3584, xcap=1280, maxrows=256)}
 
 
 def chunk_build(rp, n, cap, maxrows):
@@ -122,11 +122,12 @@ def test_27pt_128_chunk_geometry(cfg):
     cols = (r[:, None] + offs[None, :])
     rp = np.arange(0, 27 * KB_TILE + 1, 27)
     tile_chunk, chunk_row, chunk_nz = chunk_build(rp, KB_TILE, g["cap"], g["maxrows"])
-    assert tile_chunk == [0, 5 if cfg == 0 else 7]
+    assert tile_chunk == [0, 5 if cfg == 0 else 4]
     t = xt_build(cols.reshape(-1), chunk_nz, 1, N ** 3, g["xcap"])
     assert t is not None
     lo, ln, tl, lcol = t
-    assert len(lo) == 9 and tl == -1 and sum(ln) <= g["xcap"] // 2 + 256
+    # geometry 0: 103-row chunks, 9 separate lines; geometry 1: 128-row chunks = whole grid lines, the three lines of a plane merge
+    assert len(lo) == (9 if cfg == 0 else 3) and tl == -1 and sum(ln) <= g["xcap"]
 
 
 @pytest.mark.parametrize("cfg", [0, 1])
