@@ -18,6 +18,7 @@
 #include "kb_epilogue.cuh"
 #include "kb_driver.cuh"
 #include "kb_pcg_mega.cuh"
+#include "kb_pcg_resident.cuh"
 
 // ---- scalar epilogues (device, single thread) ------------------------------------------------
 struct PcgInitFin {   // pcg.rs:132-146
@@ -362,6 +363,9 @@ struct KbPcgWs {
     double* hist = nullptr; uint64_t hist_cap = 0;
     KbGraphCache gc;
     unsigned* mega_bar = nullptr;     // grid-barrier words of the persistent kernel
+    ulonglong2* res_pk = nullptr;     // resident kernel: tagged packets [n + 3 ntiles], marks [n], barrier / verdict words
+    unsigned char* res_needed = nullptr;
+    unsigned* res_bar = nullptr;
     double *u_sr = nullptr, *s_sr = nullptr;   // single-reduction variant: u (SpMV operand, with ghost tail) and s = A p
     double *m_pp = nullptr, *n_pp = nullptr, *q_pp = nullptr;   // pipelined variant: m = M^-1 w (SpMV operand, with ghost tail), n = A m, q
 };
@@ -369,7 +373,7 @@ void kb_pcg_ws_free(KbPcgWs* w) {
     if (!w) return;
     w->gc.reset();
     KB_FREE(w->x); KB_FREE(w->r); KB_FREE(w->z); KB_FREE(w->p); KB_FREE(w->ap); KB_FREE(w->b);
-    KB_FREE(w->partials); KB_FREE(w->slots); KB_FREE(w->ctl); KB_FREE(w->hist); KB_FREE(w->mega_bar); KB_FREE(w->u_sr); KB_FREE(w->s_sr); KB_FREE(w->m_pp); KB_FREE(w->n_pp); KB_FREE(w->q_pp);
+    KB_FREE(w->partials); KB_FREE(w->slots); KB_FREE(w->ctl); KB_FREE(w->hist); KB_FREE(w->mega_bar); KB_FREE(w->res_pk); KB_FREE(w->res_needed); KB_FREE(w->res_bar); KB_FREE(w->u_sr); KB_FREE(w->s_sr); KB_FREE(w->m_pp); KB_FREE(w->n_pp); KB_FREE(w->q_pp);
     if (w->h_ctl) cudaFreeHost(w->h_ctl);
     delete w;
 }
@@ -522,6 +526,58 @@ static int pcg_persistent(kb_csr_s* A, const kb_pc_s* pc, KbPcgWs* w) {
     return KB_OK;
 }
 
+// whole solve on chip in one cooperative launch (kb_pcg_resident.cuh); *ran = false: not eligible, nothing was modified
+#ifndef KB_PCG_RESIDENT_DEFAULT
+#define KB_PCG_RESIDENT_DEFAULT 1
+#endif
+static int pcg_resident(kb_csr_s* A, const kb_pc_s* pc, KbPcgWs* w, bool* ran) {
+    *ran = false;
+    kb_ctx_s* c = A->ctx;
+    const int L = (int)A->max_row_len;
+    if (L < 1 || L > KB_RES_MAXLEN || A->n != A->ncols_local || A->n == 0) return KB_OK;
+    const int G = std::min(c->sm_count, A->ntiles);
+    if ((A->ntiles + G - 1) / G > KB_RES_TEAMS) return KB_OK;
+    const int T = (A->ntiles + G - 1) / G;
+    const size_t smem_max = 226 * 1024;                            // 227 KB per CTA minus the kernel's static shared memory
+    const size_t fixed = kb_res_smem_fixed(L, T);
+    if (fixed + 12 * 256 > smem_max) return KB_OK;
+    const int ghost_cap = (int)std::min<size_t>((smem_max - fixed) / 12, (size_t)1 << 15);
+    const size_t smem = kb_res_smem_bytes(L, T, ghost_cap);
+    auto kfn = kb_pcg_resident;
+    if (!c->configured.count((const void*)kfn)) {
+        KB_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
+        c->configured.insert((const void*)kfn);
+    }
+    int occ = 0;
+    KB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kfn, KB_RES_THREADS, smem));
+    if (occ < 1) return KB_OK;
+    const size_t npk = (size_t)A->n + 3 * (size_t)A->ntiles;
+    if (!w->res_pk) {
+        KB_TRY(kb_alloc(&w->res_pk, npk));
+        KB_TRY(kb_alloc(&w->res_needed, (size_t)A->n));
+        KB_TRY(kb_alloc(&w->res_bar, 4));
+    }
+    KB_CUDA(cudaMemsetAsync(w->res_pk, 0, npk * sizeof(ulonglong2), c->stream));
+    KB_CUDA(cudaMemsetAsync(w->res_needed, 0, (size_t)A->n, c->stream));
+    KB_CUDA(cudaMemsetAsync(w->res_bar, 0, 4 * sizeof(unsigned), c->stream));
+    KbPcgResArgs m{};
+    m.row_ptr = A->row_ptr; m.col = A->col; m.vals = A->vals; m.n = (int)A->n; m.ntiles = A->ntiles; m.maxlen = L; m.tiles_per_cta = T; m.ghost_cap = ghost_cap;
+    m.x = w->x; m.r = w->r; m.p = w->p; m.inv = pc ? pc->inv_diag : nullptr; m.ctl = w->ctl;
+    m.pk_p = w->res_pk; m.pk_a = w->res_pk + A->n; m.pk_b = w->res_pk + A->n + A->ntiles;
+    m.needed = w->res_needed; m.bar = w->res_bar;
+    void* args[] = {&m};
+    {
+        KbLaunch Lc(c, KB_K_SPMV);
+        KB_CUDA(cudaLaunchCooperativeKernel((const void*)kfn, dim3(G), dim3(KB_RES_THREADS), args, smem, c->stream));
+    }
+    unsigned verdict = 0;
+    if (cudaMemcpyAsync(&verdict, w->res_bar + 2, sizeof(unsigned), cudaMemcpyDeviceToHost, c->stream) != cudaSuccess ||
+        cudaStreamSynchronize(c->stream) != cudaSuccess) { kb_set_error("pcg: resident kernel failed: %s", cudaGetErrorString(cudaGetLastError())); return KB_SOLVE_ERROR; }
+    if (verdict == 1u) { kb_set_error("pcg: resident kernel timed out waiting for a packet"); return KB_SOLVE_ERROR; }
+    *ran = verdict == 0u;
+    return KB_OK;
+}
+
 static int pcg_iteration(kb_csr_s* A, const kb_pc_s* pc, KbPcgWs* w) {
     return A->dist && A->ctx->size > 1 ? pcg_launch_iteration<true>(A, pc, w) : pcg_launch_iteration<false>(A, pc, w);
 }
@@ -600,7 +656,13 @@ extern "C" int kb_pcg_solve(kb_csr A, kb_pc pc, const double* b, double* x, doub
         const int mega_env = getenv("KB_PCG_PERSISTENT") ? atoi(getenv("KB_PCG_PERSISTENT")) : 0;
         const bool mega_ok = !single_red && !dist && jacobi_like && A->kind == 2 && !A->prod && !profile && max_iters > 0;
         const bool mega = mega_ok && mega_env != 0 && !mon.fn;
-        if (mega) {
+        // Problems that fit on chip (<= 4 tiles per SM, rows <= 8 entries): the whole loop in one launch out of shared
+        // memory and registers (KB_PCG_RESIDENT=0 keeps the CUDA-graph path).
+        const int res_env = getenv("KB_PCG_RESIDENT") ? atoi(getenv("KB_PCG_RESIDENT")) : KB_PCG_RESIDENT_DEFAULT;
+        bool resident = false;
+        if (res_env != 0 && !mega && !single_red && !dist && jacobi_like && !mon.fn && max_iters > 0 && !(flags & KB_FLAG_NO_GRAPH) && (st = pcg_resident(A, pc, w, &resident)) != KB_OK) break;
+        if (resident) {
+        } else if (mega) {
             if ((st = pcg_persistent(A, pc, w)) != KB_OK) break;
             unsigned berr = 0;
             if (cudaMemcpyAsync(&berr, w->mega_bar + 2, sizeof(unsigned), cudaMemcpyDeviceToHost, c->stream) != cudaSuccess ||

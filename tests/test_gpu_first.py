@@ -50,11 +50,13 @@ def test_jacobi_bit_exact(ctx, kind, N):
 
 @pytest.mark.parametrize("kind,N", [("poisson2d", 16), ("poisson2d", 100), ("poisson3d", 24), ("varcoef27", 12)])
 @pytest.mark.parametrize("use_pc", [True, False])
-@pytest.mark.parametrize("persistent", ["0", "1"])
-def test_pcg_bit_exact(ctx, kind, N, use_pc, persistent, monkeypatch):
-    """Both drivers: CUDA-graph replay of 3 kernels/iteration, and the single persistent cooperative kernel."""
+@pytest.mark.parametrize("driver", ["graph", "persistent", "resident"])
+def test_pcg_bit_exact(ctx, kind, N, use_pc, driver, monkeypatch):
+    """All drivers: CUDA-graph replay of 3 kernels/iteration, the persistent cooperative kernel (grid barriers), and the
+    on-chip resident kernel (default where the problem fits; the 27-point operator declines it: rows longer than 8)."""
     import kryst_b200 as kb
-    monkeypatch.setenv("KB_PCG_PERSISTENT", persistent)
+    monkeypatch.setenv("KB_PCG_PERSISTENT", "1" if driver == "persistent" else "0")
+    monkeypatch.setenv("KB_PCG_RESIDENT", "1" if driver == "resident" else "0")
     A, Ao = _mk(kind, N, ctx)
     b = o.spmv(Ao, np.ones(Ao.n))
     pc = kb.Jacobi().setup(A) if use_pc else None
