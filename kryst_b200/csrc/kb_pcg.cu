@@ -536,7 +536,7 @@ static int pcg_resident(kb_csr_s* A, const kb_pc_s* pc, KbPcgWs* w, bool* ran) {
     const int L = (int)A->max_row_len;
     if (L < 1 || L > KB_RES_MAXLEN || A->n != A->ncols_local || A->n == 0) return KB_OK;
     const int G = std::min(c->sm_count, A->ntiles);
-    if ((A->ntiles + G - 1) / G > KB_RES_TEAMS) return KB_OK;
+    if ((A->ntiles + G - 1) / G > KB_RES_TEAMS || A->ntiles > 3 * KB_THREADS) return KB_OK;
     const int T = (A->ntiles + G - 1) / G;
     const size_t smem_max = 226 * 1024;                            // 227 KB per CTA minus the kernel's static shared memory
     const size_t fixed = kb_res_smem_fixed(L, T);
@@ -561,7 +561,7 @@ static int pcg_resident(kb_csr_s* A, const kb_pc_s* pc, KbPcgWs* w, bool* ran) {
     KB_CUDA(cudaMemsetAsync(w->res_needed, 0, (size_t)A->n, c->stream));
     KB_CUDA(cudaMemsetAsync(w->res_bar, 0, 4 * sizeof(unsigned), c->stream));
     KbPcgResArgs m{};
-    m.row_ptr = A->row_ptr; m.col = A->col; m.vals = A->vals; m.n = (int)A->n; m.ntiles = A->ntiles; m.maxlen = L; m.tiles_per_cta = T; m.ghost_cap = ghost_cap;
+    m.row_ptr = A->row_ptr; m.col = A->col; m.vals = A->vals; m.n = (int)A->n; m.ntiles = A->ntiles; m.maxlen = L; m.tiles_per_cta = T; m.ghost_cap = ghost_cap; m.dbg = getenv("KB_RES_DEBUG") ? atoi(getenv("KB_RES_DEBUG")) : 0;
     m.x = w->x; m.r = w->r; m.p = w->p; m.inv = pc ? pc->inv_diag : nullptr; m.ctl = w->ctl;
     m.pk_p = w->res_pk; m.pk_a = w->res_pk + A->n; m.pk_b = w->res_pk + A->n + A->ntiles;
     m.needed = w->res_needed; m.bar = w->res_bar;

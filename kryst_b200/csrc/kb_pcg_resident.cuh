@@ -1,8 +1,9 @@
 // kb_pcg_resident.cuh — PCG (pcg.rs:148-218) for problems that fit on chip: ONE cooperative launch per solve, one CTA
 // per SM, every CTA keeps its rows of the operator in shared memory and its entries of x, r, p, D^-1 in registers
-// for the whole solve.  Nothing streams from HBM inside the loop; what is left per iteration is three L2 round trips:
-//   ghost entries of p (columns owned by other CTAs), the tile sums of p.Ap, the tile sums of r.z and the norm.
-// All three travel as 16-byte tagged packets ({lo32|tag, hi32|tag}: the data is its own flag, tag = 3*iteration +
+// for the whole solve.  Nothing streams from HBM inside the loop; what is left per iteration is two L2 round trips:
+// the tile sums of p.Ap, and the tile sums of r.z and the norm together with the entries of z that other CTAs need
+// (a CTA updates its ghost copies of p itself, p_g = z_g + beta p_g: same operands, same bits as the owner's update).
+// Everything travels as 16-byte tagged packets ({lo32|tag, hi32|tag}: the data is its own flag, tag = 3*iteration +
 // phase), so there is no grid barrier, no flag and no fence in the loop: a consumer polls the packet it needs.
 // Every CTA sums ALL tile sums itself in the canonical order (level 2 of the reduction tree, kb_internal.cuh) and
 // runs the scalar recurrences redundantly - same bits everywhere, so all CTAs leave the loop in the same iteration.
@@ -30,9 +31,11 @@ struct KbPcgResArgs {
     int n, ntiles, maxlen;
     int tiles_per_cta;       // max tiles of one CTA (<= KB_RES_TEAMS): sizes the operator rows in shared memory
     int ghost_cap;           // ghost references one CTA can hold
+    int dbg;                 // timing ablations only (KB_RES_DEBUG; results are then meaningless): 1/2/4 do not wait for p.Ap sums /
+                             // r.z sums / ghosts, 8 back off between failed polls, 16 fixed iteration count
     double* x; double* r; const double* p; const double* inv;
     KbCtl* ctl;
-    ulonglong2* pk_p;        // [n]        tagged p entries (only rows that are ghost columns of another CTA are written)
+    ulonglong2* pk_p;        // [n]        tagged entries of the initial p, then of z (only rows that are ghost columns of another CTA)
     ulonglong2* pk_a;        // [ntiles]   tagged tile sums of p.Ap
     ulonglong2* pk_b;        // [2*ntiles] tagged tile sums of r.z and of the norm
     unsigned char* needed;   // [n]        row is a ghost column of another CTA
@@ -59,10 +62,12 @@ __device__ __forceinline__ bool kb_res_load(const ulonglong2* p, unsigned tag, d
     return (unsigned)(x >> 32) == tag && (unsigned)(y >> 32) == tag;
 }
 // bounded poll; a timeout raises the CTA's error flag (checked by everybody after the next __syncthreads)
-__device__ __forceinline__ double kb_res_poll(const ulonglong2* p, unsigned tag, int* s_err) {
+__device__ __forceinline__ double kb_res_poll(const ulonglong2* p, unsigned tag, int* s_err, int nowait = 0, int backoff = 0) {
     double v;
     unsigned spins = 0;
     while (!kb_res_load(p, tag, &v)) {
+        if (nowait) break;
+        if (backoff) __nanosleep(100);
         if (++spins > KB_RES_SPIN || *reinterpret_cast<volatile int*>(s_err) != 0) { *s_err = 1; break; }
     }
     return v;
@@ -90,10 +95,26 @@ __device__ __forceinline__ void kb_team_reduce(double (&v)[NRED], double* sm /* 
     }
     kb_team_sync(team);
 }
-// level 2 over the tagged tile sums (one team; result valid in lane 0 of the team)
-__device__ __forceinline__ double kb_team_level2(const ulonglong2* pk, int P, unsigned tag, double* sm, int team, int l, int* s_err) {
+// level 2 over the tagged tile sums (one team; result valid in lane 0 of the team).  P <= 768: a lane owns the sums
+// l, l+256, l+512; their loads are issued together and repeated until every tag matches.
+__device__ __forceinline__ double kb_team_level2(const ulonglong2* pk, int P, unsigned tag, double* sm, int team, int l, int* s_err, int nowait = 0, int backoff = 0) {
+    const bool h0 = l < P, h1 = l + KB_THREADS < P, h2 = l + 2 * KB_THREADS < P;
+    bool d0 = !h0, d1 = !h1, d2 = !h2;
+    double v0 = 0.0, v1 = 0.0, v2 = 0.0;
+    unsigned spins = 0;
+    while (!(d0 && d1 && d2)) {
+        if (!d0) d0 = kb_res_load(pk + l, tag, &v0);
+        if (!d1) d1 = kb_res_load(pk + l + KB_THREADS, tag, &v1);
+        if (!d2) d2 = kb_res_load(pk + l + 2 * KB_THREADS, tag, &v2);
+        if (nowait) break;
+        if (d0 && d1 && d2) break;
+        if (backoff) __nanosleep(100);
+        if (++spins > KB_RES_SPIN || *reinterpret_cast<volatile int*>(s_err) != 0) { *s_err = 1; break; }
+    }
     double acc = 0.0;
-    for (int k = l; k < P; k += KB_THREADS) acc = acc + kb_res_poll(pk + k, tag, s_err);
+    if (h0) acc = acc + v0;
+    if (h1) acc = acc + v1;
+    if (h2) acc = acc + v2;
     double v[1] = {acc}, out[1] = {0.0};
     kb_team_reduce<1>(v, sm, out, team, l);
     return out[0];
@@ -101,6 +122,7 @@ __device__ __forceinline__ double kb_team_level2(const ulonglong2* pk, int P, un
 __global__ void __launch_bounds__(KB_RES_THREADS, 1) kb_pcg_resident(KbPcgResArgs m) {
     extern __shared__ __align__(16) unsigned char kb_res_raw[];
     const int L = m.maxlen, T = m.tiles_per_cta, OWN = T * KB_TILE;
+    const int dbg = m.dbg, boff = dbg & 8;
     double2* vals2 = reinterpret_cast<double2*>(kb_res_raw);                                  // [T][L][256]
     int2* cols2 = reinterpret_cast<int2*>(vals2 + (size_t)T * L * KB_THREADS);                // [T][L][256]
     double* ps = reinterpret_cast<double*>(cols2 + (size_t)T * L * KB_THREADS);               // [T*512 own | ghost_cap]
@@ -193,11 +215,11 @@ __global__ void __launch_bounds__(KB_RES_THREADS, 1) kb_pcg_resident(KbPcgResArg
     int status = KB_OK, converged = 0;
     double res = c->res, alpha = 0.0, beta = 0.0, pAp = 0.0;
     bool err = false;
+    for (int q = tid; q < ng; q += KB_RES_THREADS) ps[OWN + q] = kb_res_poll(m.pk_p + gcol_s[q], 3u, s_err, 0, boff);   // ghost copies of the initial p
+    __syncthreads();
     for (unsigned k = 1;; ++k) {
-        const unsigned tagX = 3u * k, tagA = 3u * k + 1u, tagB = 3u * k + 2u, tagP = 3u * k + 3u;
-        // ---- ap = A p (own columns from shared memory, ghost columns from the owners' packets), tile sum of p.Ap
-        for (int q = tid; q < ng; q += KB_RES_THREADS) ps[OWN + q] = kb_res_poll(m.pk_p + gcol_s[q], tagX, s_err);
-        __syncthreads();
+        const unsigned tagA = 3u * k + 1u, tagB = 3u * k + 2u;
+        // ---- ap = A p out of shared memory (own rows and ghost copies), tile sum of p.Ap
         double apA = 0.0, apB = 0.0;
         if (active) {
 #pragma unroll
@@ -215,13 +237,13 @@ __global__ void __launch_bounds__(KB_RES_THREADS, 1) kb_pcg_resident(KbPcgResArg
             if (l == 0) kb_res_store(m.pk_a + tile, o[0], tagA);
         }
         if (team == 0) {
-            const double s = kb_team_level2(m.pk_a, m.ntiles, tagA, tred, 0, l, s_err);
+            const double s = kb_team_level2(m.pk_a, m.ntiles, tagA, tred, 0, l, s_err, dbg & 1, boff);
             if (l == 0) scal[0] = s;
         }
         __syncthreads();
         if (*s_err) { err = true; break; }
         pAp = scal[0];
-        if (pAp <= 0.0) { status = KB_INDEFINITE_MATRIX; iter = iter + 1; converged = 0; break; }      // pcg.rs:161-173
+        if (pAp <= 0.0 && !(dbg & 16)) { status = KB_INDEFINITE_MATRIX; iter = iter + 1; converged = 0; break; }      // pcg.rs:161-173
         alpha = rz / pAp;
         // ---- x += alpha p ; r -= alpha ap ; z = D^-1 r ; tile sums of r.z and the norm
         double zA = 0.0, zB = 0.0;
@@ -238,12 +260,14 @@ __global__ void __launch_bounds__(KB_RES_THREADS, 1) kb_pcg_resident(KbPcgResArg
                 e0B = rB * zB;
                 e1B = nt == KB_NORM_PRECONDITIONED ? zB * zB : nt == KB_NORM_UNPRECONDITIONED ? rB * rB : 0.0;
             }
+            if (needA) kb_res_store(m.pk_p + rowA, zA, tagB);        // other CTAs rebuild their copy of p from z and beta
+            if (needB) kb_res_store(m.pk_p + rowB, zB, tagB);
             e[0] = e0A + e0B; e[1] = e1A + e1B;
             kb_team_reduce<2>(e, tred, o, team, l);
             if (l == 0) { kb_res_store(m.pk_b + tile, o[0], tagB); kb_res_store(m.pk_b + m.ntiles + tile, o[1], tagB); }
         }
         if (team < 2) {
-            const double s = kb_team_level2(m.pk_b + (size_t)team * m.ntiles, m.ntiles, tagB, tred, team, l, s_err);
+            const double s = kb_team_level2(m.pk_b + (size_t)team * m.ntiles, m.ntiles, tagB, tred, team, l, s_err, dbg & 2, boff);
             if (l == 0) scal[1 + team] = s;
         }
         __syncthreads();
@@ -255,17 +279,19 @@ __global__ void __launch_bounds__(KB_RES_THREADS, 1) kb_pcg_resident(KbPcgResArg
         if (blockIdx.x == 0 && tid == 0 && hist_len < hist_cap) hist[hist_len] = res;
         hist_len += 1;
         const double rel = res / res0;
-        if (rel <= tol || iter >= max_iters) { converged = 1; break; }
+        if ((rel <= tol && !(dbg & 16)) || iter >= max_iters) { converged = 1; break; }
         beta = rz_new / rz;
-        if (beta < 0.0) { status = KB_INDEFINITE_PC; converged = 0; break; }
+        if (beta < 0.0 && !(dbg & 16)) { status = KB_INDEFINITE_PC; converged = 0; break; }
         rz = rz_new;
-        // ---- p = z + beta p ; publish the entries other CTAs read
+        // ---- p = z + beta p : own rows, and the ghost copies from the owners' z
         if (active) {
             if (hasA) pA = zA + beta * pA;
             if (hasB) pB = zB + beta * pB;
             ps[team * KB_TILE + 2 * l] = pA; ps[team * KB_TILE + 2 * l + 1] = pB;
-            if (needA) kb_res_store(m.pk_p + rowA, pA, tagP);
-            if (needB) kb_res_store(m.pk_p + rowB, pB, tagP);
+        }
+        for (int q = tid; q < ng; q += KB_RES_THREADS) {
+            const double zg = kb_res_poll(m.pk_p + gcol_s[q], tagB, s_err, dbg & 4, boff);
+            ps[OWN + q] = zg + beta * ps[OWN + q];
         }
         __syncthreads();
     }
