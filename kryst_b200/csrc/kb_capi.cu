@@ -259,9 +259,11 @@ static void free_xt_table(kb_csr_s* A) {
 // one geometry: A->xt = cfg + 1 when every chunk fits, tables freed otherwise
 static int try_xt_table(kb_csr_s* A, int cfg) {
     kb_ctx_s* c = A->ctx;
-    const int cap = cfg ? KbXtCfg<1>::CAP : KbXtCfg<0>::CAP;
-    const int xcap = cfg ? KbXtCfg<1>::XCAP : KbXtCfg<0>::XCAP;
-    const int maxrows = cfg ? KbXtCfg<1>::MAXROWS : KbXtCfg<0>::MAXROWS;
+    static const int caps[KB_XT_NCFG] = {KbXtCfg<0>::CAP, KbXtCfg<1>::CAP, KbXtCfg<2>::CAP};
+    static const int xcaps[KB_XT_NCFG] = {KbXtCfg<0>::XCAP, KbXtCfg<1>::XCAP, KbXtCfg<2>::XCAP};
+    static const int mrows[KB_XT_NCFG] = {KbXtCfg<0>::MAXROWS, KbXtCfg<1>::MAXROWS, KbXtCfg<2>::MAXROWS};
+    if (cfg < 0 || cfg >= KB_XT_NCFG) return KB_OK;
+    const int cap = caps[cfg], xcap = xcaps[cfg], maxrows = mrows[cfg];
     if (A->max_row_len > (uint64_t)cap) return KB_OK;
     const int nt = A->ntiles;
     int st = KB_OK;
@@ -289,7 +291,8 @@ static int try_xt_table(kb_csr_s* A, int cfg) {
         { KbLaunch L(c, KB_K_OTHER); kb_xt_chunk_build<<<(nt + 127) / 128, 128, 0, c->stream>>>(A->row_ptr, (int)A->n, nt, cap, maxrows, A->xt_tile_chunk, A->xt_chunk_row, A->xt_chunk_nz, 1); }
         {
             KbLaunch L(c, KB_K_OTHER);
-            if (cfg) kb_xt_build<KbXtCfg<1>::CAP><<<acc, KB_THREADS, 0, c->stream>>>(A->col, A->xt_chunk_nz, (int)A->ncols_local, xcap, A->xt_lo, A->xt_len, A->xt_tail, A->xt_lcol, d_fail);
+            if (cfg == 1) kb_xt_build<KbXtCfg<1>::CAP><<<acc, KB_THREADS, 0, c->stream>>>(A->col, A->xt_chunk_nz, (int)A->ncols_local, xcap, A->xt_lo, A->xt_len, A->xt_tail, A->xt_lcol, d_fail);
+            else if (cfg == 2) kb_xt_build<KbXtCfg<2>::CAP><<<acc, KB_THREADS, 0, c->stream>>>(A->col, A->xt_chunk_nz, (int)A->ncols_local, xcap, A->xt_lo, A->xt_len, A->xt_tail, A->xt_lcol, d_fail);
             else kb_xt_build<KbXtCfg<0>::CAP><<<acc, KB_THREADS, 0, c->stream>>>(A->col, A->xt_chunk_nz, (int)A->ncols_local, xcap, A->xt_lo, A->xt_len, A->xt_tail, A->xt_lcol, d_fail);
         }
         int fail = 0;
@@ -308,7 +311,7 @@ static int build_xt_table(kb_csr_s* A) {
     // thread per row out of shared memory up to 32 entries per row on average, per-nonzero product phase beyond
     A->xt_prod = (double)A->nnz / (double)A->n > 32.0;
     if (getenv("KB_SPMV_PROD")) A->xt_prod = atoi(getenv("KB_SPMV_PROD")) != 0;
-    if (getenv("KB_XT_CFG")) return try_xt_table(A, atoi(getenv("KB_XT_CFG")) != 0 ? 1 : 0);     // tuning: this geometry or none
+    if (getenv("KB_XT_CFG")) return try_xt_table(A, atoi(getenv("KB_XT_CFG")));     // tuning: this geometry or none
     KB_TRY(try_xt_table(A, KB_XT_DEFAULT_CFG));
     if (!A->xt) KB_TRY(try_xt_table(A, 1 - KB_XT_DEFAULT_CFG));
     return KB_OK;

@@ -96,14 +96,14 @@ template <class Epi, bool RESID, int CFG>
 static int kb_launch_spmv_xtile(kb_csr_s* A, const KbSpmvArgs& a, Epi epi, int count, bool pdl) {
     kb_ctx_s* c = A->ctx;
     using S = KbXtSmem<KbXtCfg<CFG>>;
-    static_assert(sizeof(S) <= 112 * 1024, "two CTAs per SM");
+    static_assert(sizeof(S) <= (KbXtCfg<CFG>::CTAS == 2 ? 112 : 74) * 1024, "CTAs per SM");
     auto kfn = A->xt_prod ? kb_spmv_xtile<Epi, RESID, true, CFG> : kb_spmv_xtile<Epi, RESID, false, CFG>;
     if (!c->configured.count((const void*)kfn)) {
         KB_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(S)));
         c->configured.insert((const void*)kfn);
     }
     KbXtTable tb{A->xt_tile_chunk, A->xt_chunk_row, A->xt_chunk_nz, A->xt_lo, A->xt_len, A->xt_tail, A->xt_lcol, (int)A->ncols_local - 1};
-    const int grid = std::min(2 * c->sm_count, count);
+    const int grid = std::min(KbXtCfg<CFG>::CTAS * c->sm_count, count);
     KbLaunch L(c, KB_K_SPMV);
     KB_CUDA(kb_launch_ex(pdl && kb_pdl_enabled(), kfn, dim3(grid), dim3(KB_BULK_THREADS), sizeof(S), c->stream, a, tb, epi));
     return KB_OK;
@@ -119,7 +119,8 @@ static int kb_launch_spmv_tiles(kb_csr_s* A, KbSpmvArgs a, Epi epi, const int* l
         // x staged in shared memory (operators whose chunks fit, 16-byte aligned operand; no ghost columns)
         if (A->kind == 2 && A->xt && (reinterpret_cast<uintptr_t>(a.x) & 15u) == 0) {
             if (A->xt == 1) return kb_launch_spmv_xtile<Epi, RESID, 0>(A, a, epi, count, pdl);
-            return kb_launch_spmv_xtile<Epi, RESID, 1>(A, a, epi, count, pdl);
+            if (A->xt == 2) return kb_launch_spmv_xtile<Epi, RESID, 1>(A, a, epi, count, pdl);
+            return kb_launch_spmv_xtile<Epi, RESID, 2>(A, a, epi, count, pdl);
         }
     }
     if (A->kind == 2) {

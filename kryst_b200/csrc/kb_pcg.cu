@@ -27,8 +27,9 @@ struct PcgInitFin {   // pcg.rs:132-146
         KbCtl* c = ctl;
         c->rz = s[0];
         c->res0 = sqrt(fabs(s[0]));
+        // first history entry: dp.sqrt() of the raw dot (pcg.rs:137-146: no abs, NaN when r.z < 0); the loop takes abs (:191)
         double nrm = (c->norm_type == KB_NORM_PRECONDITIONED || c->norm_type == KB_NORM_UNPRECONDITIONED) ? sqrt(s[1])
-                     : (c->norm_type == KB_NORM_NATURAL ? sqrt(fabs(s[0])) : 0.0);
+                     : (c->norm_type == KB_NORM_NATURAL ? sqrt(s[0]) : 0.0);
         c->res = nrm;
         if (c->hist_len < c->hist_cap) c->hist[c->hist_len] = nrm;
         c->hist_len += 1;

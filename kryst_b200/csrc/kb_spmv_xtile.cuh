@@ -31,9 +31,11 @@ template <int CFG> struct KbXtCfg;
 // with two fused dots: kb_spmv_bulk 0.175 ms; geometry 1 thread-per-row 0.103 ms, product phase 0.157 ms; geometry 0
 // 0.128 / 0.132 ms; 3 stages of 2048 entries 0.150 ms; one CTA per SM with 5 stages 0.19-0.20 ms (the consumers, not the
 // bytes in flight, are the limiter).  Geometry 1 is tried first, geometry 0 (more room for x) when a chunk does not fit.
-template <> struct KbXtCfg<0> { static constexpr int CAP = 3072, XCAP = 2048, STAGES = 2, MAXROWS = 512; };
-template <> struct KbXtCfg<1> { static constexpr int CAP = 3584, XCAP = 1280, STAGES = 2, MAXROWS = 256; };
-#define KB_XT_NCFG 2
+template <> struct KbXtCfg<0> { static constexpr int CAP = 3072, XCAP = 2048, STAGES = 2, MAXROWS = 512, CTAS = 2; };
+template <> struct KbXtCfg<1> { static constexpr int CAP = 3584, XCAP = 1280, STAGES = 2, MAXROWS = 256, CTAS = 2; };
+// short rows (7-point): half a tile per chunk, three CTAs per SM
+template <> struct KbXtCfg<2> { static constexpr int CAP = 1792, XCAP = 1296, STAGES = 2, MAXROWS = 256, CTAS = 3; };
+#define KB_XT_NCFG 3
 
 template <class C>
 struct KbXtStage {
@@ -219,7 +221,7 @@ __device__ __forceinline__ void kb_xt_consume(const KbSpmvArgs& a, KbXtSmem<C>& 
 }
 
 template <class Epi, bool RESID, bool PROD, int CFG>
-__global__ void __launch_bounds__(KB_BULK_THREADS, 2) kb_spmv_xtile(KbSpmvArgs a, KbXtTable tb, Epi epi) {
+__global__ void __launch_bounds__(KB_BULK_THREADS, KbXtCfg<CFG>::CTAS) kb_spmv_xtile(KbSpmvArgs a, KbXtTable tb, Epi epi) {
     using C = KbXtCfg<CFG>;
     kb_pdl_wait();
     kb_pdl_launch_dependents();

@@ -506,7 +506,9 @@ int ko_pcg(const ko_csr* A, const ko_pc* pc, const double* b, double* x, double 
         default: return 0.0;
         }
     };
-    push(NORM());
+    // first push: pcg.rs:137-146 takes dp.sqrt() of the raw dot (no abs: NaN when r.z < 0 under CgNormType::Natural);
+    // inside the loop (:191) the Natural norm is ip.dot(&r, &z).abs().sqrt()
+    push(norm_type == 2 ? std::sqrt(rz) : NORM());
     for (u64 i = 0; i < max_iters; ++i) {
         ko_spmv(A, p.data(), ap.data());
         double pAp = DOT(p, ap);

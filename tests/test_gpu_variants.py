@@ -134,6 +134,26 @@ def test_pcg_norm_types_bit_exact(ctx, norm_type):
     assert np.array_equal(np.array(s.residual_history), ho)
 
 
+def test_pcg_natural_norm_first_entry_is_nan_when_rz_negative(ctx):
+    """pcg.rs:137-146 pushes dp.sqrt() of the raw r.z before the loop (no abs): with a negative Jacobi diagonal the first
+    history entry is NaN, res0 stays |r.z|.sqrt() (:134).  max_iters = 0: the loop never runs, Ok is returned."""
+    import kryst_b200 as kb
+    from kryst_b200 import stencils
+    n, rp, ci, v = stencils.stencil("poisson2d", 12)
+    A = kb.DeviceCsr.from_csr(n, n, rp, ci, -v, ctx)            # negative definite: D^-1 < 0, r.z < 0
+    Ao = o.OCsr(n, n, rp, ci, -v)
+    b = o.spmv(Ao, np.ones(n))
+    for nt in (0, 1, 2, 3):
+        s = kb.PcgSolver(1e-8, 0).with_norm(nt)
+        x = np.zeros(n)
+        st = s.solve(A, kb.Jacobi().setup(A), b, x)
+        rc, xo, so, ho = o.pcg(Ao, o.OPc.jacobi(Ao), b, np.zeros(n), 1e-8, 0, norm_type=nt, hist_cap=4)
+        assert rc == 0 and (st.iterations, st.final_residual) == (0, so.final_residual)
+        h = np.array(s.residual_history)
+        assert h.shape == ho.shape == (1,) and np.array_equal(h, ho, equal_nan=True)
+        assert np.isnan(h[0]) == (nt == 2)
+
+
 def test_pcg_max_iters_reports_converged_and_history_capacity(ctx):
     import kryst_b200 as kb
     from kryst_b200 import stencils

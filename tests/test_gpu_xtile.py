@@ -34,7 +34,7 @@ def _banded(n, m, seed, maxlen=12, last_col=True):
     return np.array(rp, dtype=np.uint64), np.array(ci, dtype=np.uint64), np.array(v)
 
 
-@pytest.mark.parametrize("cfg", [0, 1])
+@pytest.mark.parametrize("cfg", [0, 1, 2])
 @pytest.mark.parametrize("kind,N", [("varcoef27", 14), ("varcoef27", 31), ("poisson3d", 17), ("convdiff3d", 24), ("poisson2d", 33),
                                     ("convdiff2d", 130)])
 def test_xtile_spmv_stencils_bit_exact(ctx, kind, N, cfg, monkeypatch):
@@ -49,7 +49,7 @@ def test_xtile_spmv_stencils_bit_exact(ctx, kind, N, cfg, monkeypatch):
         assert np.array_equal(y, o.spmv(Ao, x))
 
 
-@pytest.mark.parametrize("cfg", [0, 1])
+@pytest.mark.parametrize("cfg", [0, 1, 2])
 @pytest.mark.parametrize("n,m", [(1, 1), (5, 5), (513, 513), (700, 707), (1500, 1501), (4099, 4099)])
 def test_xtile_ragged_odd_rectangular(ctx, n, m, cfg, monkeypatch):
     import kryst_b200 as kb
@@ -151,7 +151,7 @@ def test_xtile_unaligned_device_operand_falls_back(ctx, monkeypatch):
     assert np.array_equal(y.cpu().numpy(), o.spmv(Ao, xh))
 
 
-@pytest.mark.parametrize("cfg", [0, 1])
+@pytest.mark.parametrize("cfg", [0, 1, 2])
 def test_xtile_pcg_jacobi_bit_exact(ctx, cfg, monkeypatch):
     import kryst_b200 as kb
     _env(monkeypatch, cfg)
@@ -165,7 +165,7 @@ def test_xtile_pcg_jacobi_bit_exact(ctx, cfg, monkeypatch):
     assert st.final_residual == so.final_residual and np.array_equal(x, xo)
 
 
-@pytest.mark.parametrize("cfg", [0, 1])
+@pytest.mark.parametrize("cfg", [0, 1, 2])
 @pytest.mark.parametrize("kind,N", [("varcoef27", 20), ("convdiff3d", 16)])
 def test_xtile_bicgstab_jacobi_bit_exact(ctx, kind, N, cfg, monkeypatch):
     import kryst_b200 as kb
@@ -180,7 +180,7 @@ def test_xtile_bicgstab_jacobi_bit_exact(ctx, kind, N, cfg, monkeypatch):
     assert st.final_residual == so.final_residual and np.array_equal(x, xo)
 
 
-@pytest.mark.parametrize("cfg", [0, 1])
+@pytest.mark.parametrize("cfg", [0, 1, 2])
 def test_xtile_matches_bulk_inside_gmres_ilu0(ctx, cfg, monkeypatch):
     """GMRES(30)+ILU(0): the staged-x SpMV must reproduce the default path bit for bit (the default path is pinned to the
     oracle in test_gpu_ilu_gmres.py)."""

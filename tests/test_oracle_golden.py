@@ -167,6 +167,22 @@ def test_pcg_indefinite_preconditioner():
     assert rc in (3, 4)
 
 
+def test_pcg_natural_norm_first_history_entry_has_no_abs():
+    """pcg.rs:137-146: the entry pushed before the loop is dp.sqrt() of the raw r.z (NaN when the preconditioner makes
+    it negative); inside the loop (:191) CgNormType::Natural is |r.z|.sqrt()."""
+    A = o.OCsr.from_dense(np.diag([2.0, 3.0, 5.0]))
+    neg = o.OPc.jacobi(o.OCsr.from_dense(np.diag([-1.0, -1.0, -1.0])))
+    rc, x, st, h = o.pcg(A, neg, [1, 2, 3], np.zeros(3), 1e-12, 0, norm_type=2, hist_cap=4)
+    assert rc == 0 and st.iterations == 0 and len(h) == 1 and np.isnan(h[0])
+    assert st.final_residual == np.sqrt(14.0)                    # res0 = |r.z|.sqrt() (pcg.rs:134)
+    for nt, want in ((0, np.sqrt(14.0)), (1, np.sqrt(14.0)), (3, 0.0)):
+        rc, x, st, h = o.pcg(A, neg, [1, 2, 3], np.zeros(3), 1e-12, 0, norm_type=nt, hist_cap=4)
+        assert h[0] == want
+    pos = o.OPc.jacobi(A)
+    rc, x, st, h = o.pcg(A, pos, [1, 2, 3], np.zeros(3), 1e-12, 5, norm_type=2, hist_cap=8)
+    assert rc == 0 and np.all(np.isfinite(h)) and abs(h[0] - np.sqrt(0.5 + 4.0 / 3.0 + 9.0 / 5.0)) < 1e-15
+
+
 # ---- (2) independent numpy transliteration ------------------------------------------------------------
 def _dense(name):
     import importlib.util

@@ -10,7 +10,7 @@ import pytest
 from kryst_b200 import stencils
 
 KB_TILE, KMAX, GAP = 512, 16, 4
-CFGS = {0: dict(cap=3072, xcap=2048, maxrows=512), 1: dict(cap=3584, xcap=1280, maxrows=256)}
+CFGS = {0: dict(cap=3072, xcap=2048, maxrows=512), 1: dict(cap=3584, xcap=1280, maxrows=256), 2: dict(cap=1792, xcap=1296, maxrows=256)}
 
 
 def chunk_build(rp, n, cap, maxrows):
@@ -104,7 +104,7 @@ def model(n, ncols, rp, ci, cfg):
     return len(chunk_row) - 1
 
 
-@pytest.mark.parametrize("cfg", [0, 1])
+@pytest.mark.parametrize("cfg", [0, 1, 2])
 @pytest.mark.parametrize("kind,N", [("varcoef27", 9), ("varcoef27", 24), ("poisson3d", 17), ("convdiff3d", 12), ("poisson2d", 33), ("convdiff2d", 70)])
 def test_stencils_fit_and_cover(cfg, kind, N):
     n, rp, ci, v = stencils.stencil(kind, N)
@@ -130,7 +130,7 @@ def test_27pt_128_chunk_geometry(cfg):
     assert len(lo) == (9 if cfg == 0 else 3) and tl == -1 and sum(ln) <= g["xcap"]
 
 
-@pytest.mark.parametrize("cfg", [0, 1])
+@pytest.mark.parametrize("cfg", [0, 1, 2])
 @pytest.mark.parametrize("n,m", [(1, 1), (5, 5), (513, 513), (700, 707), (1500, 1501)])
 def test_ragged_and_odd(cfg, n, m):
     rng = np.random.default_rng(n)
