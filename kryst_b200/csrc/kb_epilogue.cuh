@@ -95,8 +95,9 @@ static int kb_finish_dist(kb_ctx_s* c, Fin fin, KbCtl* ctl, double* slots, int n
 template <class Epi, bool RESID, int CFG>
 static int kb_launch_spmv_xtile(kb_csr_s* A, const KbSpmvArgs& a, Epi epi, int count, bool pdl) {
     kb_ctx_s* c = A->ctx;
-    using S = KbXtSmem<KbXtCfg<CFG>>;
-    static_assert(sizeof(S) <= (KbXtCfg<CFG>::CTAS == 2 ? 112 : 74) * 1024, "CTAs per SM");
+    constexpr int ND = (Epi::WDOT ? 1 : 0) + (Epi::YDOT ? 1 : 0) > 0 ? (Epi::WDOT ? 1 : 0) + (Epi::YDOT ? 1 : 0) : 1;
+    using S = KbXtSmem<KbXtCfg<CFG>, ND>;
+    static_assert(sizeof(S) <= KB_XT_SMEM_LIMIT(KbXtCfg<CFG>::CTAS), "CTAs per SM");
     auto kfn = A->xt_prod ? kb_spmv_xtile<Epi, RESID, true, CFG> : kb_spmv_xtile<Epi, RESID, false, CFG>;
     if (!c->configured.count((const void*)kfn)) {
         KB_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(S)));

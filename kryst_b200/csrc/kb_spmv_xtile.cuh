@@ -33,9 +33,13 @@ template <int CFG> struct KbXtCfg;
 // bytes in flight, are the limiter).  Geometry 1 is tried first, geometry 0 (more room for x) when a chunk does not fit.
 template <> struct KbXtCfg<0> { static constexpr int CAP = 3072, XCAP = 2048, STAGES = 2, MAXROWS = 512, CTAS = 2; };
 template <> struct KbXtCfg<1> { static constexpr int CAP = 3584, XCAP = 1280, STAGES = 2, MAXROWS = 256, CTAS = 2; };
-// short rows (7-point): half a tile per chunk, three CTAs per SM
+// short rows (7-point), opt-in (KB_SPMV_XTILE=1 KB_XT_CFG=2): half a tile per chunk, three CTAs per SM.  Measured on C4 (256^3):
+// 0.311 ms per SpMV against 0.301 ms for kb_spmv_bulk (a whole tile per chunk with a 2056-entry x window, two CTAs per SM:
+// 0.344 ms; 256-row chunks in geometry 0: 0.384 ms) - staging x costs more shared-memory fill than the L1-served gather
+// of seven entries per row saves, so short rows keep kb_spmv_bulk.
 template <> struct KbXtCfg<2> { static constexpr int CAP = 1792, XCAP = 1296, STAGES = 2, MAXROWS = 256, CTAS = 3; };
 #define KB_XT_NCFG 3
+#define KB_XT_SMEM_LIMIT(ctas) ((233472 / (ctas)) - 1024)     // 228 KB per SM, 1 KB reserved per CTA
 
 template <class C>
 struct KbXtStage {
@@ -45,10 +49,10 @@ struct KbXtStage {
     int rp[C::MAXROWS + 8];
     int hdr[8];          // written by the producer: {ra, rb, b0, r_al, tile, last_chunk_of_tile, window, -}
 };
-template <class C>
+template <class C, int ND>
 struct KbXtSmem {
     KbXtStage<C> st[C::STAGES];
-    double d[2][KB_TILE];
+    double d[ND][KB_TILE];       // dot terms of the current tile (ND = fused dots, at least 1: the epilogue's scratch)
     double red[2 * 8];
     unsigned long long full[C::STAGES];
     unsigned long long empty[C::STAGES];
@@ -78,8 +82,8 @@ __device__ __forceinline__ void kb_bulk_g2s_plain(void* dst, const void* src, un
 }
 
 // producer: the whole warp 8.  Lane 0 owns the ring (waits, header, expect_tx, matrix copies); lane k copies x interval k.
-template <class C>
-__device__ __forceinline__ void kb_xt_produce(const KbSpmvArgs& a, const KbXtTable& tb, KbXtSmem<C>& S, unsigned long long pol) {
+template <class C, class SM>
+__device__ __forceinline__ void kb_xt_produce(const KbSpmvArgs& a, const KbXtTable& tb, SM& S, unsigned long long pol) {
     const int lane = threadIdx.x & 31;
     const int ntl = a.ntiles_launch;
     int it = 0;
@@ -126,8 +130,8 @@ __device__ __forceinline__ void kb_xt_produce(const KbSpmvArgs& a, const KbXtTab
     }
 }
 
-template <class C, bool WD, bool YD, bool RESID, bool PROD>
-__device__ __forceinline__ void kb_xt_consume(const KbSpmvArgs& a, KbXtSmem<C>& S) {
+template <class C, bool WD, bool YD, bool RESID, bool PROD, class SM>
+__device__ __forceinline__ void kb_xt_consume(const KbSpmvArgs& a, SM& S) {
     constexpr int NDOT = (WD ? 1 : 0) + (YD ? 1 : 0);
     constexpr int ND = NDOT > 0 ? NDOT : 1;
     constexpr int YS = WD ? 1 : 0;                      // slot of <y,y>
@@ -230,7 +234,8 @@ __global__ void __launch_bounds__(KB_BULK_THREADS, KbXtCfg<CFG>::CTAS) kb_spmv_x
     constexpr int NDOT = (WD ? 1 : 0) + (YD ? 1 : 0);
     constexpr int ND = NDOT > 0 ? NDOT : 1;
     extern __shared__ __align__(128) unsigned char kb_smem_raw[];
-    KbXtSmem<C>& S = *reinterpret_cast<KbXtSmem<C>*>(kb_smem_raw);
+    using SM = KbXtSmem<C, ND>;
+    SM& S = *reinterpret_cast<SM*>(kb_smem_raw);
     const int tid = threadIdx.x;
     if (tid == 0) {
 #pragma unroll
@@ -239,10 +244,10 @@ __global__ void __launch_bounds__(KB_BULK_THREADS, KbXtCfg<CFG>::CTAS) kb_spmv_x
     }
     __syncthreads();
     if (tid >= KB_THREADS) {
-        kb_xt_produce<C>(a, tb, S, kb_policy_evict_first());
+        kb_xt_produce<C, SM>(a, tb, S, kb_policy_evict_first());
         return;
     }
-    kb_xt_consume<C, WD, YD, RESID, PROD>(a, S);
+    kb_xt_consume<C, WD, YD, RESID, PROD, SM>(a, S);
     if constexpr (NDOT > 0) {
         if (a.finalize) {
             if (tid == 0) {
