@@ -550,7 +550,7 @@ static int pcg_resident(kb_csr_s* A, const kb_pc_s* pc, KbPcgWs* w, bool* ran) {
         c->configured.insert((const void*)kfn);
     }
     int occ = 0;
-    KB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kfn, KB_RES_THREADS, smem));
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kfn, KB_RES_THREADS, smem) != cudaSuccess) { (void)cudaGetLastError(); return KB_OK; }
     if (occ < 1) return KB_OK;
     const size_t npk = (size_t)A->n + 3 * (size_t)A->ntiles;
     if (!w->res_pk) {
@@ -569,7 +569,11 @@ static int pcg_resident(kb_csr_s* A, const kb_pc_s* pc, KbPcgWs* w, bool* ran) {
     void* args[] = {&m};
     {
         KbLaunch Lc(c, KB_K_SPMV);
-        KB_CUDA(cudaLaunchCooperativeKernel((const void*)kfn, dim3(G), dim3(KB_RES_THREADS), args, smem, c->stream));
+        // a grid that cannot be co-resident right now (SMs taken by another context) is not an error: the CUDA-graph path runs
+        if (cudaLaunchCooperativeKernel((const void*)kfn, dim3(G), dim3(KB_RES_THREADS), args, smem, c->stream) != cudaSuccess) {
+            (void)cudaGetLastError();
+            return KB_OK;
+        }
     }
     unsigned verdict = 0;
     if (cudaMemcpyAsync(&verdict, w->res_bar + 2, sizeof(unsigned), cudaMemcpyDeviceToHost, c->stream) != cudaSuccess ||
