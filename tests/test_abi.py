@@ -90,3 +90,14 @@ def test_header_is_plain_c(tmp_path):
     src = tmp_path / "abi.c"
     src.write_text('#include "kryst_b200.h"\nint main(void) { kb_stats s; kb_profile p; (void)s; (void)p; return KB_OK; }\n')
     subprocess.check_call(["gcc", "-std=c99", "-pedantic", "-Wall", "-Werror", "-I", os.path.join(root, "include"), "-fsyntax-only", str(src)])
+
+
+def test_integration_md_rust_block_declares_every_header_symbol():
+    """INTEGRATION.md section 2 is the binding a kryst maintainer would paste: it must not drift from the header."""
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    header = open(os.path.join(root, "include", "kryst_b200.h")).read()
+    declared = set(re.findall(r"\b(kb_[a-z0-9_]+)\s*\(", header))
+    rust = set(re.findall(r"pub fn (kb_[a-z0-9_]+)", open(os.path.join(root, "INTEGRATION.md")).read()))
+    assert declared - rust == set(), sorted(declared - rust)
+    assert rust - declared == set(), sorted(rust - declared)
