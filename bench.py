@@ -439,7 +439,7 @@ def main():
         return solver_obj.solve(A, pc, b_dev, x_dev).iterations
 
     def step_host():
-        x_np[:] = 0.0
+        x_host.zero_()          # x0 = 0 in the pinned host buffer (x_np is its numpy view; numpy's own fill is 5x slower: one thread)
         return solver_obj.solve(A, pc, b_np, x_np).iterations
 
     # warm-up (>= 3), both paths
