@@ -665,7 +665,7 @@ extern "C" int kb_pcg_solve(kb_csr A, kb_pc pc, const double* b, double* x, doub
         // memory and registers (KB_PCG_RESIDENT=0 keeps the CUDA-graph path).
         const int res_env = getenv("KB_PCG_RESIDENT") ? atoi(getenv("KB_PCG_RESIDENT")) : KB_PCG_RESIDENT_DEFAULT;
         bool resident = false;
-        if (res_env != 0 && !mega && !single_red && !dist && jacobi_like && !mon.fn && max_iters > 0 && !(flags & KB_FLAG_NO_GRAPH) && (st = pcg_resident(A, pc, w, &resident)) != KB_OK) break;
+        if (res_env != 0 && !mega && !single_red && !dist && jacobi_like && !mon.fn && max_iters > 0 && max_iters < (1ull << 30) /* packet tags are 3k+phase in 32 bits */ && !(flags & KB_FLAG_NO_GRAPH) && (st = pcg_resident(A, pc, w, &resident)) != KB_OK) break;
         if (resident) {
         } else if (mega) {
             if ((st = pcg_persistent(A, pc, w)) != KB_OK) break;
