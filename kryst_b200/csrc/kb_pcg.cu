@@ -536,7 +536,8 @@ static int pcg_resident(kb_csr_s* A, const kb_pc_s* pc, KbPcgWs* w, bool* ran) {
     kb_ctx_s* c = A->ctx;
     const int L = (int)A->max_row_len;
     if (L < 1 || L > KB_RES_MAXLEN || A->n != A->ncols_local || A->n == 0) return KB_OK;
-    const int G = std::min(c->sm_count, A->ntiles);
+    int G = std::min(c->sm_count, A->ntiles);
+    if (getenv("KB_RES_GRID")) G = std::max(1, std::min(G, atoi(getenv("KB_RES_GRID"))));      // tuning: fewer, evenly loaded CTAs
     if ((A->ntiles + G - 1) / G > KB_RES_TEAMS || A->ntiles > 3 * KB_THREADS) return KB_OK;
     const int T = (A->ntiles + G - 1) / G;
     const size_t smem_max = 226 * 1024;                            // 227 KB per CTA minus the kernel's static shared memory
