@@ -250,7 +250,7 @@ static int build_chunk_table(kb_csr_s* A) {
 // x-staging tables of kb_spmv_xtile (kb_spmv_xtile.cuh): a second chunk table, the x intervals of every chunk and the
 // chunk-local 16-bit column ids.  All or nothing: if one chunk does not fit, the operator keeps kb_spmv_bulk.
 // KB_SPMV_XTILE = 0 never, 1 whenever the chunks fit, 2 (default) only for long rows (the product-phase operators,
-// where the gather is the limiter); KB_XT_CFG = 0 | 1 forces one stage geometry (default: 1, then 0).
+// where the gather is the limiter); KB_XT_CFG = 0 | 1 | 2 forces one stage geometry (default: 1, then 0; 2 is the short-row geometry).
 static void free_xt_table(kb_csr_s* A) {
     A->xt = 0; A->xt_nchunks = 0;
     KB_FREE(A->xt_tile_chunk); KB_FREE(A->xt_chunk_row); KB_FREE(A->xt_chunk_nz);
